@@ -1,0 +1,146 @@
+/*
+ * rcf_loss.h -- C ABI of librcf_loss.so: the RCF relaxed-common-fate motion loss, forward and
+ * backward, as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (TonyLianLong/RCF-UnsupVideoSeg) has no FFI on this path: the whole loss is the
+ * Python body of models/flow_aggregation_head_with_residual.py:33-399 executed op by op through
+ * ATen.  This header is therefore NEW surface; every entry point names the reference lines whose
+ * arithmetic it replaces.  The Python drop-in (rcf_unsupvideoseg_b200/head.py) binds it with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers to fp32 unless said
+ *     otherwise; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no allocation, no host synchronisation, no default-stream use inside rcf_forward/backward:
+ *     the caller supplies `ctx` (state kept from forward to backward) and `ws` (scratch) sized by
+ *     rcf_query_sizes();
+ *   - return value: 0 ok, <0 invalid argument (RCF_ERR_*), >0 a cudaError_t.  Nothing throws or
+ *     exits across the boundary (unlike tools/torchCRF, permutohedral_gpu.cu:44-53).
+ *
+ * Tensor layouts (identical to the reference's, NCHW fp32):
+ *   mask  [B, K, H, W]   one frame's soft masks; batch stride free (views masks[:, i] of
+ *                        [B,2,K,H,W] are taken as they are, reference :331-332), inner [K,H,W] dense
+ *   flow  [B, 2, H, W]   RAFT flow of that frame (un-clamped; the clamp of :155-156 is fused)
+ *   resid [B, 2K, H, W]  residual map, channel c*K+k  (unflatten(1,(2,K)), reference :274-275)
+ *   feat  [B, Cf, H, W]  output of flow_feat_before_agg (reference :246); only when Cf > 0
+ *   theta [B, 2, K]      per-segment constant flow (output of flow_feat_after_agg, :258) when supplied
+ * A "direction" is one (mask, flow, resid[, feat]) quadruple: forward = (masks[:,0], gt_fw_flows[:,0],
+ * all_pred_residual_fw), backward = (masks[:,1], gt_bw_flows[:,0], all_pred_residual_bw)
+ * (reference :331-347).  One call processes ndir (1 or 2) directions.
+ */
+#ifndef RCF_LOSS_H_
+#define RCF_LOSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RCF_API __attribute__((visibility("default")))
+#else
+#define RCF_API
+#endif
+
+#define RCF_ABI_VERSION 1
+#define RCF_MAX_K 8          /* mask_layer supported by the compiled kernels */
+#define RCF_MAX_CF 256       /* num_flow_feat_channels supported by the segment kernels */
+
+#define RCF_OK 0
+#define RCF_ERR_NULL (-1)        /* required pointer missing */
+#define RCF_ERR_SHAPE (-2)       /* B/K/H/W/Cf/D/ndir out of range */
+#define RCF_ERR_UNSUPPORTED (-3) /* valid for the reference, not compiled here (e.g. K > RCF_MAX_K) */
+#define RCF_ERR_ALIGN (-4)       /* pointer not 4-byte aligned / stride inconsistent */
+#define RCF_ERR_MODE (-5)        /* inconsistent flags (e.g. theta_mode 1 without feat / weights) */
+
+/* Problem descriptor (host memory, read during the call only). */
+typedef struct RcfDesc {
+    int32_t B;                 /* samples in this call (per rank)                                   */
+    int32_t K;                 /* mask_layer, 1..RCF_MAX_K                         (ref :53,:75)    */
+    int32_t H, W;              /* mask_size                                        (ref :60,:111)   */
+    int32_t Cf;                /* num_flow_feat_channels when pooling feat, else 0 (ref :56)        */
+    int32_t D;                 /* 0 free_residual | 2 free_residual_with_affine | 5 ..._quadratic
+                                                                                   (ref :123-127)   */
+    int32_t ndir;              /* 1 or 2                                                            */
+    int32_t theta_mode;        /* 0: theta supplied; 1: pool feat + segment MLP    (ref :246-258)   */
+    int32_t robust;            /* outlier_robust_loss                              (ref :359-368)   */
+    int32_t unbounded_residual;/* residual_adjustment_scale == -1 && free_residual (ref :282-286)   */
+    float eps, q;              /* robust loss (|d|+eps)^q                          (ref :58-59)     */
+    float resid_scale;         /* residual_adjustment_scale                        (ref :61)        */
+    float pred_div;            /* pred_div_coeff                                   (ref :73)        */
+    float clamp_t;             /* clamp_flow_t; < 0 means "no clamp"               (ref :155-156)   */
+    float inv_n;               /* 1 / (number of elements in the mean); 0 => 1/(B*2*H*W) (ref :361) */
+    int64_t mask_bstride[2];   /* batch strides in ELEMENTS, per direction                          */
+    int64_t flow_bstride[2];
+    int64_t resid_bstride[2];
+    int64_t feat_bstride[2];
+    int64_t dmask_bstride[2];  /* strides of the gradient buffers (rcf_backward)                    */
+    int64_t dresid_bstride[2];
+    int64_t dfeat_bstride[2];
+    /* visualisation flows (reference :18-30, :370-395): out[b*vis_bstride + dir*vis_dstride + c*H*W + p]
+       = value * vis_scale[c].  The reference uses [B,4,H,W] with vis_scale = {2/H, 2/W}.            */
+    int64_t vis_bstride;
+    int64_t vis_dstride;
+    float vis_scale[2];
+} RcfDesc;
+
+typedef struct RcfInputs {
+    const float* mask[2];
+    const float* flow[2];
+    const float* resid[2];
+    const float* feat[2];      /* NULL when Cf == 0 */
+    const float* theta[2];     /* theta_mode 0 */
+    const float* w1;           /* flow_feat_after_agg.0.weight [Cf,Cf]   theta_mode 1 (ref :96) */
+    const float* b1;           /* flow_feat_after_agg.0.bias   [Cf]                             */
+    const float* w2;           /* flow_feat_after_agg.2.weight [2,Cf]                 (ref :99) */
+    const float* b2;           /* flow_feat_after_agg.2.bias   [2]                              */
+} RcfInputs;
+
+/* Optional per-pixel outputs of the forward pass; any pointer may be NULL. */
+typedef struct RcfVisOut {
+    float* gt;     /* prepared (clamped) flow             -> flows['gt_flow']      */
+    float* pred;   /* reconstructed flow                  -> flows['pred_flow']    */
+    float* agg;    /* piece-wise constant part            -> flows['agg_flow']     */
+    float* res;    /* residual part                       -> flows['residual_adj'] */
+    float* aff;    /* affine / quadratic part (D > 0)     -> flows['affine_flow']  */
+} RcfVisOut;
+
+/* Gradient outputs; any pointer may be NULL (that gradient is skipped). */
+typedef struct RcfGrads {
+    float* dmask[2];   /* [B,K,H,W]  with dmask_bstride  */
+    float* dresid[2];  /* [B,2K,H,W] with dresid_bstride */
+    float* dfeat[2];   /* [B,Cf,H,W] with dfeat_bstride  (theta_mode 1) */
+    float* dtheta[2];  /* [B,2,K] dense                  (theta_mode 0) */
+    float* dw1;        /* [Cf,Cf]  summed over directions (theta_mode 1) */
+    float* db1;        /* [Cf] */
+    float* dw2;        /* [2,Cf] */
+    float* db2;        /* [2] */
+} RcfGrads;
+
+/* ABI version of the loaded library (== RCF_ABI_VERSION of the header it was built from). */
+RCF_API int rcf_abi_version(void);
+
+/* Human-readable text for a return code of this library (RCF_ERR_* or a cudaError_t). */
+RCF_API const char* rcf_error_string(int code);
+
+/* Bytes of `ctx` (forward -> backward state: per-segment statistics, replaces autograd's saved
+ * per-pixel intermediates of reference :242-304) and of `ws` (scratch partial sums). */
+RCF_API int rcf_query_sizes(const RcfDesc* desc, size_t* ctx_bytes, size_t* ws_bytes);
+
+/* Forward: replaces norm_and_clamp_flow's clamp (:155-156), aggregate_flow_with_residual (:235-310,
+ * incl. get_demean_affine_flow :164-233) and the loss terms (:359-368) for ndir directions.
+ * loss[dir] (device, fp32) receives flow_loss['seg_fw'] / ['seg_bw'].  `vis` may be NULL. */
+RCF_API int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss, void* ctx, void* ws,
+                const RcfVisOut* vis, void* stream);
+
+/* Backward of sum_dir grad_loss[dir] * loss[dir] (grad_loss: device, fp32, [ndir]); replaces the
+ * autograd replay of every op of :242-368.  `ctx` must come from rcf_forward on the same inputs. */
+RCF_API int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const float* grad_loss, const void* ctx,
+                 void* ws, const RcfGrads* grads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCF_LOSS_H_ */

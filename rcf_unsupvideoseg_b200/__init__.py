@@ -1,0 +1,13 @@
+"""B200-native (sm_100a) RCF relaxed-common-fate motion loss.
+
+Public surface (mirrors /root/reference/models/flow_aggregation_head_with_residual.py):
+    FlowAggregationHeadWithResidual, get_norm_flow, Objectview
+plus the functional layer over the C ABI (include/rcf_loss.h):
+    LossSpec, rcf_motion_loss, RcfMotionLossFn, load_library
+"""
+from ._lib import LIB_PATH, RcfLibraryError, load_library  # noqa: F401
+from .function import LossSpec, RcfMotionLossFn, rcf_motion_loss  # noqa: F401
+from .head import FlowAggregationHeadWithResidual, Objectview, get_norm_flow  # noqa: F401
+
+__all__ = ["FlowAggregationHeadWithResidual", "get_norm_flow", "Objectview", "LossSpec", "rcf_motion_loss",
+           "RcfMotionLossFn", "load_library", "RcfLibraryError", "LIB_PATH"]

@@ -1,0 +1,107 @@
+"""ctypes binding of librcf_loss.so (include/rcf_loss.h).  No torch types cross this boundary.
+
+The library is the product: if it cannot be loaded this module raises -- there is no CPU or
+PyTorch fallback for the loss.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "librcf_loss.so")
+
+RCF_ABI_VERSION = 1
+RCF_MAX_K = 8
+RCF_MAX_CF = 256
+
+_f32p = C.POINTER(C.c_float)
+_i64x2 = C.c_int64 * 2
+_ptr2 = C.c_void_p * 2
+
+
+class RcfDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("Cf", C.c_int32), ("D", C.c_int32), ("ndir", C.c_int32), ("theta_mode", C.c_int32),
+        ("robust", C.c_int32), ("unbounded_residual", C.c_int32),
+        ("eps", C.c_float), ("q", C.c_float), ("resid_scale", C.c_float), ("pred_div", C.c_float),
+        ("clamp_t", C.c_float), ("inv_n", C.c_float),
+        ("mask_bstride", _i64x2), ("flow_bstride", _i64x2), ("resid_bstride", _i64x2), ("feat_bstride", _i64x2),
+        ("dmask_bstride", _i64x2), ("dresid_bstride", _i64x2), ("dfeat_bstride", _i64x2),
+        ("vis_bstride", C.c_int64), ("vis_dstride", C.c_int64), ("vis_scale", C.c_float * 2),
+    ]
+
+
+class RcfInputs(C.Structure):
+    _fields_ = [
+        ("mask", _ptr2), ("flow", _ptr2), ("resid", _ptr2), ("feat", _ptr2), ("theta", _ptr2),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+    ]
+
+
+class RcfVisOut(C.Structure):
+    _fields_ = [("gt", C.c_void_p), ("pred", C.c_void_p), ("agg", C.c_void_p), ("res", C.c_void_p),
+                ("aff", C.c_void_p)]
+
+
+class RcfGrads(C.Structure):
+    _fields_ = [
+        ("dmask", _ptr2), ("dresid", _ptr2), ("dfeat", _ptr2), ("dtheta", _ptr2),
+        ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
+    ]
+
+
+EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "rcf_forward", "rcf_backward")
+
+_lib = None
+_lock = threading.Lock()
+
+
+class RcfLibraryError(RuntimeError):
+    pass
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen librcf_loss.so; optionally build it with nvcc first.  Raises RcfLibraryError otherwise."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise RcfLibraryError(f"{LIB_PATH} not built; run `python -m rcf_unsupvideoseg_b200.build`")
+            from . import build as _build
+            try:
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise RcfLibraryError(f"cannot build {LIB_PATH}: {e}. The RCF loss has no CPU fallback.") from e
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as e:
+            raise RcfLibraryError(f"cannot load {LIB_PATH}: {e}. The RCF loss has no CPU fallback.") from e
+        lib.rcf_abi_version.restype = C.c_int
+        lib.rcf_abi_version.argtypes = []
+        lib.rcf_error_string.restype = C.c_char_p
+        lib.rcf_error_string.argtypes = [C.c_int]
+        lib.rcf_query_sizes.restype = C.c_int
+        lib.rcf_query_sizes.argtypes = [C.POINTER(RcfDesc), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        lib.rcf_forward.restype = C.c_int
+        lib.rcf_forward.argtypes = [C.POINTER(RcfDesc), C.POINTER(RcfInputs), C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(RcfVisOut), C.c_void_p]
+        lib.rcf_backward.restype = C.c_int
+        lib.rcf_backward.argtypes = [C.POINTER(RcfDesc), C.POINTER(RcfInputs), C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(RcfGrads), C.c_void_p]
+        if lib.rcf_abi_version() != RCF_ABI_VERSION:
+            raise RcfLibraryError(f"ABI mismatch: library {lib.rcf_abi_version()} vs binding {RCF_ABI_VERSION}")
+        _lib = lib
+    return _lib
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = load_library().rcf_error_string(code).decode()
+        raise RuntimeError(f"{what} failed with code {code}: {msg}")

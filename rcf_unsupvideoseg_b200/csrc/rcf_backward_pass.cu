@@ -1,0 +1,173 @@
+// rcf_backward_pass.cu -- the single streaming backward pass: recompute, then write dM and dR.
+//
+// Nothing per-pixel is saved from the forward (the reference's autograd keeps ~20 full-resolution
+// tensors alive between :242 and :368).  Per pixel this kernel re-evaluates tanh / pred / phi' and
+// emits (gs = -gbar/N):
+//   g_c      = gs * w_c
+//   dR_ck    = g_c * (s/div) * (1 - T_ck^2) * m_k                      (or g_c * m_k when unbounded)
+//   dM_k     = sum_c g_c (theta_ck + A_kc.v_k + s T_ck)
+//              + f_k^T B_k v_k + v_k^T C_k v_k + mubar_k.v_k + c0_k    (B, C, mubar, c0 pre-divided by S_k)
+//              [+ the pooled-feature term already stored in dM by k_pool_bwd]
+// HBM-bound: algorithmic bytes per pixel = (4K + 8 + 8K) read + (4K + 8K) written.
+#include "rcf_common.cuh"
+
+template <int K, int D, int PX>
+__global__ void __launch_bounds__(RCF_BLOCK) k_bwd(const RcfK a) {
+    constexpr int CF = rcf_cf(D);
+    constexpr int CB = rcf_cb(D);
+    constexpr int ITER = RCF_CHUNK_BWD / (RCF_BLOCK * PX);
+    constexpr int DD = D > 0 ? D : 1;
+    __shared__ float cf[K * CF];
+    __shared__ float cb[K * CB];
+
+    const int fd = blockIdx.y;
+    const int dir = fd / a.B;
+    const int b = fd - dir * a.B;
+    const int chunk = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int P = a.P;
+    const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
+    const float* __restrict__ flow = a.flow[dir] + (long long)b * a.flow_bs[dir];
+    const float* __restrict__ resid = a.resid[dir] + (long long)b * a.resid_bs[dir];
+    float* __restrict__ dmask = a.dmask[dir] ? a.dmask[dir] + (long long)b * a.dmask_bs[dir] : nullptr;
+    float* __restrict__ dresid = a.dresid[dir] ? a.dresid[dir] + (long long)b * a.dresid_bs[dir] : nullptr;
+
+    for (int i = tid; i < K * CF; i += RCF_BLOCK) cf[i] = a.coef[(size_t)fd * K * CF + i];
+    for (int i = tid; i < K * CB; i += RCF_BLOCK) cb[i] = a.coefb[(size_t)fd * K * CB + i];
+    __syncthreads();
+    const float gs = a.gscale[fd];
+
+    const int p0 = chunk * RCF_CHUNK_BWD;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int p = p0 + (it * RCF_BLOCK + tid) * PX;
+        if (p < P) {
+            float m[K][PX], r[2][K][PX], f[2][PX];
+#pragma unroll
+            for (int k = 0; k < K; ++k) Pack<PX>::ld(m[k], mask + (long long)k * P + p);
+            Pack<PX>::ld(f[0], flow + p);
+            Pack<PX>::ld(f[1], flow + P + p);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int k = 0; k < K; ++k) Pack<PX>::ld(r[c][k], resid + (long long)(c * K + k) * P + p);
+            float dm[K][PX];
+            if (a.add_dmask && dmask) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) Pack<PX>::ld(dm[k], dmask + (long long)k * P + p);
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) dm[k][j] = 0.0f;
+            }
+            float y[PX], x[PX];
+            if constexpr (D > 0) px_coords<PX>(p, a, y, x);
+
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                float u[DD];
+                if constexpr (D > 0) px_feats<D>(y[j], x[j], u);
+                float fc[2];
+                fc[0] = clamp_flow(f[0][j], a.clamp_t);
+                fc[1] = clamp_flow(f[1][j], a.clamp_t);
+                // q_ck = theta_ck + A_kc.v_k + s*T_ck ; r[c][k][j] is overwritten by T_ck
+                float qv[2][K];
+                float pred[2] = {0.0f, 0.0f};
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float* ck = cf + k * CF;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float t = a.unbounded ? r[c][k][j] : tanh_scaled(r[c][k][j], a.ex2_scale);
+                        r[c][k][j] = t;
+                        float qq = fmaf(a.scale, t, ck[c]);
+                        if constexpr (D > 0) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d) qq = fmaf(ck[2 + c * D + d], u[d] - ck[2 + 2 * D + d], qq);
+                        }
+                        qv[c][k] = qq;
+                        pred[c] = fmaf(m[k][j], qq, pred[c]);
+                    }
+                }
+                float g[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    float phi, w;
+                    loss_terms(fc[c] - pred[c], a, phi, w);
+                    g[c] = gs * w;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float mk = m[k][j];
+                    float acc = dm[k][j] + fmaf(g[0], qv[0][k], g[1] * qv[1][k]);
+                    const float* bk = cb + k * CB;
+                    if constexpr (D > 0) {
+                        // bk: muF[2], B[2][D], Csym[D(D+1)/2], mubar[D], c0
+                        const float* ck = cf + k * CF;
+                        const float ff0 = fc[0] - bk[0], ff1 = fc[1] - bk[1];
+                        float v[D];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) v[d] = u[d] - ck[2 + 2 * D + d];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            float lin = fmaf(ff0, bk[2 + d], fmaf(ff1, bk[2 + D + d], bk[2 + 2 * D + D * (D + 1) / 2 + d]));
+#pragma unroll
+                            for (int e = d; e < D; ++e) lin = fmaf(bk[2 + 2 * D + rcf_sym_idx(D, d, e)], v[e], lin);
+                            acc = fmaf(lin, v[d], acc);
+                        }
+                    }
+                    acc += bk[CB - 1];
+                    dm[k][j] = acc;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float t = r[c][k][j];
+                        r[c][k][j] = a.unbounded ? g[c] * mk : g[c] * a.dres_scale * fmaf(-t, t, 1.0f) * mk;
+                    }
+                }
+            }
+            if (dmask) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) Pack<PX>::st(dmask + (long long)k * P + p, dm[k]);
+            }
+            if (dresid) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) Pack<PX>::st(dresid + (long long)(c * K + k) * P + p, r[c][k]);
+            }
+        }
+    }
+}
+
+template <int K, int D>
+static cudaError_t launch_kd(const RcfK& a, bool vec, cudaStream_t s) {
+    dim3 grid(a.nchunkb, a.nfd), block(RCF_BLOCK);
+    if (vec) k_bwd<K, D, 4><<<grid, block, 0, s>>>(a);
+    else k_bwd<K, D, 1><<<grid, block, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int K>
+static cudaError_t launch_k(const RcfK& a, bool vec, cudaStream_t s) {
+    switch (a.D) {
+        case 0: return launch_kd<K, 0>(a, vec, s);
+        case 2: return launch_kd<K, 2>(a, vec, s);
+        case 5: return launch_kd<K, 5>(a, vec, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t rcf_launch_bwd(const RcfK& a, bool vec, cudaStream_t s) {
+    switch (a.K) {
+        case 1: return launch_k<1>(a, vec, s);
+        case 2: return launch_k<2>(a, vec, s);
+        case 3: return launch_k<3>(a, vec, s);
+        case 4: return launch_k<4>(a, vec, s);
+        case 5: return launch_k<5>(a, vec, s);
+        case 6: return launch_k<6>(a, vec, s);
+        case 7: return launch_k<7>(a, vec, s);
+        case 8: return launch_k<8>(a, vec, s);
+    }
+    return cudaErrorInvalidValue;
+}

@@ -1,0 +1,226 @@
+// rcf_common.cuh -- shared definitions of the sm_100a RCF motion-loss kernels.
+//
+// Math reference: SURVEY.md 8(a)-math; reference Python lines cited per kernel.
+// Notation: fd = frame-direction index = dir * B + b; P = H*W pixels; K segments; D coordinate
+// features (0 / 2 / 5); Cf pooled feature channels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rcf_loss.h"
+
+#define RCF_BLOCK 256
+#define RCF_WARPS (RCF_BLOCK / 32)
+
+// pixels handled by one CTA of each streaming kernel
+#define RCF_CHUNK_MOM 4096   // pass 1 (moments)
+#define RCF_CHUNK_LOSS 2048  // pass 2 (reconstruct + loss + gradient moments)
+#define RCF_CHUNK_BWD 1024   // backward (no reduction)
+
+#define RCF_HD __host__ __device__ __forceinline__
+
+// ---- sizes of the small per-segment records ------------------------------------------------
+// pass-1 statistics per (fd,k): [0] S, [1..2] sum m*F_c, [3..3+D) sum m*u_d,
+//   [3+D .. 3+3D) sum m*F_c*u_d (c*D+d), [3+3D ..) sum m*u_d*u_e packed d<=e
+RCF_HD constexpr int rcf_ns(int D) { return D == 0 ? 1 : 3 + 3 * D + D * (D + 1) / 2; }
+// pass-2 gradient moments per fd: [0] sum phi, [1 + c*K + k] sum w_c m_k,
+//   [1 + 2K + (k*2+c)*D + d] sum w_c m_k (u_d - mu_kd)
+RCF_HD constexpr int rcf_gm(int K, int D) { return 1 + 2 * K + 2 * K * D; }
+// forward coefficients per (fd,k) (fp32): theta[2], A[2][D], mu_u[D]
+RCF_HD constexpr int rcf_cf(int D) { return 2 + 3 * D; }
+// backward coefficients per (fd,k) (fp32), all pre-divided by S_k:
+//   muF[2], B[2][D], Csym[D(D+1)/2] (off-diagonals doubled), mubar_u[D], c0
+RCF_HD constexpr int rcf_cb(int D) { return 3 + 3 * D + D * (D + 1) / 2; }
+// fp64 per-segment state kept for backward: S, mu_u[D], mu_F[2], SFu[2D], Suu[D*D], Sinv[D*D], A[2D]
+RCF_HD constexpr int rcf_segd(int D) { return 3 + 5 * D + 2 * D * D; }
+RCF_HD constexpr int rcf_sym_idx(int D, int d, int e) { return d * D - d * (d - 1) / 2 + (e - d); }
+
+RCF_HD int rcf_pool_chunk(int K) { return K <= 4 ? 2048 : 1024; }
+
+// ---- memory plan ------------------------------------------------------------------------------
+struct RcfLayout {
+    int nfd, P, ns, gm, cf, cb, segd;
+    int nchunk1, nchunk2, nchunkb, nchunkp;
+    // ctx (bytes offsets)
+    size_t c_segd, c_coef, c_mlp, c_gm, c_bytes;
+    // ws
+    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_bytes;
+};
+
+static inline size_t rcf_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
+    RcfLayout L;
+    L.nfd = d.ndir * d.B;
+    L.P = d.H * d.W;
+    L.ns = rcf_ns(d.D);
+    L.gm = rcf_gm(d.K, d.D);
+    L.cf = rcf_cf(d.D);
+    L.cb = rcf_cb(d.D);
+    L.segd = rcf_segd(d.D);
+    L.nchunk1 = (L.P + RCF_CHUNK_MOM - 1) / RCF_CHUNK_MOM;
+    L.nchunk2 = (L.P + RCF_CHUNK_LOSS - 1) / RCF_CHUNK_LOSS;
+    L.nchunkb = (L.P + RCF_CHUNK_BWD - 1) / RCF_CHUNK_BWD;
+    const int pc = rcf_pool_chunk(d.K);
+    L.nchunkp = (L.P + pc - 1) / pc;
+    const size_t nseg = (size_t)L.nfd * d.K;
+    size_t o = 0;
+    L.c_segd = o; o = rcf_align256(o + nseg * L.segd * sizeof(double));
+    L.c_coef = o; o = rcf_align256(o + nseg * L.cf * sizeof(float));
+    L.c_mlp = o;  o = rcf_align256(o + nseg * 2 * (size_t)d.Cf * sizeof(double));
+    L.c_gm = o;   o = rcf_align256(o + (size_t)L.nfd * L.gm * sizeof(double));
+    L.c_bytes = o ? o : 256;
+    o = 0;
+    L.w_part1 = o;   o = rcf_align256(o + nseg * L.ns * L.nchunk1 * sizeof(float));
+    L.w_partp = o;   o = rcf_align256(o + nseg * d.Cf * L.nchunkp * sizeof(float));
+    L.w_part2 = o;   o = rcf_align256(o + (size_t)L.nfd * L.gm * L.nchunk2 * sizeof(float));
+    L.w_coefb = o;   o = rcf_align256(o + nseg * L.cb * sizeof(float));
+    L.w_gscale = o;  o = rcf_align256(o + (size_t)L.nfd * sizeof(float));
+    L.w_poolbar = o; o = rcf_align256(o + nseg * d.Cf * sizeof(float));
+    L.w_dh = o;      o = rcf_align256(o + nseg * d.Cf * sizeof(double));
+    L.w_thbar = o;   o = rcf_align256(o + nseg * 2 * sizeof(double));
+    L.w_bytes = o ? o : 256;
+    return L;
+}
+
+// ---- kernel argument block (passed by value) ---------------------------------------------------
+struct RcfK {
+    int B, K, H, W, P, Cf, D, ndir, nfd;
+    int robust, unbounded, theta_mode;
+    float eps, q;
+    float scale;        // residual_adjustment_scale (1 when unbounded)
+    float ex2_scale;    // 2*log2(e)/pred_div : tanh(r/div) = 1 - 2/(1+2^(r*ex2_scale))
+    float dres_scale;   // scale/pred_div (1 when unbounded)
+    float clamp_t;      // <0: none
+    float inv_n;
+    float cy, cx, sy, sx;  // coordinate centring / scaling (u = ((row-cy)*sy, (col-cx)*sx))
+    const float* mask[2];
+    const float* flow[2];
+    const float* resid[2];
+    const float* feat[2];
+    const float* theta[2];
+    long long mask_bs[2], flow_bs[2], resid_bs[2], feat_bs[2];
+    const float *w1, *b1, *w2, *b2;
+    // ctx
+    double* segd;
+    float* coef;
+    double* mlp;
+    double* gm;
+    // ws
+    float* part1;
+    float* partp;
+    float* part2;
+    float* coefb;
+    float* gscale;
+    float* poolbar;
+    double* dh;
+    double* thbar;
+    int nchunk1, nchunk2, nchunkb, nchunkp;
+    // forward outputs
+    float* loss;
+    float* vis_gt; float* vis_pred; float* vis_agg; float* vis_res; float* vis_aff;
+    long long vis_bs, vis_ds;
+    float vis_scale[2];
+    // backward
+    const float* grad_loss;
+    float* dmask[2]; float* dresid[2]; float* dfeat[2]; float* dtheta[2];
+    long long dmask_bs[2], dresid_bs[2], dfeat_bs[2];
+    float *dw1, *db1, *dw2, *db2;
+    int add_dmask;   // dmask already holds the pooled-feature term (written by k_pool_bwd)
+};
+
+#ifdef __CUDACC__
+// ---- device helpers ----------------------------------------------------------------------------
+template <int PX> struct Pack;
+template <> struct Pack<4> {
+    static __device__ __forceinline__ void ld(float (&v)[4], const float* p) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Pack<1> {
+    static __device__ __forceinline__ void ld(float (&v)[1], const float* p) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[1]) { *p = v[0]; }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// tanh(r/div) with absolute error ~3e-7 (2 MUFU + 3 FP32 ops); saturates cleanly to +-1.
+__device__ __forceinline__ float tanh_scaled(float r, float ex2_scale) {
+    const float e = fast_ex2(r * ex2_scale);
+    return fmaf(-2.0f, fast_rcp(1.0f + e), 1.0f);
+}
+__device__ __forceinline__ float clamp_flow(float f, float t) {
+    return t >= 0.0f ? fminf(fmaxf(f, -t), t) : f;
+}
+
+// coordinates of PX consecutive flat pixels starting at p
+template <int PX>
+__device__ __forceinline__ void px_coords(int p, const RcfK& a, float (&y)[PX], float (&x)[PX]) {
+    int row = p / a.W;
+    int col = p - row * a.W;
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+        y[j] = ((float)row - a.cy) * a.sy;
+        x[j] = ((float)col - a.cx) * a.sx;
+        if (++col == a.W) { col = 0; ++row; }
+    }
+}
+template <int D>
+__device__ __forceinline__ void px_feats(float y, float x, float (&u)[D > 0 ? D : 1]) {
+    if (D >= 2) { u[0] = y; u[1] = x; }
+    if (D == 5) { u[2] = y * y; u[3] = x * x; u[4] = y * x; }
+}
+
+// loss value and derivative weight of one residual d = F - pred (reference :359-368)
+__device__ __forceinline__ void loss_terms(float d, const RcfK& a, float& phi, float& w) {
+    const float ad = fabsf(d);
+    const float sg = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+    if (a.robust) {
+        const float t = ad + a.eps;
+        phi = fast_ex2(a.q * fast_lg2(t));
+        w = a.q * phi * fast_rcp(t) * sg;
+    } else {
+        phi = ad;
+        w = sg;
+    }
+}
+#endif  // __CUDACC__
+
+// launchers (one translation unit each)
+cudaError_t rcf_launch_moments(const RcfK& a, bool vec, cudaStream_t s);
+cudaError_t rcf_launch_pool(const RcfK& a, bool vec, cudaStream_t s);
+cudaError_t rcf_launch_segment_fwd(const RcfK& a, cudaStream_t s);
+cudaError_t rcf_launch_loss(const RcfK& a, bool vec, cudaStream_t s);
+cudaError_t rcf_launch_finalize(const RcfK& a, cudaStream_t s);
+cudaError_t rcf_launch_segment_bwd(const RcfK& a, cudaStream_t s);
+cudaError_t rcf_launch_pool_bwd(const RcfK& a, bool vec, cudaStream_t s);
+cudaError_t rcf_launch_bwd(const RcfK& a, bool vec, cudaStream_t s);

@@ -1,0 +1,118 @@
+// rcf_moments.cu -- pass 1: per-(frame-direction, segment) weighted moment sums.
+//
+// Replaces, in one coalesced read of the mask (and of the flow when an affine fit is on):
+//   * mask.sum over pixels                                   reference :242-243, :168
+//   * mu_F, mu_omega, sigma_F_omega, sigma_omega_omega sums   reference :173-209
+// (the reference materialises [B,K,HW,2,2] einsum temporaries; here only K*NS scalars per CTA leave
+// the SM).  Raw moments are taken in a centred, [-1,1]-scaled coordinate basis; the segment kernel
+// converts them to the de-meaned covariances in fp64.
+//
+// HBM-bound: algorithmic bytes per pixel = 4K (+8 with the affine fit).
+#include "rcf_common.cuh"
+
+template <int K, int D, int PX>
+__global__ void __launch_bounds__(RCF_BLOCK) k_moments(const RcfK a) {
+    constexpr int NS = rcf_ns(D);
+    constexpr int ITER = RCF_CHUNK_MOM / (RCF_BLOCK * PX);
+    constexpr int DD = D > 0 ? D : 1;
+    __shared__ float red[RCF_WARPS][K * NS];
+
+    const int fd = blockIdx.y;
+    const int dir = fd / a.B;
+    const int b = fd - dir * a.B;
+    const int chunk = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
+    const float* __restrict__ flow = a.flow[dir] + (long long)b * a.flow_bs[dir];
+    const int P = a.P;
+    const int p0 = chunk * RCF_CHUNK_MOM;
+
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float acc[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[s] = 0.0f;
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int p = p0 + (it * RCF_BLOCK + tid) * PX;
+            if (p < P) {
+                float m[PX];
+                Pack<PX>::ld(m, mask + (long long)k * P + p);
+                if constexpr (D == 0) {
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) acc[0] += m[j];
+                } else {
+                    float f0[PX], f1[PX], y[PX], x[PX];
+                    Pack<PX>::ld(f0, flow + p);
+                    Pack<PX>::ld(f1, flow + P + p);
+                    px_coords<PX>(p, a, y, x);
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) {
+                        float u[DD];
+                        px_feats<D>(y[j], x[j], u);
+                        const float mj = m[j];
+                        const float g0 = mj * clamp_flow(f0[j], a.clamp_t);
+                        const float g1 = mj * clamp_flow(f1[j], a.clamp_t);
+                        acc[0] += mj;
+                        acc[1] += g0;
+                        acc[2] += g1;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            const float mu = mj * u[d];
+                            acc[3 + d] += mu;
+                            acc[3 + D + d] = fmaf(g0, u[d], acc[3 + D + d]);
+                            acc[3 + 2 * D + d] = fmaf(g1, u[d], acc[3 + 2 * D + d]);
+#pragma unroll
+                            for (int e = d; e < D; ++e)
+                                acc[3 + 3 * D + rcf_sym_idx(D, d, e)] = fmaf(mu, u[e], acc[3 + 3 * D + rcf_sym_idx(D, d, e)]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const float v = warp_sum(acc[s]);
+            if (lane == 0) red[warp][k * NS + s] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < K * NS; i += RCF_BLOCK) {
+        float v = 0.0f;
+#pragma unroll
+        for (int w = 0; w < RCF_WARPS; ++w) v += red[w][i];
+        a.part1[((size_t)fd * (K * NS) + i) * a.nchunk1 + chunk] = v;
+    }
+}
+
+template <int K, int D>
+static cudaError_t launch_kd(const RcfK& a, bool vec, cudaStream_t s) {
+    dim3 grid(a.nchunk1, a.nfd), block(RCF_BLOCK);
+    if (vec) k_moments<K, D, 4><<<grid, block, 0, s>>>(a);
+    else k_moments<K, D, 1><<<grid, block, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int K>
+static cudaError_t launch_k(const RcfK& a, bool vec, cudaStream_t s) {
+    switch (a.D) {
+        case 0: return launch_kd<K, 0>(a, vec, s);
+        case 2: return launch_kd<K, 2>(a, vec, s);
+        case 5: return launch_kd<K, 5>(a, vec, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t rcf_launch_moments(const RcfK& a, bool vec, cudaStream_t s) {
+    switch (a.K) {
+        case 1: return launch_k<1>(a, vec, s);
+        case 2: return launch_k<2>(a, vec, s);
+        case 3: return launch_k<3>(a, vec, s);
+        case 4: return launch_k<4>(a, vec, s);
+        case 5: return launch_k<5>(a, vec, s);
+        case 6: return launch_k<6>(a, vec, s);
+        case 7: return launch_k<7>(a, vec, s);
+        case 8: return launch_k<8>(a, vec, s);
+    }
+    return cudaErrorInvalidValue;
+}

@@ -1,0 +1,145 @@
+// rcf_pool.cu -- masked pooling of the conv feature map and its backward ("Scope H" in SURVEY.md 8(d)).
+//
+// Forward (reference :251-256): Pool[f,k] = sum_p G[f,p] * M[k,p] / S_k.  The reference materialises
+// G[:, :, None] * Mn[:, None] = [B,Cf,K,H,W] (6.7 GB at B=16, K=4, 480x854) and sums it; here G is
+// read exactly once and the mask tile of the CTA is staged in shared memory so every warp (one feature
+// channel at a time) reuses it.  Cf x K is a skinny contraction (K <= 8): bandwidth-bound, CUDA cores.
+//
+// Backward: dG[f,p] = sum_k c[f,k] M[k,p]   and   dM[k,p] += sum_f c[f,k] G[f,p],  c = Poolbar / S.
+// Thread-per-pixel-pack mapping: G is read once, dG written once, the dM term is kept in registers.
+#include "rcf_common.cuh"
+
+template <int K, int PX, int CHUNK>
+__global__ void __launch_bounds__(RCF_BLOCK) k_pool(const RcfK a) {
+    __shared__ __align__(16) float ms[K][CHUNK];
+    const int fd = blockIdx.y;
+    const int dir = fd / a.B;
+    const int b = fd - dir * a.B;
+    const int chunk = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = a.P, Cf = a.Cf;
+    const int p0 = chunk * CHUNK;
+    const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
+    const float* __restrict__ feat = a.feat[dir] + (long long)b * a.feat_bs[dir];
+
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        for (int i = tid * PX; i < CHUNK; i += RCF_BLOCK * PX) {
+            float v[PX];
+            if (p0 + i < P) Pack<PX>::ld(v, mask + (long long)k * P + p0 + i);
+            else {
+#pragma unroll
+                for (int j = 0; j < PX; ++j) v[j] = 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < PX; ++j) ms[k][i + j] = v[j];
+        }
+    }
+    __syncthreads();
+
+    for (int f = warp; f < Cf; f += RCF_WARPS) {
+        const float* __restrict__ g = feat + (long long)f * P + p0;
+        float acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = 0.0f;
+#pragma unroll 4
+        for (int i = lane * PX; i < CHUNK; i += 32 * PX) {
+            if (p0 + i < P) {
+                float gv[PX];
+                Pack<PX>::ld(gv, g + i);
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) acc[k] = fmaf(gv[j], ms[k][i + j], acc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float v = warp_sum(acc[k]);
+            if (lane == 0) a.partp[((size_t)fd * Cf * K + (size_t)f * K + k) * a.nchunkp + chunk] = v;
+        }
+    }
+}
+
+template <int K, int PX>
+__global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
+    extern __shared__ float cs[];   // [Cf*K]
+    const int fd = blockIdx.y;
+    const int dir = fd / a.B;
+    const int b = fd - dir * a.B;
+    const int tid = threadIdx.x;
+    const int P = a.P, Cf = a.Cf;
+    const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
+    const float* __restrict__ feat = a.feat[dir] + (long long)b * a.feat_bs[dir];
+    float* __restrict__ dmask = a.dmask[dir] ? a.dmask[dir] + (long long)b * a.dmask_bs[dir] : nullptr;
+    float* __restrict__ dfeat = a.dfeat[dir] ? a.dfeat[dir] + (long long)b * a.dfeat_bs[dir] : nullptr;
+
+    for (int i = tid; i < Cf * K; i += RCF_BLOCK) cs[i] = a.poolbar[(size_t)fd * Cf * K + i];
+    __syncthreads();
+
+    const int p = (blockIdx.x * RCF_BLOCK + tid) * PX;
+    if (p >= P) return;
+    float m[K][PX], dm[K][PX];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        Pack<PX>::ld(m[k], mask + (long long)k * P + p);
+#pragma unroll
+        for (int j = 0; j < PX; ++j) dm[k][j] = 0.0f;
+    }
+#pragma unroll 4
+    for (int f = 0; f < Cf; ++f) {
+        float gv[PX], dg[PX];
+        Pack<PX>::ld(gv, feat + (long long)f * P + p);
+#pragma unroll
+        for (int j = 0; j < PX; ++j) dg[j] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float c = cs[f * K + k];
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                dm[k][j] = fmaf(c, gv[j], dm[k][j]);
+                dg[j] = fmaf(c, m[k][j], dg[j]);
+            }
+        }
+        if (dfeat) Pack<PX>::st(dfeat + (long long)f * P + p, dg);
+    }
+    if (dmask) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) Pack<PX>::st(dmask + (long long)k * P + p, dm[k]);
+    }
+}
+
+template <int K>
+static cudaError_t launch_pool_k(const RcfK& a, bool vec, cudaStream_t s) {
+    constexpr int CHUNK = K <= 4 ? 2048 : 1024;
+    dim3 grid(a.nchunkp, a.nfd), block(RCF_BLOCK);
+    if (vec) k_pool<K, 4, CHUNK><<<grid, block, 0, s>>>(a);
+    else k_pool<K, 1, CHUNK><<<grid, block, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int K>
+static cudaError_t launch_pool_bwd_k(const RcfK& a, bool vec, cudaStream_t s) {
+    const int px = vec ? 4 : 1;
+    dim3 grid((a.P + RCF_BLOCK * px - 1) / (RCF_BLOCK * px), a.nfd), block(RCF_BLOCK);
+    const size_t smem = (size_t)a.Cf * K * sizeof(float);
+    if (vec) k_pool_bwd<K, 4><<<grid, block, smem, s>>>(a);
+    else k_pool_bwd<K, 1><<<grid, block, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+#define RCF_K_SWITCH(fn)                                   \
+    switch (a.K) {                                         \
+        case 1: return fn<1>(a, vec, s);                   \
+        case 2: return fn<2>(a, vec, s);                   \
+        case 3: return fn<3>(a, vec, s);                   \
+        case 4: return fn<4>(a, vec, s);                   \
+        case 5: return fn<5>(a, vec, s);                   \
+        case 6: return fn<6>(a, vec, s);                   \
+        case 7: return fn<7>(a, vec, s);                   \
+        case 8: return fn<8>(a, vec, s);                   \
+    }                                                      \
+    return cudaErrorInvalidValue;
+
+cudaError_t rcf_launch_pool(const RcfK& a, bool vec, cudaStream_t s) { RCF_K_SWITCH(launch_pool_k) }
+cudaError_t rcf_launch_pool_bwd(const RcfK& a, bool vec, cudaStream_t s) { RCF_K_SWITCH(launch_pool_bwd_k) }

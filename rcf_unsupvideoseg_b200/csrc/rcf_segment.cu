@@ -1,0 +1,390 @@
+// rcf_segment.cu -- the tiny per-(frame-direction, segment) kernels, all in fp64 registers/smem.
+//
+//   k_segment_fwd : reduce pass-1 partials (fixed order => bit-reproducible), de-mean the moments,
+//                   solve the D x D normal equations (reference :198-217, torch.linalg.solve),
+//                   pooled features / S (:251-256) and the segment MLP flow_feat_after_agg (:95-101, :258),
+//                   emit the fp32 coefficient pack pass 2 consumes.
+//   k_finalize    : reduce pass-2 partials -> per-fd loss sums and gradient moments.
+//   k_loss_sum    : loss[dir] = inv_n * sum_b (mean of :361-368).
+//   k_segment_bwd : per-segment backward incl. MLP backward; emits the fp32
+//                   coefficient pack of the streaming backward and d_theta.
+//   k_mlp_param_grad : dW1, db1, dW2, db2 summed over all segments in a fixed order.
+// One CTA per frame-direction; cost is O(K * (NS*nchunk + Cf^2)) -- microseconds.
+#include "rcf_common.cuh"
+
+// sum `nchunk` fp32 partials of each of `nstat` statistics ([stat][chunk] layout); warp per stat,
+// lanes stride over chunks, butterfly in fp64: the order is fixed by (nchunk) only.
+__device__ static void reduce_partials(const float* __restrict__ part, int nstat, int nchunk, double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int s = warp; s < nstat; s += nw) {
+        const float* p = part + (size_t)s * nchunk;
+        double v = 0.0;
+        for (int c = lane; c < nchunk; c += 32) v += (double)p[c];
+        v = warp_sum_d(v);
+        if (lane == 0) out[s] = v;
+    }
+}
+
+// inverse of a symmetric positive definite D x D matrix via Cholesky (row-major in/out)
+template <int D>
+__device__ static void spd_inverse(const double* a, double* inv) {
+    double L[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) L[i][j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        double s = a[j * D + j];
+#pragma unroll
+        for (int t = 0; t < j; ++t) s -= L[j][t] * L[j][t];
+        const double dj = sqrt(s);
+        L[j][j] = dj;
+#pragma unroll
+        for (int i = j + 1; i < D; ++i) {
+            double v = a[i * D + j];
+#pragma unroll
+            for (int t = 0; t < j; ++t) v -= L[i][t] * L[j][t];
+            L[i][j] = v / dj;
+        }
+    }
+    // Linv (lower) by forward substitution, then inv = Linv^T Linv
+    double Li[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) Li[i][j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        Li[j][j] = 1.0 / L[j][j];
+#pragma unroll
+        for (int i = j + 1; i < D; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int t = j; t < i; ++t) v -= L[i][t] * Li[t][j];
+            Li[i][j] = v / L[i][i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            double v = 0.0;
+#pragma unroll
+            for (int t = 0; t < D; ++t) v += Li[t][i] * Li[t][j];
+            inv[i * D + j] = v;
+        }
+}
+
+// segd record: [0] S, [1..1+D) mu_u, [1+D..3+D) mu_F, SFu[2D], Suu[D*D], Sinv[D*D], A[2D]
+template <int D>
+__device__ static void seg_affine_fwd(const double* st, double* sd) {
+    const double S = st[0];
+    sd[0] = S;
+    if constexpr (D > 0) {
+        const double inv = 1.0 / S;
+        double mu[D], muF[2], SFu[2][D], Suu[D * D], Sinv[D * D];
+        muF[0] = st[1] * inv; muF[1] = st[2] * inv;
+#pragma unroll
+        for (int d = 0; d < D; ++d) mu[d] = st[3 + d] * inv;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int d = 0; d < D; ++d) SFu[c][d] = st[3 + D + c * D + d] * inv - muF[c] * mu[d];
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+#pragma unroll
+            for (int e = d; e < D; ++e) {
+                const double v = st[3 + 3 * D + rcf_sym_idx(D, d, e)] * inv - mu[d] * mu[e];
+                Suu[d * D + e] = v; Suu[e * D + d] = v;
+            }
+        spd_inverse<D>(Suu, Sinv);
+        double* o = sd + 1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) *o++ = mu[d];
+        *o++ = muF[0]; *o++ = muF[1];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int d = 0; d < D; ++d) *o++ = SFu[c][d];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) *o++ = Suu[i];
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) *o++ = Sinv[i];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                double v = 0.0;
+#pragma unroll
+                for (int e = 0; e < D; ++e) v += SFu[c][e] * Sinv[e * D + d];
+                *o++ = v;   // A[c][d]
+            }
+    }
+}
+
+#define RCF_SEG_MAXSTAT (RCF_MAX_K * 33)
+
+template <int D>
+__global__ void __launch_bounds__(RCF_BLOCK) k_segment_fwd(const RcfK a) {
+    constexpr int NS = rcf_ns(D), SEGD = rcf_segd(D), CF = rcf_cf(D);
+    __shared__ double stat[RCF_SEG_MAXSTAT];
+    __shared__ double theta_s[2 * RCF_MAX_K];
+    extern __shared__ double dyn[];            // pool[Cf*K], h[Cf*K]   (theta_mode 1)
+    const int fd = blockIdx.x, K = a.K, Cf = a.Cf, tid = threadIdx.x;
+    const int dir = fd / a.B, b = fd - dir * a.B;
+
+    reduce_partials(a.part1 + (size_t)fd * K * NS * a.nchunk1, K * NS, a.nchunk1, stat);
+    __syncthreads();
+    double* sd = a.segd + (size_t)fd * K * SEGD;
+    if (tid < K) seg_affine_fwd<D>(stat + tid * NS, sd + tid * SEGD);
+
+    if (a.theta_mode == 1) {
+        double* pool = dyn;              // [f*K + k]
+        double* hpre = dyn + Cf * K;     // [i*K + k]
+        reduce_partials(a.partp + (size_t)fd * Cf * K * a.nchunkp, Cf * K, a.nchunkp, pool);
+        __syncthreads();
+        for (int i = tid; i < Cf * K; i += blockDim.x) pool[i] /= stat[(i % K) * NS];
+        __syncthreads();
+        double* mlp = a.mlp + (size_t)fd * K * 2 * Cf;   // [k][0: pool | 1: hpre][Cf]
+        for (int t = tid; t < Cf * K; t += blockDim.x) {
+            const int i = t / K, k = t - i * K;
+            double v = (double)a.b1[i];
+            const float* w = a.w1 + (size_t)i * Cf;
+            for (int j = 0; j < Cf; ++j) v += (double)w[j] * pool[j * K + k];
+            hpre[t] = v;
+            mlp[(size_t)k * 2 * Cf + Cf + i] = v;
+            mlp[(size_t)k * 2 * Cf + i] = pool[t];
+        }
+        __syncthreads();
+        if (tid < 2 * K) {
+            const int c = tid / K, k = tid - c * K;
+            double v = (double)a.b2[c];
+            const float* w = a.w2 + (size_t)c * Cf;
+            for (int i = 0; i < Cf; ++i) {
+                const double h = hpre[i * K + k];
+                v += (double)w[i] * (h >= 0.0 ? h : 0.1 * h);
+            }
+            theta_s[c * K + k] = v;
+        }
+    } else {
+        if (tid < 2 * K) theta_s[tid] = (double)a.theta[dir][(size_t)b * 2 * K + tid];   // [B,2,K]
+    }
+    __syncthreads();
+    if (tid < K) {
+        float* cf = a.coef + ((size_t)fd * K + tid) * CF;
+        const double* s = sd + tid * SEGD;
+        cf[0] = (float)theta_s[tid];
+        cf[1] = (float)theta_s[K + tid];
+        if constexpr (D > 0) {
+            const double* A = s + 3 + 3 * D + 2 * D * D;
+#pragma unroll
+            for (int i = 0; i < 2 * D; ++i) cf[2 + i] = (float)A[i];
+#pragma unroll
+            for (int d = 0; d < D; ++d) cf[2 + 2 * D + d] = (float)s[1 + d];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RCF_BLOCK) k_finalize(const RcfK a, int GM) {
+    const int fd = blockIdx.x;
+    __shared__ double out[1 + 2 * RCF_MAX_K + 2 * RCF_MAX_K * 5];
+    reduce_partials(a.part2 + (size_t)fd * GM * a.nchunk2, GM, a.nchunk2, out);
+    __syncthreads();
+    for (int i = threadIdx.x; i < GM; i += blockDim.x) a.gm[(size_t)fd * GM + i] = out[i];
+}
+
+__global__ void k_loss_sum(const RcfK a, int GM) {
+    // one warp per direction; lanes stride over the batch, fp64 butterfly
+    const int dir = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (dir >= a.ndir) return;
+    double v = 0.0;
+    for (int b = lane; b < a.B; b += 32) v += a.gm[(size_t)(dir * a.B + b) * GM];
+    v = warp_sum_d(v);
+    if (lane == 0) a.loss[dir] = (float)(v * (double)a.inv_n);
+}
+
+template <int D>
+__global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
+    constexpr int SEGD = rcf_segd(D), CB = rcf_cb(D);
+    __shared__ double thbar[2 * RCF_MAX_K];      // [c*K + k]
+    __shared__ double inner[RCF_MAX_K];          // <SFubar,SFu> + <Suubar,Suu>
+    __shared__ double poolterm[RCF_MAX_K];
+    extern __shared__ double dyn[];              // dh[Cf*K], pbar[Cf*K]
+    const int fd = blockIdx.x, K = a.K, Cf = a.Cf, tid = threadIdx.x;
+    const int dir = fd / a.B, b = fd - dir * a.B;
+    const int GM = rcf_gm(K, D);
+    const double gs = -(double)a.grad_loss[dir] * (double)a.inv_n;
+    const double* gm = a.gm + (size_t)fd * GM;
+    const double* sd = a.segd + (size_t)fd * K * SEGD;
+    if (tid == 0) a.gscale[fd] = (float)gs;
+
+    if (tid < K) {
+        const int k = tid;
+        const double* s = sd + k * SEGD;
+        const double S = s[0];
+        const double tb0 = gs * gm[1 + k], tb1 = gs * gm[1 + K + k];
+        thbar[k] = tb0; thbar[K + k] = tb1;
+        float* cb = a.coefb + ((size_t)fd * K + k) * CB;
+        double in = 0.0;
+        if constexpr (D > 0) {
+            const double* muF = s + 1 + D;
+            const double* SFu = s + 3 + D;
+            const double* Suu = s + 3 + 3 * D;
+            const double* Sinv = s + 3 + 3 * D + D * D;
+            const double* A = s + 3 + 3 * D + 2 * D * D;
+            double Ab[2][D], SFb[2][D], Sub[D][D], mub[D];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int d = 0; d < D; ++d) Ab[c][d] = gs * gm[1 + 2 * K + (k * 2 + c) * D + d];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int e = 0; e < D; ++e) v += Ab[c][e] * Sinv[e * D + d];
+                    SFb[c][d] = v;
+                    in += v * SFu[c * D + d];
+                }
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+#pragma unroll
+                for (int e = 0; e < D; ++e) {
+                    const double v = -(A[d] * SFb[0][e] + A[D + d] * SFb[1][e]);
+                    Sub[d][e] = v;
+                    in += v * Suu[d * D + e];
+                }
+                mub[d] = -(A[d] * tb0 + A[D + d] * tb1);
+            }
+            const double iS = 1.0 / S;
+            cb[0] = (float)muF[0]; cb[1] = (float)muF[1];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int d = 0; d < D; ++d) cb[2 + c * D + d] = (float)(SFb[c][d] * iS);
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+#pragma unroll
+                for (int e = d; e < D; ++e)
+                    cb[2 + 2 * D + rcf_sym_idx(D, d, e)] = (float)((d == e ? Sub[d][d] : Sub[d][e] + Sub[e][d]) * iS);
+#pragma unroll
+            for (int d = 0; d < D; ++d) cb[2 + 2 * D + D * (D + 1) / 2 + d] = (float)(mub[d] * iS);
+        } else {
+            cb[0] = 0.0f; cb[1] = 0.0f;
+        }
+        inner[k] = in;
+        poolterm[k] = 0.0;
+        if (a.theta_mode == 0 && a.dtheta[dir]) {
+            float* dt = a.dtheta[dir] + (size_t)b * 2 * K;
+            dt[k] = (float)tb0; dt[K + k] = (float)tb1;
+        }
+        a.thbar[((size_t)fd * K + k) * 2 + 0] = tb0;
+        a.thbar[((size_t)fd * K + k) * 2 + 1] = tb1;
+    }
+    __syncthreads();
+
+    if (a.theta_mode == 1) {
+        double* dh = dyn;             // [i*K + k]
+        double* pbar = dyn + Cf * K;  // [j*K + k]
+        const double* mlp = a.mlp + (size_t)fd * K * 2 * Cf;
+        for (int t = tid; t < Cf * K; t += blockDim.x) {
+            const int i = t / K, k = t - i * K;
+            const double hp = mlp[(size_t)k * 2 * Cf + Cf + i];
+            const double v = ((double)a.w2[i] * thbar[k] + (double)a.w2[Cf + i] * thbar[K + k]) * (hp >= 0.0 ? 1.0 : 0.1);
+            dh[t] = v;
+            a.dh[((size_t)fd * K + k) * Cf + i] = v;
+        }
+        __syncthreads();
+        for (int t = tid; t < Cf * K; t += blockDim.x) {
+            const int k = t / Cf, j = t - k * Cf;       // consecutive threads -> consecutive j (coalesced w1 reads)
+            double v = 0.0;
+            for (int i = 0; i < Cf; ++i) v += (double)a.w1[(size_t)i * Cf + j] * dh[i * K + k];
+            pbar[j * K + k] = v;
+            a.poolbar[((size_t)fd * Cf + j) * K + k] = (float)(v / sd[k * SEGD]);
+        }
+        __syncthreads();
+        if (tid < K) {
+            double v = 0.0;
+            for (int j = 0; j < Cf; ++j) v += pbar[j * K + tid] * mlp[(size_t)tid * 2 * Cf + j];
+            poolterm[tid] = v;
+        }
+        __syncthreads();
+    }
+    if (tid < K) {
+        float* cb = a.coefb + ((size_t)fd * K + tid) * CB;
+        cb[CB - 1] = (float)(-(inner[tid] + poolterm[tid]) / sd[tid * SEGD]);
+    }
+}
+
+// grid = Cf + 1 blocks.  Block i < Cf: row i of dW1 and db1[i].  Block Cf: dW2, db2.
+__global__ void k_mlp_param_grad(const RcfK a) {
+    const int Cf = a.Cf, K = a.K, nseg = a.nfd * K;
+    const int i = blockIdx.x;
+    if (i < Cf) {
+        for (int j = threadIdx.x; j < Cf; j += blockDim.x) {
+            double v = 0.0;
+            for (int s = 0; s < nseg; ++s)
+                v += a.dh[(size_t)s * Cf + i] * a.mlp[(size_t)s * 2 * Cf + j];
+            a.dw1[(size_t)i * Cf + j] = (float)v;
+        }
+        if (threadIdx.x == 0) {
+            double v = 0.0;
+            for (int s = 0; s < nseg; ++s) v += a.dh[(size_t)s * Cf + i];
+            a.db1[i] = (float)v;
+        }
+    } else {
+        for (int t = threadIdx.x; t < 2 * Cf; t += blockDim.x) {
+            const int c = t / Cf, j = t - c * Cf;
+            double v = 0.0;
+            for (int s = 0; s < nseg; ++s) {
+                const double hp = a.mlp[(size_t)s * 2 * Cf + Cf + j];
+                v += a.thbar[(size_t)s * 2 + c] * (hp >= 0.0 ? hp : 0.1 * hp);
+            }
+            a.dw2[(size_t)c * Cf + j] = (float)v;
+        }
+        if (threadIdx.x < 2) {
+            double v = 0.0;
+            for (int s = 0; s < nseg; ++s) v += a.thbar[(size_t)s * 2 + threadIdx.x];
+            a.db2[threadIdx.x] = (float)v;
+        }
+    }
+}
+
+cudaError_t rcf_launch_segment_fwd(const RcfK& a, cudaStream_t s) {
+    const size_t dyn = a.theta_mode == 1 ? (size_t)2 * a.Cf * a.K * sizeof(double) : 0;
+    switch (a.D) {
+        case 0: k_segment_fwd<0><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
+        case 2: k_segment_fwd<2><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
+        case 5: k_segment_fwd<5><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t rcf_launch_finalize(const RcfK& a, cudaStream_t s) {
+    const int GM = rcf_gm(a.K, a.D);
+    k_finalize<<<a.nfd, RCF_BLOCK, 0, s>>>(a, GM);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_loss_sum<<<1, 64, 0, s>>>(a, GM);
+    return cudaGetLastError();
+}
+
+cudaError_t rcf_launch_segment_bwd(const RcfK& a, cudaStream_t s) {
+    const size_t dyn = a.theta_mode == 1 ? (size_t)2 * a.Cf * a.K * sizeof(double) : 0;
+    switch (a.D) {
+        case 0: k_segment_bwd<0><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
+        case 2: k_segment_bwd<2><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
+        case 5: k_segment_bwd<5><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (a.theta_mode == 1 && a.dw1 && a.db1 && a.dw2 && a.db2) {
+        k_mlp_param_grad<<<a.Cf + 1, 128, 0, s>>>(a);
+        e = cudaGetLastError();
+    }
+    return e;
+}

@@ -1,0 +1,259 @@
+"""torch.autograd.Function over the C-ABI library: the RCF motion loss, forward + backward.
+
+PyTorch is used here for device memory, streams and the autograd hook only; every per-pixel and
+per-segment computation of reference models/flow_aggregation_head_with_residual.py:235-310 and
+:359-368 runs inside librcf_loss.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+@dataclass(frozen=True)
+class LossSpec:
+    """Static description of one loss call (mirrors the reference constructor flags that reach the math)."""
+    K: int
+    H: int
+    W: int
+    D: int = 0                      # 0 free_residual, 2 affine, 5 quadratic
+    Cf: int = 0                     # pooled feature channels (0 => theta supplied)
+    robust: bool = False
+    eps: float = 0.01
+    q: float = 0.4
+    resid_scale: float = 10.0
+    pred_div: float = 10.0
+    clamp_t: Optional[float] = None
+    unbounded_residual: bool = False
+    inv_n: float = 0.0              # 0 => 1/(B*2*H*W); set for batch-sharded (multi-GPU) use
+    want_vis: bool = False
+    vis_scale: Tuple[float, float] = (1.0, 1.0)
+
+    @property
+    def theta_mode(self) -> int:
+        return 1 if self.Cf > 0 else 0
+
+
+def _inner_dense(t: torch.Tensor, nd: int) -> bool:
+    """last `nd` dims laid out densely (row-major) -- what the kernels require of [C,H,W] blocks."""
+    exp = 1
+    for size, stride in zip(reversed(t.shape[-nd:]), reversed(t.stride()[-nd:])):
+        if size != 1 and stride != exp:
+            return False
+        exp *= size
+    return True
+
+
+def _as_dir_view(t: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] fp32 CUDA tensor whose [C,H,W] block is dense; batch stride is free."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not _inner_dense(t, 3):
+        t = t.contiguous()
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _make_desc(spec: LossSpec, B: int, ndir: int) -> _lib.RcfDesc:
+    d = _lib.RcfDesc()
+    d.B, d.K, d.H, d.W, d.Cf, d.D, d.ndir = B, spec.K, spec.H, spec.W, spec.Cf, spec.D, ndir
+    d.theta_mode = spec.theta_mode
+    d.robust = int(spec.robust)
+    d.unbounded_residual = int(spec.unbounded_residual)
+    d.eps, d.q = spec.eps, spec.q
+    d.resid_scale, d.pred_div = spec.resid_scale, spec.pred_div
+    d.clamp_t = -1.0 if spec.clamp_t is None else float(spec.clamp_t)
+    d.inv_n = spec.inv_n
+    return d
+
+
+class RcfMotionLossFn(torch.autograd.Function):
+    """loss[dir] = mean(phi(F_dir - pred_dir)) for ndir directions.
+
+    Inputs (all fp32 CUDA):
+      masks  [B, ndir, K, H, W]           (grad)
+      flows  tuple of ndir  [B, 2, H, W]  (no grad; the clamp is applied inside the kernels)
+      resids tuple of ndir  [B, 2K, H, W] (grad)
+      feats  tuple of ndir  [B, Cf, H, W] (grad)  + w1,b1,w2,b2 (grad)      when spec.Cf > 0
+      thetas tuple of ndir  [B, 2, K]     (grad)                            when spec.Cf == 0
+    Returns loss [ndir] and, when spec.want_vis, the un-differentiable tensors
+    (gt, pred, agg, res[, aff]) each [B, 2*ndir, H, W].
+    """
+
+    @staticmethod
+    def forward(ctx, spec: LossSpec, masks, w1, b1, w2, b2, *per_dir):
+        lib = _lib.load_library()
+        ndir = masks.shape[1]
+        assert len(per_dir) == 4 * ndir
+        flows = per_dir[0:ndir]
+        resids = per_dir[ndir:2 * ndir]
+        feats = per_dir[2 * ndir:3 * ndir]
+        thetas = per_dir[3 * ndir:4 * ndir]
+        if not masks.is_cuda:
+            raise RuntimeError("RcfMotionLossFn needs CUDA tensors: the loss has no CPU implementation")
+        B, _, K, H, W = masks.shape
+        assert (K, H, W) == (spec.K, spec.H, spec.W), f"mask shape {tuple(masks.shape)} vs spec {spec}"
+        dev = masks.device
+        P = H * W
+
+        masks_v = masks if (masks.dtype == torch.float32 and _inner_dense(masks, 3)) else masks.float().contiguous()
+        flows_v = [_as_dir_view(f) for f in flows]
+        resids_v = [_as_dir_view(r) for r in resids]
+        feats_v = [_as_dir_view(g) if g is not None else None for g in feats]
+        thetas_v = [t.float().contiguous() if t is not None else None for t in thetas]
+        for f in flows_v:
+            assert f.shape == (B, 2, H, W), f"flow shape {tuple(f.shape)}"
+        for r in resids_v:
+            assert r.shape == (B, 2 * K, H, W), f"residual shape {tuple(r.shape)}"
+        if spec.Cf > 0:
+            for g in feats_v:
+                assert g is not None and g.shape == (B, spec.Cf, H, W), "feature map shape"
+            w1c, b1c, w2c, b2c = (t.detach().float().contiguous() for t in (w1, b1, w2, b2))
+            assert w1c.numel() == spec.Cf * spec.Cf and w2c.numel() == 2 * spec.Cf
+        else:
+            for t in thetas_v:
+                assert t is not None and t.shape == (B, 2, K), "theta shape"
+            w1c = b1c = w2c = b2c = None
+
+        desc = _make_desc(spec, B, ndir)
+        inp = _lib.RcfInputs()
+        for i in range(ndir):
+            inp.mask[i] = masks_v.data_ptr() + i * masks_v.stride(1) * 4
+            desc.mask_bstride[i] = masks_v.stride(0)
+            inp.flow[i] = flows_v[i].data_ptr(); desc.flow_bstride[i] = flows_v[i].stride(0)
+            inp.resid[i] = resids_v[i].data_ptr(); desc.resid_bstride[i] = resids_v[i].stride(0)
+            if spec.Cf > 0:
+                inp.feat[i] = feats_v[i].data_ptr(); desc.feat_bstride[i] = feats_v[i].stride(0)
+            else:
+                inp.theta[i] = thetas_v[i].data_ptr()
+        if spec.Cf > 0:
+            inp.w1, inp.b1, inp.w2, inp.b2 = (t.data_ptr() for t in (w1c, b1c, w2c, b2c))
+
+        ctx_bytes, ws_bytes = C.c_size_t(), C.c_size_t()
+        _lib.check(lib.rcf_query_sizes(C.byref(desc), C.byref(ctx_bytes), C.byref(ws_bytes)), "rcf_query_sizes")
+        ctx_buf = torch.empty(ctx_bytes.value, dtype=torch.uint8, device=dev)
+        ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+        loss = torch.empty(ndir, dtype=torch.float32, device=dev)
+
+        vis_tensors: Tuple[torch.Tensor, ...] = ()
+        vis_struct = None
+        if spec.want_vis:
+            n_out = 5 if spec.D > 0 else 4
+            vis_tensors = tuple(torch.empty(B, 2 * ndir, H, W, dtype=torch.float32, device=dev) for _ in range(n_out))
+            vis_struct = _lib.RcfVisOut()
+            vis_struct.gt, vis_struct.pred, vis_struct.agg, vis_struct.res = (t.data_ptr() for t in vis_tensors[:4])
+            vis_struct.aff = vis_tensors[4].data_ptr() if n_out == 5 else None
+            desc.vis_bstride = 2 * ndir * P
+            desc.vis_dstride = 2 * P
+            desc.vis_scale[0], desc.vis_scale[1] = spec.vis_scale
+
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.rcf_forward(C.byref(desc), C.byref(inp), loss.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
+                                       C.byref(vis_struct) if vis_struct is not None else None, stream), "rcf_forward")
+
+        ctx.spec, ctx.ndir, ctx.B = spec, ndir, B
+        ctx.masks_shape = tuple(masks.shape)
+        ctx.save_for_backward(masks_v, ctx_buf, *flows_v, *resids_v,
+                              *[g for g in feats_v if g is not None], *[t for t in thetas_v if t is not None],
+                              *([w1c, b1c, w2c, b2c] if spec.Cf > 0 else []))
+        ctx.mark_non_differentiable(*vis_tensors)
+        return (loss, *vis_tensors)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loss, *grad_vis):
+        lib = _lib.load_library()
+        spec, ndir, B = ctx.spec, ctx.ndir, ctx.B
+        K, H, W, Cf = spec.K, spec.H, spec.W, spec.Cf
+        saved = list(ctx.saved_tensors)
+        masks_v, ctx_buf = saved[0], saved[1]
+        flows_v = saved[2:2 + ndir]
+        resids_v = saved[2 + ndir:2 + 2 * ndir]
+        rest = saved[2 + 2 * ndir:]
+        dev = masks_v.device
+        # needs_input_grad: (spec, masks, w1, b1, w2, b2, *flows, *resids, *feats, *thetas)
+        need = ctx.needs_input_grad
+        need_masks = need[1]
+        need_w = any(need[2:6])
+        need_resid = [need[6 + ndir + i] for i in range(ndir)]
+        need_feat = [need[6 + 2 * ndir + i] for i in range(ndir)]
+        need_theta = [need[6 + 3 * ndir + i] for i in range(ndir)]
+
+        desc = _make_desc(spec, B, ndir)
+        inp = _lib.RcfInputs()
+        grads = _lib.RcfGrads()
+        if Cf > 0:
+            feats_v = rest[0:ndir]
+            w1c, b1c, w2c, b2c = rest[ndir:ndir + 4]
+            inp.w1, inp.b1, inp.w2, inp.b2 = (t.data_ptr() for t in (w1c, b1c, w2c, b2c))
+        else:
+            thetas_v = rest[0:ndir]
+
+        d_masks = torch.empty(ctx.masks_shape, dtype=torch.float32, device=dev) if need_masks else None
+        d_resids, d_feats, d_thetas = [None] * ndir, [None] * ndir, [None] * ndir
+        for i in range(ndir):
+            inp.mask[i] = masks_v.data_ptr() + i * masks_v.stride(1) * 4
+            desc.mask_bstride[i] = masks_v.stride(0)
+            inp.flow[i] = flows_v[i].data_ptr(); desc.flow_bstride[i] = flows_v[i].stride(0)
+            inp.resid[i] = resids_v[i].data_ptr(); desc.resid_bstride[i] = resids_v[i].stride(0)
+            if d_masks is not None:
+                grads.dmask[i] = d_masks.data_ptr() + i * d_masks.stride(1) * 4
+                desc.dmask_bstride[i] = d_masks.stride(0)
+            if need_resid[i]:
+                d_resids[i] = torch.empty(B, 2 * K, H, W, dtype=torch.float32, device=dev)
+                grads.dresid[i] = d_resids[i].data_ptr(); desc.dresid_bstride[i] = d_resids[i].stride(0)
+            if Cf > 0:
+                inp.feat[i] = feats_v[i].data_ptr(); desc.feat_bstride[i] = feats_v[i].stride(0)
+                if need_feat[i]:
+                    d_feats[i] = torch.empty(B, Cf, H, W, dtype=torch.float32, device=dev)
+                    grads.dfeat[i] = d_feats[i].data_ptr(); desc.dfeat_bstride[i] = d_feats[i].stride(0)
+            else:
+                inp.theta[i] = thetas_v[i].data_ptr()
+                if need_theta[i]:
+                    d_thetas[i] = torch.empty(B, 2, K, dtype=torch.float32, device=dev)
+                    grads.dtheta[i] = d_thetas[i].data_ptr()
+        dw = [None, None, None, None]
+        if Cf > 0 and need_w:
+            dw = [torch.empty(Cf, Cf, 1, dtype=torch.float32, device=dev), torch.empty(Cf, dtype=torch.float32, device=dev),
+                  torch.empty(2, Cf, 1, dtype=torch.float32, device=dev), torch.empty(2, dtype=torch.float32, device=dev)]
+            grads.dw1, grads.db1, grads.dw2, grads.db2 = (t.data_ptr() for t in dw)
+
+        ctx_bytes, ws_bytes = C.c_size_t(), C.c_size_t()
+        _lib.check(lib.rcf_query_sizes(C.byref(desc), C.byref(ctx_bytes), C.byref(ws_bytes)), "rcf_query_sizes")
+        ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+        gl = grad_loss.detach().to(torch.float32).contiguous()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.rcf_backward(C.byref(desc), C.byref(inp), gl.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
+                                        C.byref(grads), stream), "rcf_backward")
+        return (None, d_masks, *dw, *([None] * ndir), *d_resids, *d_feats, *d_thetas)
+
+
+def rcf_motion_loss(spec: LossSpec, masks: torch.Tensor, flows: Sequence[torch.Tensor],
+                    resids: Sequence[torch.Tensor], *, feats: Optional[Sequence[torch.Tensor]] = None,
+                    mlp: Optional[Sequence[torch.Tensor]] = None, thetas: Optional[Sequence[torch.Tensor]] = None):
+    """Functional entry point.  masks [B,ndir,K,H,W]; flows/resids (and feats or thetas) per direction.
+
+    Returns (loss [ndir], vis tuple).  Exactly one of (feats + mlp weights) or thetas must be given,
+    consistently with spec.Cf.
+    """
+    ndir = masks.shape[1]
+    if spec.Cf > 0:
+        assert feats is not None and mlp is not None and len(mlp) == 4
+        w1, b1, w2, b2 = mlp
+        per_dir = (*flows, *resids, *feats, *([None] * ndir))
+    else:
+        assert thetas is not None
+        w1 = b1 = w2 = b2 = None
+        per_dir = (*flows, *resids, *([None] * ndir), *thetas)
+    out = RcfMotionLossFn.apply(spec, masks, w1, b1, w2, b2, *per_dir)
+    return out[0], tuple(out[1:])

@@ -1,0 +1,261 @@
+"""Drop-in replacement of the reference's FlowAggregationHeadWithResidual.
+
+Mirrors /root/reference/models/flow_aggregation_head_with_residual.py:33-399: same class name,
+constructor keywords and defaults, parameter names (``flow_feat_before_agg.{0,2}``,
+``flow_feat_after_agg.{0,2}`` -- checkpoints load unchanged), ``forward`` signature and the
+``(flows, flow_loss)`` return structure.  The reference instantiates heads by class name from the
+module globals of models/rcf_model.py (:75); see INTEGRATION.md for the one-line rebinding.
+
+What runs where:
+  * ``flow_feat_before_agg`` (two small convs, reference :84-93) -> cuDNN through torch (library GEMM work);
+  * everything else (mask normalisation, masked pooling, segment MLP, affine / quadratic fit,
+    residual, reconstruction, loss, and the whole backward) -> librcf_loss.so (sm_100a kernels).
+There is no PyTorch implementation of the loss in this package: without the CUDA library (or on CPU
+tensors) ``forward`` raises.
+
+Documented deviations from the reference:
+  * the returned visualisation ``flows`` are detached (the reference returns graph-attached tensors,
+    but its only caller uses them for JPEG dumps, models/rcf_model.py:446-460);
+  * ``coord_map`` is not materialised (the kernels generate coordinates on the fly), so no
+    hard-coded ``.cuda()`` at construction (reference :143,:146);
+  * no gradient is produced for the ground-truth flows.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .function import LossSpec, rcf_motion_loss
+
+logger = logging.getLogger("main")
+
+
+class Objectview(object):
+    """dict -> attribute shim kept for import compatibility (reference :10-15)."""
+
+    def __init__(self, d):
+        self.__dict__ = d
+
+    def keys(self):
+        return self.__dict__.keys()
+
+
+def get_norm_flow(lis1, lis2):
+    """Visualisation scaling of two [B,2,H,W] flows (reference :18-30): ch0 / (H/2), ch1 / (W/2)."""
+    def norm(x):
+        _h, _w = x.shape[2:]
+        return _h, _w, torch.cat([x[:, 0:1] / (_h / 2.0), x[:, 1:2] / (_w / 2.0)], 1)
+
+    _, _, flow = norm(lis1)
+    _h, _w, flow2 = norm(lis2)
+    return _h, _w, flow, flow2
+
+
+class FlowAggregationHeadWithResidual(nn.Module):
+    """RCF motion-loss head; see module docstring.  Constructor mirrors reference :50-74."""
+
+    def __init__(self,
+                 args,
+                 ssim_sz=1,
+                 mask_layer=5,
+                 create_flownet=False,
+                 flow_feat_before_agg_kernel_size=3,
+                 num_flow_feat_channels=64,
+                 outlier_robust_loss=False,
+                 eps=0.01,
+                 q=0.4,
+                 mask_size=(48, 48),
+                 residual_adjustment_scale=10.,
+                 norm_flow=False,
+                 clamp_flow_t=None,
+                 filter_flow_t=None,
+                 free_residual=False,
+                 free_residual_with_affine=False,
+                 free_residual_with_affine_quadratic=False,
+                 object_free_residual=False,
+                 free_scale=False,
+                 affine_residual=False,
+                 allow_residual_resize=False,
+                 pred_div_coeff=10.):
+        self.mask_layer = mask_layer
+        super().__init__()
+        logger.info("[info] ssim_sz={}".format(ssim_sz))
+        self.args = args
+        assert create_flownet            # reference :82
+
+        ks = flow_feat_before_agg_kernel_size
+        self.flow_feat_before_agg = nn.Sequential(
+            nn.Conv2d(2, num_flow_feat_channels, kernel_size=ks, stride=1, dilation=1, padding=(ks - 1) // 2, bias=True),
+            nn.LeakyReLU(0.1, inplace=True),
+            nn.Conv2d(num_flow_feat_channels, num_flow_feat_channels, kernel_size=ks, stride=1, dilation=1,
+                      padding=(ks - 1) // 2, bias=True),
+            nn.LeakyReLU(0.1, inplace=True),
+        )
+        # Parameters of the segment MLP; applied inside the CUDA segment kernel (never called as modules).
+        self.flow_feat_after_agg = nn.Sequential(
+            nn.Conv1d(num_flow_feat_channels, num_flow_feat_channels, kernel_size=1, stride=1, dilation=1, bias=True),
+            nn.LeakyReLU(0.1, inplace=True),
+            nn.Conv1d(num_flow_feat_channels, 2, kernel_size=1, stride=1, dilation=1, bias=True),
+        )
+        self.num_flow_feat_channels = num_flow_feat_channels
+
+        self.outlier_robust_loss = outlier_robust_loss
+        if self.outlier_robust_loss:
+            logger.info("Using outlier robust loss")
+        self.eps = eps
+        self.q = q
+        self.mask_size = tuple(mask_size)
+        self.residual_adjustment_scale = residual_adjustment_scale
+        self.pred_div_coeff = pred_div_coeff
+        logger.info(f"Prediction division coefficient: {self.pred_div_coeff}")
+        self.norm_flow = norm_flow
+        self.clamp_flow_t = clamp_flow_t
+        self.filter_flow_t = filter_flow_t
+
+        self.free_residual = free_residual
+        self.free_residual_with_affine = free_residual_with_affine
+        self.free_residual_with_affine_quadratic = free_residual_with_affine_quadratic
+        if self.free_residual_with_affine_quadratic:
+            assert self.free_residual_with_affine, \
+                "free_residual_with_affine needs to be enabled to enable free_residual_with_affine_quadratic"
+        self.object_free_residual = object_free_residual
+        self.free_scale = free_scale
+        self.affine_residual = affine_residual
+        assert (int(self.free_residual) + int(self.free_residual_with_affine) + int(self.object_free_residual)
+                + int(self.free_scale) + int(self.affine_residual)) <= 1, \
+            f"Only one of {self.free_residual}, {self.free_residual_with_affine}, {self.object_free_residual}, " \
+            f"{self.free_scale}, {self.affine_residual}"
+        self.allow_residual_resize = allow_residual_resize
+        # benchmark switch: skip the visualisation tensors (the reference always builds them, :370-395)
+        self.return_flows = True
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def _D(self) -> int:
+        if not self.free_residual_with_affine:
+            return 0
+        return 5 if self.free_residual_with_affine_quadratic else 2
+
+    def _fused_clamp(self) -> bool:
+        """Clamp can be fused into the kernels' loads unless norm/filter (torch path) are in play."""
+        return not self.norm_flow and self.filter_flow_t is None
+
+    def norm_and_clamp_flow(self, flow):
+        """reference :150-162, including its in-place filter on the caller's tensor when no copy preceded."""
+        if self.norm_flow:
+            flow = flow / flow.abs().max()
+        if self.clamp_flow_t is not None:
+            flow = flow.clamp(min=-self.clamp_flow_t, max=self.clamp_flow_t)
+        if self.filter_flow_t is not None:
+            flow[flow.abs() < self.filter_flow_t] = 0.
+        return flow
+
+    def _check_residual_mode(self):
+        if not (self.free_residual or self.free_residual_with_affine):
+            # the reference reaches `return ..., residual_adjustment, ...` with the name unbound (:305-310)
+            raise UnboundLocalError("local variable 'residual_adjustment' referenced before assignment")
+
+    def _spec(self, K, H, W, *, want_vis, vis_norm, inv_n=0.0, clamp_fused=True) -> LossSpec:
+        unbounded = bool(self.free_residual and self.residual_adjustment_scale == -1.)
+        return LossSpec(K=K, H=H, W=W, D=self._D, Cf=self.num_flow_feat_channels,
+                        robust=bool(self.outlier_robust_loss), eps=float(self.eps), q=float(self.q),
+                        resid_scale=float(self.residual_adjustment_scale), pred_div=float(self.pred_div_coeff),
+                        clamp_t=(self.clamp_flow_t if clamp_fused else None), unbounded_residual=unbounded,
+                        inv_n=inv_n, want_vis=want_vis,
+                        vis_scale=((2.0 / H, 2.0 / W) if vis_norm else (1.0, 1.0)))
+
+    def _prepare(self, flow, resid, H, W):
+        """Returns (flow for the kernels, flow for the conv branch, clamp_fused, residual at mask_size)."""
+        if self._fused_clamp():
+            k_flow = flow
+            c_flow = flow.clamp(min=-self.clamp_flow_t, max=self.clamp_flow_t) if self.clamp_flow_t is not None else flow
+            fused = True
+        else:
+            k_flow = c_flow = self.norm_and_clamp_flow(flow)
+            fused = False
+        if self.allow_residual_resize and tuple(resid.shape[-2:]) != self.mask_size:   # :271-273, :294-296
+            resid = F.interpolate(resid, self.mask_size, mode='bilinear')
+        return k_flow, c_flow, fused, resid
+
+    def _mlp_params(self):
+        l0, l2 = self.flow_feat_after_agg[0], self.flow_feat_after_agg[2]
+        return l0.weight, l0.bias, l2.weight, l2.bias
+
+    def _run(self, masks5, flows, resids, *, want_vis, vis_norm, inv_n=0.0):
+        """masks5 [B,ndir,K,H,W]; flows / resids: per-direction lists."""
+        self._check_residual_mode()
+        if not masks5.is_cuda:
+            raise RuntimeError("FlowAggregationHeadWithResidual (B200) needs CUDA tensors; there is no CPU fallback")
+        B, ndir, K, H, W = masks5.shape
+        with torch.autocast(device_type="cuda", enabled=False):
+            masks5 = masks5.float()
+            k_flows, feats, rs = [], [], []
+            fused = True
+            for flow, resid in zip(flows, resids):
+                kf, cf_, fused_i, r = self._prepare(flow.float(), resid.float(), H, W)
+                fused = fused and fused_i
+                feat = self.flow_feat_before_agg(cf_)
+                assert feat.shape[2:] == masks5.shape[3:], \
+                    f"{feat.shape[2:]} != {masks5.shape[3:]} (should match on spatial dimension)"   # :247-248
+                assert r.shape[-2:] == (H, W), f"residual spatial size {tuple(r.shape[-2:])} != mask size {(H, W)}"
+                k_flows.append(kf.detach()); feats.append(feat); rs.append(r)
+            spec = self._spec(K, H, W, want_vis=want_vis, vis_norm=vis_norm, inv_n=inv_n, clamp_fused=fused)
+            loss, vis = rcf_motion_loss(spec, masks5, k_flows, rs, feats=feats, mlp=self._mlp_params())
+        return loss, vis
+
+    # ------------------------------------------------------------------------------------------
+    def get_demean_affine_flow(self, mask, flow):
+        """reference :164-233: the de-meaned affine / quadratic part of the fit, [B,2,H,W] (no grad).
+        `flow` is used as given (the reference passes the already clamped flow)."""
+        assert self.free_residual_with_affine
+        B, K, H, W = mask.shape
+        zeros = mask.new_zeros(B, 2 * K, H, W)
+        theta = mask.new_zeros(B, 2, K)
+        spec = LossSpec(K=K, H=H, W=W, D=self._D, Cf=0, clamp_t=None, want_vis=True)
+        with torch.no_grad():
+            _, vis = rcf_motion_loss(spec, mask.detach().unsqueeze(1), [flow.detach()], [zeros], thetas=[theta])
+        return vis[4]
+
+    def aggregate_flow_with_residual(self, mask, flow, all_pred_residual):
+        """reference :235-310 -> (flow_overall, flow_agg, residual_adjustment, flow_affine), detached.
+        `flow` is taken as already prepared (clamped), as in the reference's call sites (:344-347)."""
+        self._check_residual_mode()
+        B, K, H, W = mask.shape
+        flow = flow.float()
+        resid = all_pred_residual.float()
+        if self.allow_residual_resize and tuple(resid.shape[-2:]) != self.mask_size:
+            resid = F.interpolate(resid, self.mask_size, mode='bilinear')
+        with torch.no_grad(), torch.autocast(device_type="cuda", enabled=False):
+            feat = self.flow_feat_before_agg(flow)
+            assert feat.shape[2:] == mask.shape[2:], f"{feat.shape[2:]} != {mask.shape[2:]} (should match on spatial dimension)"
+            spec = self._spec(K, H, W, want_vis=True, vis_norm=False, clamp_fused=False)
+            _, vis = rcf_motion_loss(spec, mask.float().unsqueeze(1), [flow], [resid], feats=[feat], mlp=self._mlp_params())
+        return vis[1], vis[2], vis[3], (vis[4] if len(vis) > 4 else None)
+
+    def forward(self, imgs, masks, gt_fw_flows, gt_bw_flows, all_pred_residual_fw, all_pred_residual_bw):
+        """reference :312-399.  masks [B,2,K,H,W]; gt_*_flows [B,1,2,H,W]; residuals [B,2K,h,w]."""
+        flow_loss = {'seg_fw': 0., 'seg_bw': 0.}
+        flows: Dict[str, List[torch.Tensor]] = {'gt_flow': [], 'pred_flow': [], 'agg_flow': [],
+                                                'residual_adj': [], 'affine_flow': []}
+        batch_size, im_num, _, im_h, im_w = imgs.shape
+        assert im_num == 2, "Other im_num not implemented"           # :324
+
+        gt_fw_flow = gt_fw_flows[:, 0, ...]
+        gt_bw_flow = gt_bw_flows[:, 0, ...]
+        loss, vis = self._run(masks, [gt_fw_flow, gt_bw_flow], [all_pred_residual_fw, all_pred_residual_bw],
+                              want_vis=self.return_flows, vis_norm=True, inv_n=getattr(self, "_inv_n_override", 0.0))
+        flow_loss['seg_fw'] = loss[0]
+        flow_loss['seg_bw'] = loss[1]
+        if self.return_flows:
+            flows['gt_flow'].append(vis[0])
+            flows['pred_flow'].append(vis[1])
+            flows['agg_flow'].append(vis[2])
+            flows['residual_adj'].append(vis[3])
+            if len(vis) > 4:
+                flows['affine_flow'].append(vis[4])
+        flow_loss['seg'] = flow_loss['seg_fw'] + flow_loss['seg_bw']
+        return flows, flow_loss

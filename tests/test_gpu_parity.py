@@ -1,0 +1,276 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(ctypes -> librcf_loss.so); the checker is the committed golden fixtures (reference outputs) and the
+numpy oracle.  Tolerances (BASELINE.json north_star): loss <= 1e-5 relative, mask/residual
+gradients <= 1e-4 relative (rel-L2 over the tensor; per-element max-rel is meaningless at sign flips
+of d ~ 0).  For the ill-conditioned quadratic fit the bar is
+max(1e-4, the reference's own fp32 error against its fp64 run).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR, Golden, golden_names, rel_l2
+from oracle import rcf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def rcf():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import rcf_unsupvideoseg_b200 as pkg
+    pkg.load_library()          # fail loudly if the native library is missing
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return pkg
+
+
+def build_head(rcf, g: Golden):
+    head = rcf.FlowAggregationHeadWithResidual(args=None, create_flownet=True, **g.head_kwargs()).cuda()
+    head.load_state_dict({k: torch.from_numpy(v) for k, v in g.params.items()})
+    return head
+
+
+def run_head(head, inputs, gbar):
+    masks, fw, bw, rfw, rbw = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in inputs]
+    masks.requires_grad_(True); rfw.requires_grad_(True); rbw.requires_grad_(True)
+    imgs = torch.zeros(masks.shape[0], 2, 3, 8, 8, device="cuda")
+    for p in head.parameters():
+        p.grad = None
+    flows, loss = head(imgs, masks, fw, bw, rfw, rbw)
+    (loss["seg"] * gbar).backward()
+    torch.cuda.synchronize()
+    return flows, loss, dict(d_masks=masks.grad, d_resid_fw=rfw.grad, d_resid_bw=rbw.grad)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_head_matches_reference_golden(rcf, name):
+    g = Golden(name)
+    head = build_head(rcf, g)
+    flows, loss, grads = run_head(head, g.inputs, g.gbar)
+    for k in ("seg_fw", "seg_bw", "seg"):
+        ref = float(g.ref("f64", "loss." + k))
+        assert abs(float(loss[k]) - ref) <= LOSS_RTOL * abs(ref), (k, float(loss[k]), ref)
+    quad = g.kwargs.get("free_residual_with_affine_quadratic", False)
+    for k in ("d_masks", "d_resid_fw", "d_resid_bw"):
+        ref64 = g.ref("f64", k)
+        tol = GRAD_RTOL
+        if quad:
+            tol = max(tol, rel_l2(g.ref("f32", k), ref64))
+        err = rel_l2(grads[k].cpu().numpy(), ref64)
+        assert err <= tol, (k, err, tol)
+    for k, p in head.named_parameters():
+        ref64 = g.ref("f64", "dparam." + k)
+        err = rel_l2(p.grad.cpu().numpy(), ref64)
+        tol = max(2e-4, 2 * rel_l2(g.ref("f32", "dparam." + k), ref64))
+        assert err <= tol, (k, err, tol)
+    for k, v in flows.items():
+        if g.has("f64", "flows." + k):
+            assert len(v) == 1
+            assert rel_l2(v[0].cpu().numpy(), g.ref("f64", "flows." + k)) <= 2e-5, k
+        else:
+            assert v == []
+
+
+@pytest.mark.parametrize("D,robust,K", [(0, False, 4), (0, True, 3), (2, False, 4), (2, True, 2), (5, False, 3),
+                                         (0, False, 1), (2, False, 8), (0, False, 8)])
+def test_loss_core_theta_given_vs_oracle(rcf, D, robust, K):
+    """Scope L: theta supplied, no feature pooling (C-ABI theta_mode 0) against the numpy oracle."""
+    B, H, W = 3, 20, 24
+    cfg = O.OracleConfig(mask_layer=K, mask_size=(H, W), num_flow_feat_channels=4, clamp_flow_t=20.0,
+                         outlier_robust_loss=robust, free_residual=(D == 0), free_residual_with_affine=(D > 0),
+                         free_residual_with_affine_quadratic=(D == 5))
+    params = O.init_params(cfg, seed=3)
+    params["flow_feat_after_agg.2.weight"] = np.zeros_like(params["flow_feat_after_agg.2.weight"])
+    params["flow_feat_after_agg.2.bias"] = np.array([1.5, -2.25])
+    masks, fw, bw, rfw, rbw = O.synthetic_inputs(B, K, H, W, seed=11)
+    _, loss_o, caches = O.head_forward(masks, fw, bw, rfw, rbw, params, cfg)
+    g_o = O.head_backward(caches, params, gbar=1.3)
+
+    spec = rcf.LossSpec(K=K, H=H, W=W, D=D, Cf=0, robust=robust, clamp_t=20.0)
+    tm = torch.from_numpy(masks).cuda().requires_grad_(True)
+    flows = [torch.from_numpy(fw[:, 0]).cuda(), torch.from_numpy(bw[:, 0]).cuda()]
+    resids = [torch.from_numpy(rfw).cuda().requires_grad_(True), torch.from_numpy(rbw).cuda().requires_grad_(True)]
+    thetas = [torch.tensor([1.5, -2.25], device="cuda").view(1, 2, 1).expand(B, 2, K).contiguous().requires_grad_(True)
+              for _ in range(2)]
+    loss, _ = rcf.rcf_motion_loss(spec, tm, flows, resids, thetas=thetas)
+    (loss.sum() * 1.3).backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss[0]) - loss_o["seg_fw"]) <= LOSS_RTOL * loss_o["seg_fw"]
+    assert abs(float(loss[1]) - loss_o["seg_bw"]) <= LOSS_RTOL * loss_o["seg_bw"]
+    tol = GRAD_RTOL if D < 5 else 2e-3
+    assert rel_l2(tm.grad.cpu().numpy(), g_o["d_masks"]) <= tol
+    assert rel_l2(resids[0].grad.cpu().numpy(), g_o["d_resid_fw"]) <= tol
+    assert rel_l2(resids[1].grad.cpu().numpy(), g_o["d_resid_bw"]) <= tol
+    assert rel_l2(thetas[0].grad.cpu().numpy(), g_o["fw"]["d_theta"]) <= tol
+    assert rel_l2(thetas[1].grad.cpu().numpy(), g_o["bw"]["d_theta"]) <= tol
+
+
+def _torch_inputs(B, K, H, W, seed, device="cuda"):
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(B, 2, K, H, W, generator=g) * 2.0
+    masks = torch.softmax(logits, dim=2)
+    fw = torch.randn(B, 1, 2, H, W, generator=g) * 8.0
+    bw = torch.randn(B, 1, 2, H, W, generator=g) * 8.0
+    rfw = torch.randn(B, 2 * K, H, W, generator=g) * 5.0
+    rbw = torch.randn(B, 2 * K, H, W, generator=g) * 5.0
+    return [t.to(device) for t in (masks, fw, bw, rfw, rbw)]
+
+
+def _checksum(t):
+    t = t.double().cpu()
+    idx = torch.linspace(0, t.numel() - 1, 16).long()
+    return dict(sum=float(t.sum()), l2=float(t.norm()), abs_sum=float(t.abs().sum()),
+                sample=[float(x) for x in t.flatten()[idx]])
+
+
+@pytest.mark.parametrize("case", ["c1_free_l1_full_head", "c1_free_l1_proxy_head", "c1_affine_l1_proxy_head"])
+def test_full_size_c1_against_reference_scalars(rcf, case):
+    """BASELINE.json config C1 (B=2, K=4, 480x854): reference fp32 loss scalars and gradient checksums."""
+    with open(os.path.join(GOLDEN_DIR, "full_size_scalars.json")) as f:
+        ref = json.load(f)[case]
+    s = ref["shape"]
+    torch.manual_seed(ref["param_seed"])
+    head = rcf.FlowAggregationHeadWithResidual(args=None, create_flownet=True, mask_layer=s["K"],
+                                               mask_size=(s["H"], s["W"]), **ref["kwargs"]).cuda()
+    masks, fw, bw, rfw, rbw = _torch_inputs(s["B"], s["K"], s["H"], s["W"], ref["seed"])
+    masks.requires_grad_(True); rfw.requires_grad_(True); rbw.requires_grad_(True)
+    imgs = torch.zeros(s["B"], 2, 3, 8, 8, device="cuda")
+    flows, loss = head(imgs, masks, fw, bw, rfw, rbw)
+    loss["seg"].backward()
+    torch.cuda.synchronize()
+    for k in ("seg_fw", "seg_bw", "seg"):
+        assert abs(float(loss[k]) - ref["loss"][k]) <= LOSS_RTOL * abs(ref["loss"][k]), k
+    for name, t in (("d_masks", masks.grad), ("d_resid_fw", rfw.grad), ("d_resid_bw", rbw.grad),
+                    ("pred_flow", flows["pred_flow"][0])):
+        cs = _checksum(t)
+        assert abs(cs["l2"] - ref[name]["l2"]) <= GRAD_RTOL * ref[name]["l2"], name
+        assert abs(cs["abs_sum"] - ref[name]["abs_sum"]) <= GRAD_RTOL * ref[name]["abs_sum"], name
+        scale = ref[name]["l2"] / np.sqrt(t.numel())
+        for a, b in zip(cs["sample"], ref[name]["sample"]):
+            assert abs(a - b) <= 1e-3 * scale + 1e-4 * abs(b), (name, a, b)
+
+
+def test_full_size_properties(rcf):
+    """Size-independent properties at C2-like shapes: determinism, linearity in the upstream gradient,
+    batch-shard consistency and direction symmetry."""
+    B, K, H, W = 4, 4, 480, 854
+    masks, fw, bw, rfw, rbw = _torch_inputs(B, K, H, W, seed=5)
+    spec = rcf.LossSpec(K=K, H=H, W=W, D=2, Cf=0, clamp_t=20.0)
+    thetas = [torch.randn(B, 2, K, device="cuda") for _ in range(2)]
+
+    def run(m, f, r, th, gl, inv_n=0.0):
+        sp = spec if inv_n == 0.0 else rcf.LossSpec(K=K, H=H, W=W, D=2, Cf=0, clamp_t=20.0, inv_n=inv_n)
+        m = m.detach().clone().requires_grad_(True)
+        r = [x.detach().clone().requires_grad_(True) for x in r]
+        loss, _ = rcf.rcf_motion_loss(sp, m, f, r, thetas=th)
+        (loss * gl).sum().backward()
+        return loss.detach(), m.grad, [x.grad for x in r]
+
+    gl = torch.tensor([1.0, 1.0], device="cuda")
+    l1, dm1, dr1 = run(masks, [fw[:, 0], bw[:, 0]], [rfw, rbw], thetas, gl)
+    l2, dm2, dr2 = run(masks, [fw[:, 0], bw[:, 0]], [rfw, rbw], thetas, gl)
+    assert torch.equal(l1, l2) and torch.equal(dm1, dm2) and torch.equal(dr1[0], dr2[0])   # bit-reproducible
+    # linearity: scaling the upstream gradient scales every gradient
+    gl3 = torch.tensor([0.25, 3.0], device="cuda")
+    _, dm3, dr3 = run(masks, [fw[:, 0], bw[:, 0]], [rfw, rbw], thetas, gl3)
+    assert rel_l2(dm3[:, 0].cpu().numpy(), 0.25 * dm1[:, 0].cpu().numpy()) < 1e-6
+    assert rel_l2(dm3[:, 1].cpu().numpy(), 3.0 * dm1[:, 1].cpu().numpy()) < 1e-6
+    assert rel_l2(dr3[1].cpu().numpy(), 3.0 * dr1[1].cpu().numpy()) < 1e-6
+    # direction symmetry: swapping the two directions swaps the two losses
+    ls, dms, _ = run(masks.flip(1), [bw[:, 0], fw[:, 0]], [rbw, rfw], thetas[::-1], gl)
+    assert torch.equal(ls.flip(0), l1) and torch.equal(dms.flip(1), dm1)
+    # batch sharding (multi-GPU layout): halves with the global normaliser reproduce the full batch
+    inv_n = 1.0 / (B * 2 * H * W)
+    h = B // 2
+    parts = [run(masks[i:i + h], [fw[i:i + h, 0], bw[i:i + h, 0]], [rfw[i:i + h], rbw[i:i + h]],
+                 [t[i:i + h] for t in thetas], gl, inv_n) for i in (0, h)]
+    lsum = parts[0][0] + parts[1][0]
+    assert torch.allclose(lsum, l1, rtol=1e-6, atol=0)
+    assert torch.equal(torch.cat([parts[0][1], parts[1][1]], 0), dm1)
+
+
+def test_vector_and_scalar_paths_agree(rcf):
+    """Odd widths / misaligned views take the scalar path; results must match the 128-bit path."""
+    B, K, H, W = 2, 4, 16, 20
+    masks, fw, bw, rfw, rbw = _torch_inputs(B, K, H, W, seed=9)
+    spec = rcf.LossSpec(K=K, H=H, W=W, D=2, Cf=0, clamp_t=20.0, robust=True)
+    thetas = [torch.randn(B, 2, K, device="cuda") for _ in range(2)]
+
+    def run(shift):
+        def mis(t):  # same values, storage shifted by `shift` floats => not 16-byte aligned
+            buf = torch.empty(t.numel() + 8, device="cuda")
+            v = buf[shift:shift + t.numel()].view(t.shape)
+            v.copy_(t)
+            return v
+        m = mis(masks).requires_grad_(True)
+        r = [mis(rfw).requires_grad_(True), mis(rbw).requires_grad_(True)]
+        loss, _ = rcf.rcf_motion_loss(spec, m, [mis(fw[:, 0]), mis(bw[:, 0])], r, thetas=thetas)
+        loss.sum().backward()
+        return loss.detach(), m.grad, r[0].grad
+
+    la, dma, dra = run(0)
+    lb, dmb, drb = run(1)
+    assert torch.allclose(la, lb, rtol=1e-6)
+    assert rel_l2(dmb.cpu().numpy(), dma.cpu().numpy()) < 1e-6
+    assert rel_l2(drb.cpu().numpy(), dra.cpu().numpy()) < 1e-6
+
+
+def test_batch_strided_mask_views_and_amp(rcf):
+    g = Golden("free_l1")
+    head = build_head(rcf, g)
+    masks, fw, bw, rfw, rbw = [torch.from_numpy(a).cuda() for a in g.inputs]
+    imgs = torch.zeros(masks.shape[0], 2, 3, 8, 8, device="cuda")
+    _, ref = head(imgs, masks, fw, bw, rfw, rbw)
+    # masks as a strided slice of a larger buffer (batch stride != 2*K*H*W)
+    big = torch.zeros(masks.shape[0], 3, *masks.shape[2:], device="cuda")
+    big[:, :2] = masks
+    _, l2 = head(imgs, big[:, :2], fw, bw, rfw, rbw)
+    assert torch.equal(l2["seg"], ref["seg"])
+    with torch.autocast("cuda", dtype=torch.float16):
+        _, l3 = head(imgs, masks.half(), fw, bw, rfw.half(), rbw.half())
+    assert l3["seg"].dtype == torch.float32
+    assert abs(float(l3["seg"]) - float(ref["seg"])) < 2e-2 * float(ref["seg"])
+
+
+def test_error_behaviour(rcf):
+    head = rcf.FlowAggregationHeadWithResidual(args=None, create_flownet=True, mask_layer=2, mask_size=(8, 8)).cuda()
+    x = torch.rand(1, 2, 2, 8, 8, device="cuda")
+    with pytest.raises(UnboundLocalError):            # reference :305-310
+        head(torch.zeros(1, 2, 3, 8, 8), x, torch.zeros(1, 1, 2, 8, 8, device="cuda"),
+             torch.zeros(1, 1, 2, 8, 8, device="cuda"), torch.zeros(1, 4, 8, 8, device="cuda"),
+             torch.zeros(1, 4, 8, 8, device="cuda"))
+    head = rcf.FlowAggregationHeadWithResidual(args=None, create_flownet=True, mask_layer=2, mask_size=(8, 8),
+                                               free_residual=True).cuda()
+    with pytest.raises(AssertionError):               # reference :324
+        head(torch.zeros(1, 3, 3, 8, 8), x, None, None, None, None)
+    spec = rcf.LossSpec(K=9, H=8, W=8)
+    with pytest.raises(RuntimeError, match="not compiled"):
+        rcf.rcf_motion_loss(spec, torch.rand(1, 1, 9, 8, 8, device="cuda"), [torch.zeros(1, 2, 8, 8, device="cuda")],
+                            [torch.zeros(1, 18, 8, 8, device="cuda")], thetas=[torch.zeros(1, 2, 9, device="cuda")])
+
+
+def test_helper_methods_vs_oracle(rcf):
+    g = Golden("affine_l1")
+    head = build_head(rcf, g)
+    cfg = O.OracleConfig(**g.head_kwargs())
+    params = {k: v.astype(np.float64) for k, v in g.params.items()}
+    masks, fw, bw, rfw, rbw = g.inputs
+    c = O.direction_forward(masks[:, 0], fw[:, 0], rfw, params, cfg)
+    flow_prepared = torch.from_numpy(O.prepare_flow(fw[:, 0], cfg).astype(np.float32)).cuda()
+    B, _, K, H, W = masks.shape
+    overall, agg, res, aff = head.aggregate_flow_with_residual(torch.from_numpy(masks[:, 0]).cuda(), flow_prepared,
+                                                               torch.from_numpy(rfw).cuda())
+    assert rel_l2(overall.cpu().numpy().reshape(B, 2, -1), c.pred) < 2e-5
+    assert rel_l2(agg.cpu().numpy().reshape(B, 2, -1), c.agg) < 2e-5
+    assert rel_l2(res.cpu().numpy().reshape(B, 2, -1), c.res) < 2e-5
+    assert rel_l2(aff.cpu().numpy().reshape(B, 2, -1), c.aff) < 2e-5
+    aff2 = head.get_demean_affine_flow(torch.from_numpy(masks[:, 0]).cuda(), flow_prepared)
+    assert rel_l2(aff2.cpu().numpy().reshape(B, 2, -1), c.aff) < 2e-5
