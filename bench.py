@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- RCF motion loss fwd+bwd throughput on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload (config C2 of BASELINE.json, per GPU): B=16 samples (frame pairs), K=4 soft masks, 480x854,
+stage-1 DAVIS flags (free_residual, L1, clamp_flow_t=20, s=tau=10; configs/rcf/rcf_stage1.yaml:99-111),
+synthetic inputs of SURVEY.md 8(d).  Weak scaling: every rank owns its own B=16 shard; the mean's
+normaliser is the global element count, so the per-rank losses SUM to the global loss with one NCCL
+all-reduce of 2 floats per step (issued asynchronously, off the critical path).
+
+  value  : device-resident loss core (theta supplied = SURVEY 8(d) "Scope L"): rcf_forward + rcf_backward
+           through the C ABI, samples/s over all ranks, CUDA-event timed, max over ranks.
+  e2e    : the drop-in nn.Module call (FlowAggregationHeadWithResidual with the loss-core proxy feature
+           branch Cf=2,k=1 of SURVEY 8(d)) fed from PINNED HOST buffers every step: H2D of masks/flows/
+           residuals, fwd+bwd, D2H of the loss scalars and of the mask/residual gradients.
+  roofline: dominant kernel k_bwd (streaming backward): algorithmic bytes per launch / mean CUDA-event
+           duration of that kernel inside the timed region (library timing hook), vs MEASURED_PEAKS.json.
+  cpu_baseline: oracle/torch_port.py (op-for-op PyTorch CPU port of the reference head, pinned to the
+           reference's outputs by tests) on the host cores, bounded sample (B=2), rank 0, N=1 only.
+--impl reference times that CPU port alone on the same config (the reference itself is Python under
+/root/reference, which does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "RCF loss fwd+bwd frames/sec and % HBM roofline at 1/2/4/8 B200 vs host-CPU ref"
+UNIT = "samples/s"
+B_PER_GPU, K, H, W = 16, 4, 480, 854
+HEAD_KW = dict(mask_layer=K, mask_size=(H, W), free_residual=True, clamp_flow_t=20.0,
+               num_flow_feat_channels=2, flow_feat_before_agg_kernel_size=1)
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": f"C2: RCF loss fwd+bwd, B={B_PER_GPU}/GPU, K={K}, {H}x{W}, free_residual+L1+clamp20 (stage-1 DAVIS flags)",
+        "value_path": "loss core, theta supplied (SURVEY 8d Scope L), C ABI rcf_forward+rcf_backward, device-resident",
+        "e2e_path": "drop-in head, proxy feature branch Cf=2 k=1, pinned host buffers in, loss+grads out",
+        "global_batch": B_PER_GPU * n_gpus, "parallelism": f"batch-sharded x{n_gpus}",
+        "l2_policy": "inputs (735 MB/GPU) larger than L2 (126 MB); no flush needed",
+        "algorithmic_bytes_per_sample": 2 * H * W * (36 * K + 16),
+    }
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _reasons(self):
+        nv = self.nv
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:  # noqa: BLE001
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            except Exception:  # noqa: BLE001
+                return
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        for bit, name in names.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self._reasons()
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# ------------------------------------------------------------------------------------------------
+def cpu_port_time(steps, warmup, budget_s=150.0):
+    """Times oracle/torch_port.py (the reference's op sequence in PyTorch CPU) on a bounded sample."""
+    import torch
+
+    from oracle.torch_port import PortedHead, synthetic_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = 2
+    torch.manual_seed(1)
+    head = PortedHead(**HEAD_KW)
+    masks, fw, bw, rfw, rbw = synthetic_inputs(Bs, K, H, W, seed=0)
+    masks.requires_grad_(True); rfw.requires_grad_(True); rbw.requires_grad_(True)
+    imgs = torch.zeros(Bs, 2, 3, 8, 8)
+
+    def step():
+        for t in (masks, rfw, rbw):
+            t.grad = None
+        _, loss = head(imgs, masks, fw, bw, rfw, rbw)
+        loss["seg"].backward()
+        return float(loss["seg"].detach())
+
+    t0 = time.perf_counter(); step(); first = time.perf_counter() - t0
+    steps = max(1, min(steps, int(budget_s / max(first, 1e-3))))
+    for _ in range(max(0, warmup - 1)):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); step(); times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return {"value": Bs / mean, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"B={Bs} of the C2 workload ({K=}, {H}x{W}, proxy head Cf=2 k=1), {len(times)} timed steps, "
+                      f"mean {mean * 1e3:.1f} ms/step, best {min(times) * 1e3:.1f} ms; torch {torch.__version__} CPU, "
+                      f"{cores} threads"}, mean, steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, mean, steps = cpu_port_time(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import rcf_unsupvideoseg_b200 as pkg
+    from rcf_unsupvideoseg_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = pkg.load_library(build_if_missing=False)
+
+    B = B_PER_GPU
+    P = H * W
+    inv_n = 1.0 / (B * world * 2 * P)
+    from oracle.torch_port import synthetic_inputs   # input generator only (torch CPU generator)
+    masks_h, fw_h, bw_h, rfw_h, rbw_h = synthetic_inputs(B, K, H, W, seed=rank)
+    masks = masks_h.to(dev).requires_grad_(True)
+    fw, bw = fw_h.to(dev), bw_h.to(dev)
+    rfw = rfw_h.to(dev).requires_grad_(True)
+    rbw = rbw_h.to(dev).requires_grad_(True)
+    g = torch.Generator().manual_seed(100 + rank)
+    thetas = [torch.randn(B, 2, K, generator=g).to(dev).requires_grad_(True) for _ in range(2)]
+    spec = pkg.LossSpec(K=K, H=H, W=W, D=0, Cf=0, clamp_t=20.0, inv_n=inv_n)
+    flows = [fw[:, 0], bw[:, 0]]
+    gl = torch.ones(2, device=dev)
+    inputs = [masks, rfw, rbw, *thetas]
+    pending = []
+
+    def step():
+        loss, _ = pkg.rcf_motion_loss(spec, masks, flows, [rfw, rbw], thetas=thetas)
+        grads = torch.autograd.grad(loss, inputs, grad_outputs=gl)
+        if world > 1:
+            lr = loss.detach().clone()
+            pending.append((dist.all_reduce(lr, async_op=True), lr))
+        return loss, grads
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # kernel timing hook: one event pair per timed step around k_bwd
+    ev_pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev_pairs:      # materialise the handles
+        a.record(); b.record()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        start.record()
+        for i in range(args.steps):
+            lib.rcf_debug_time_kernel(3, ev_pairs[i][0].cuda_event, ev_pairs[i][1].cuda_event)
+            loss, grads = step()
+        end.record()
+        lib.rcf_debug_time_kernel(0, None, None)
+        barrier()
+    for w, _ in pending:
+        w.wait()
+    ms_total = start.elapsed_time(end)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t) / args.steps
+    value = B * world / (ms_step * 1e-3)
+    kb_ms = sorted(a.elapsed_time(b) for a, b in ev_pairs)
+    kb_mean = sum(kb_ms) / len(kb_ms)
+    loss_val = [float(x) for x in loss.detach().cpu()]
+
+    # e2e through the drop-in module, pinned host buffers in / loss + grads out
+    torch.manual_seed(1)
+    head = pkg.FlowAggregationHeadWithResidual(args=None, create_flownet=True, **HEAD_KW).to(dev)
+    head.return_flows = False
+    head._inv_n_override = inv_n
+    pin = [t.pin_memory() for t in (masks_h, fw_h, bw_h, rfw_h, rbw_h)]
+    d_in = [torch.empty_like(t, device=dev) for t in pin]
+    out_pin = [torch.empty(2, dtype=torch.float32).pin_memory(), torch.empty_like(masks_h).pin_memory(),
+               torch.empty_like(rfw_h).pin_memory(), torch.empty_like(rbw_h).pin_memory()]
+    imgs = torch.zeros(B, 2, 3, 8, 8)
+    h2d = sum(t.numel() * 4 for t in pin)
+    d2h = sum(t.numel() * 4 for t in out_pin)
+
+    def e2e_step():
+        for d, s in zip(d_in, pin):
+            d.copy_(s, non_blocking=True)
+        m = d_in[0].requires_grad_(True)
+        r1 = d_in[3].requires_grad_(True)
+        r2 = d_in[4].requires_grad_(True)
+        _, fl = head(imgs, m, d_in[1], d_in[2], r1, r2)
+        lvec = torch.stack([fl["seg_fw"], fl["seg_bw"]])
+        gm, g1, g2 = torch.autograd.grad(fl["seg"], [m, r1, r2])
+        out_pin[0].copy_(lvec.detach(), non_blocking=True)
+        out_pin[1].copy_(gm, non_blocking=True)
+        out_pin[2].copy_(g1, non_blocking=True)
+        out_pin[3].copy_(g2, non_blocking=True)
+        for t_ in (d_in[0], d_in[3], d_in[4]):
+            t_.requires_grad_(False)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2.record()
+    barrier()
+    t2 = torch.tensor([s2.elapsed_time(e2)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2) / e2e_steps
+    e2e_val = B * world / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        bytes_sample = 2 * P * (36 * K + 16)
+        kb_bytes = B * 2 * P * ((4 * K + 8 + 8 * K) + (4 * K + 8 * K))       # k_bwd: re-read inputs + write dM, dR
+        achieved = kb_bytes / (kb_mean * 1e-3) / 1e9
+        step_gbs = B * bytes_sample / (ms_step * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "gpu_launches": 7 * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_bwd<K=4,D=0,PX=4> (streaming backward)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": kb_mean, "kernel_ms_min": kb_ms[0],
+                         "algorithmic_bytes_per_launch": kb_bytes},
+            "step_roofline": {"algorithmic_gbs": step_gbs, "frac": step_gbs / peak,
+                              "frame_directions_per_s": 2 * value},
+            "loss": loss_val,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _, _ = cpu_port_time(3, 1, budget_s=30.0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,18 @@ RCF_API int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss, v
 RCF_API int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const float* grad_loss, const void* ctx,
                  void* ws, const RcfGrads* grads, void* stream);
 
+/* Measurement hook (bench.py): record the two caller-owned cudaEvent_t handles immediately before and
+ * after the launch of streaming kernel `which` in the following rcf_forward / rcf_backward calls of this
+ * process (on the stream those calls are given).  which: 0 off, 1 k_moments, 2 k_loss, 3 k_bwd,
+ * 4 k_pool, 5 k_pool_bwd.  Has no effect on results. */
+#define RCF_TIME_OFF 0
+#define RCF_TIME_MOMENTS 1
+#define RCF_TIME_LOSS 2
+#define RCF_TIME_BWD 3
+#define RCF_TIME_POOL 4
+#define RCF_TIME_POOL_BWD 5
+RCF_API int rcf_debug_time_kernel(int which, void* start_event, void* stop_event);
+
 #ifdef __cplusplus
 }
 #endif

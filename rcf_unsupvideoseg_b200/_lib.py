@@ -53,7 +53,8 @@ class RcfGrads(C.Structure):
     ]
 
 
-EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "rcf_forward", "rcf_backward")
+EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "rcf_forward", "rcf_backward",
+                    "rcf_debug_time_kernel")
 
 _lib = None
 _lock = threading.Lock()
@@ -95,6 +96,8 @@ def load_library(build_if_missing: bool = True):
         lib.rcf_backward.restype = C.c_int
         lib.rcf_backward.argtypes = [C.POINTER(RcfDesc), C.POINTER(RcfInputs), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(RcfGrads), C.c_void_p]
+        lib.rcf_debug_time_kernel.restype = C.c_int
+        lib.rcf_debug_time_kernel.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         if lib.rcf_abi_version() != RCF_ABI_VERSION:
             raise RcfLibraryError(f"ABI mismatch: library {lib.rcf_abi_version()} vs binding {RCF_ABI_VERSION}")
         _lib = lib

@@ -86,7 +86,26 @@ bool vec_ok_inputs(const RcfDesc& d, const RcfInputs& in, bool with_feat) {
     return true;
 }
 
+struct TimeHook { int which = 0; cudaEvent_t start = nullptr, stop = nullptr; };
+TimeHook g_hook;   // process-wide: autograd runs rcf_backward on its own device thread
+
+struct ScopedTime {
+    cudaStream_t s; bool on;
+    ScopedTime(int which, cudaStream_t st) : s(st), on(g_hook.which == which && g_hook.start && g_hook.stop) {
+        if (on) cudaEventRecord(g_hook.start, s);
+    }
+    ~ScopedTime() { if (on) cudaEventRecord(g_hook.stop, s); }
+};
+
 }  // namespace
+
+extern "C" int rcf_debug_time_kernel(int which, void* start_event, void* stop_event) {
+    if (which < 0 || which > 5) return RCF_ERR_MODE;
+    g_hook.which = which;
+    g_hook.start = static_cast<cudaEvent_t>(start_event);
+    g_hook.stop = static_cast<cudaEvent_t>(stop_event);
+    return RCF_OK;
+}
 
 extern "C" int rcf_abi_version(void) { return RCF_ABI_VERSION; }
 
@@ -136,10 +155,10 @@ extern "C" int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss
             if (p && (!aligned16(p) || desc->vis_bstride % 4 || desc->vis_dstride % 4)) vec = false;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    RCF_CUDA(rcf_launch_moments(a, vec, s));
-    if (desc->theta_mode == 1) RCF_CUDA(rcf_launch_pool(a, vec_ok_inputs(*desc, *in, true), s));
+    { ScopedTime t(RCF_TIME_MOMENTS, s); RCF_CUDA(rcf_launch_moments(a, vec, s)); }
+    if (desc->theta_mode == 1) { ScopedTime t(RCF_TIME_POOL, s); RCF_CUDA(rcf_launch_pool(a, vec_ok_inputs(*desc, *in, true), s)); }
     RCF_CUDA(rcf_launch_segment_fwd(a, s));
-    RCF_CUDA(rcf_launch_loss(a, vec, s));
+    { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_loss(a, vec, s)); }
     RCF_CUDA(rcf_launch_finalize(a, s));
     return RCF_OK;
 }
@@ -177,9 +196,9 @@ extern "C" int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const floa
     bool any_dmask = false;
     for (int i = 0; i < desc->ndir; ++i) any_dmask |= (a.dmask[i] != nullptr);
     if (desc->theta_mode == 1 && (any_dmask || any_dfeat)) {
-        RCF_CUDA(rcf_launch_pool_bwd(a, vec_pool, s));
+        { ScopedTime t(RCF_TIME_POOL_BWD, s); RCF_CUDA(rcf_launch_pool_bwd(a, vec_pool, s)); }
         a.add_dmask = 1;
     }
-    RCF_CUDA(rcf_launch_bwd(a, vec, s));
+    { ScopedTime t(RCF_TIME_BWD, s); RCF_CUDA(rcf_launch_bwd(a, vec, s)); }
     return RCF_OK;
 }

@@ -219,8 +219,9 @@ def test_vector_and_scalar_paths_agree(rcf):
     la, dma, dra = run(0)
     lb, dmb, drb = run(1)
     assert torch.allclose(la, lb, rtol=1e-6)
-    assert rel_l2(dmb.cpu().numpy(), dma.cpu().numpy()) < 1e-6
-    assert rel_l2(drb.cpu().numpy(), dra.cpu().numpy()) < 1e-6
+    # different partial-sum chunking between the two paths => fp32 rounding noise only
+    assert rel_l2(dmb.cpu().numpy(), dma.cpu().numpy()) < 2e-5
+    assert rel_l2(drb.cpu().numpy(), dra.cpu().numpy()) < 2e-5
 
 
 def test_batch_strided_mask_views_and_amp(rcf):

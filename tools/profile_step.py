@@ -1,0 +1,76 @@
+"""Run a few device-resident loss-core steps (the bench.py `value` path) -- target for ncu captures.
+
+    ncu --set full --clock-control none --import-source on -k regex:k_bwd -s 2 -c 2 -o gpurun_out/prof \
+        python tools/profile_step.py --steps 3
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import rcf_unsupvideoseg_b200 as pkg  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=16)
+    ap.add_argument("--K", type=int, default=4)
+    ap.add_argument("--H", type=int, default=480)
+    ap.add_argument("--W", type=int, default=854)
+    ap.add_argument("--D", type=int, default=0)
+    ap.add_argument("--robust", action="store_true")
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--time", action="store_true", help="print CUDA-event time per step and per kernel")
+    a = ap.parse_args()
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev).manual_seed(0)
+    B, K, H, W = a.B, a.K, a.H, a.W
+    masks = torch.softmax(torch.randn(B, 2, K, H, W, device=dev, generator=g) * 2, dim=2).requires_grad_(True)
+    flows = [torch.randn(B, 2, H, W, device=dev, generator=g) * 8 for _ in range(2)]
+    resids = [(torch.randn(B, 2 * K, H, W, device=dev, generator=g) * 5).requires_grad_(True) for _ in range(2)]
+    thetas = [torch.randn(B, 2, K, device=dev, generator=g).requires_grad_(True) for _ in range(2)]
+    spec = pkg.LossSpec(K=K, H=H, W=W, D=a.D, Cf=0, clamp_t=20.0, robust=a.robust)
+    gl = torch.ones(2, device=dev)
+    lib = pkg.load_library()
+
+    def step():
+        loss, _ = pkg.rcf_motion_loss(spec, masks, flows, resids, thetas=thetas)
+        return loss, torch.autograd.grad(loss, [masks, *resids, *thetas], grad_outputs=gl)
+
+    if not a.time:
+        for _ in range(a.steps):
+            loss, _ = step()
+        torch.cuda.synchronize()
+        print("loss", loss.tolist())
+        return
+    P = H * W
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(a.steps):
+        step()
+    e.record(); torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / a.steps
+    alg = B * 2 * P * (36 * K + 16)
+    print(f"step {ms:.4f} ms  {B / ms * 1e3:.0f} samples/s  algorithmic {alg / ms / 1e6:.0f} GB/s")
+    names = {1: ("k_moments", 4 * K + (8 if a.D else 0)), 2: ("k_loss", 12 * K + 8), 3: ("k_bwd", 24 * K + 8)}
+    for which, (name, bpp) in names.items():
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        for x, y in evs:
+            x.record(); y.record()
+        for x, y in evs:
+            lib.rcf_debug_time_kernel(which, x.cuda_event, y.cuda_event)
+            step()
+        lib.rcf_debug_time_kernel(0, None, None)
+        torch.cuda.synchronize()
+        t = sorted(x.elapsed_time(y) for x, y in evs)
+        mean = sum(t) / len(t)
+        print(f"  {name:10s} mean {mean * 1e3:8.1f} us  min {t[0] * 1e3:8.1f} us  {B * 2 * P * bpp / mean / 1e6:7.0f} GB/s (algorithmic {bpp} B/px)")
+
+
+if __name__ == "__main__":
+    main()
