@@ -7,12 +7,12 @@
 //   dR_ck    = g_c * (s/div) * (1 - T_ck^2) * m_k                      (or g_c * m_k when unbounded)
 //   dM_k     = sum_c g_c (theta_ck + A_kc.v_k + s T_ck)
 //              + f_k^T B_k v_k + v_k^T C_k v_k + mubar_k.v_k + c0_k    (B, C, mubar, c0 pre-divided by S_k)
-//              [+ the pooled-feature term already stored in dM by k_pool_bwd]
+//              [the pooled-feature term is added afterwards by k_pool_bwd]
 // HBM-bound: algorithmic bytes per pixel = (4K + 8 + 8K) read + (4K + 8K) written.
 #include "rcf_common.cuh"
 
 template <int K, int D, int PX>
-__global__ void __launch_bounds__(RCF_BLOCK) k_bwd(const RcfK a) {
+__global__ void __launch_bounds__(RCF_BLOCK, (K <= 4 && D <= 2) ? 2 : 1) k_bwd(const RcfK a) {
     constexpr int CF = rcf_cf(D);
     constexpr int CB = rcf_cb(D);
     constexpr int ITER = RCF_CHUNK_BWD / (RCF_BLOCK * PX);
@@ -51,64 +51,74 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_bwd(const RcfK a) {
             for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int k = 0; k < K; ++k) Pack<PX>::ld(r[c][k], resid + (long long)(c * K + k) * P + p);
-            float dm[K][PX];
-            if (a.add_dmask && dmask) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) Pack<PX>::ld(dm[k], dmask + (long long)k * P + p);
-            } else {
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-#pragma unroll
-                    for (int j = 0; j < PX; ++j) dm[k][j] = 0.0f;
-            }
             float y[PX], x[PX];
             if constexpr (D > 0) px_coords<PX>(p, a, y, x);
 
+            // ---- phase 1: recompute T (kept in r) and pred, segment-outer ------------------------
+            float g[2][PX];
 #pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                float u[DD];
-                if constexpr (D > 0) px_feats<D>(y[j], x[j], u);
-                float fc[2];
-                fc[0] = clamp_flow(f[0][j], a.clamp_t);
-                fc[1] = clamp_flow(f[1][j], a.clamp_t);
-                // q_ck = theta_ck + A_kc.v_k + s*T_ck ; r[c][k][j] is overwritten by T_ck
-                float qv[2][K];
-                float pred[2] = {0.0f, 0.0f};
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float* ck = cf + k * CF;
+                for (int j = 0; j < PX; ++j) g[c][j] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float ck[CF];
+#pragma unroll
+                for (int i = 0; i < CF; ++i) ck[i] = cf[k * CF + i];
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    float u[DD];
+                    if constexpr (D > 0) px_feats<D>(y[j], x[j], u);
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         const float t = a.unbounded ? r[c][k][j] : tanh_scaled(r[c][k][j], a.ex2_scale);
                         r[c][k][j] = t;
-                        float qq = fmaf(a.scale, t, ck[c]);
+                        float q = fmaf(a.scale, t, ck[c]);
                         if constexpr (D > 0) {
 #pragma unroll
-                            for (int d = 0; d < D; ++d) qq = fmaf(ck[2 + c * D + d], u[d] - ck[2 + 2 * D + d], qq);
+                            for (int d = 0; d < D; ++d) q = fmaf(ck[2 + c * D + d], u[d] - ck[2 + 2 * D + d], q);
                         }
-                        qv[c][k] = qq;
-                        pred[c] = fmaf(m[k][j], qq, pred[c]);
+                        g[c][j] = fmaf(m[k][j], q, g[c][j]);
                     }
                 }
-                float g[2];
+            }
+            // ---- g_c = gs * phi'(F_c - pred_c); f keeps the clamped flow -------------------------
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    const float fc = clamp_flow(f[c][j], a.clamp_t);
+                    f[c][j] = fc;
                     float phi, w;
-                    loss_terms(fc[c] - pred[c], a, phi, w);
-                    g[c] = gs * w;
+                    loss_terms(fc - g[c][j], a, phi, w);
+                    g[c][j] = gs * w;
                 }
+            // ---- phase 2: gradients, segment-outer; each segment's outputs are stored at once ----
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
+            for (int k = 0; k < K; ++k) {
+                float ck[CF], bk[CB];
+#pragma unroll
+                for (int i = 0; i < CF; ++i) ck[i] = cf[k * CF + i];
+#pragma unroll
+                for (int i = 0; i < CB; ++i) bk[i] = cb[k * CB + i];
+                float dm[PX];
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
                     const float mk = m[k][j];
-                    float acc = dm[k][j] + fmaf(g[0], qv[0][k], g[1] * qv[1][k]);
-                    const float* bk = cb + k * CB;
+                    const float t0 = r[0][k][j], t1 = r[1][k][j];
+                    float q0 = fmaf(a.scale, t0, ck[0]), q1 = fmaf(a.scale, t1, ck[1]);
+                    float acc = bk[CB - 1];
                     if constexpr (D > 0) {
                         // bk: muF[2], B[2][D], Csym[D(D+1)/2], mubar[D], c0
-                        const float* ck = cf + k * CF;
-                        const float ff0 = fc[0] - bk[0], ff1 = fc[1] - bk[1];
-                        float v[D];
+                        float u[DD], v[DD];
+                        px_feats<D>(y[j], x[j], u);
 #pragma unroll
-                        for (int d = 0; d < D; ++d) v[d] = u[d] - ck[2 + 2 * D + d];
+                        for (int d = 0; d < D; ++d) {
+                            v[d] = u[d] - ck[2 + 2 * D + d];
+                            q0 = fmaf(ck[2 + d], v[d], q0);
+                            q1 = fmaf(ck[2 + D + d], v[d], q1);
+                        }
+                        const float ff0 = f[0][j] - bk[0], ff1 = f[1][j] - bk[1];
 #pragma unroll
                         for (int d = 0; d < D; ++d) {
                             float lin = fmaf(ff0, bk[2 + d], fmaf(ff1, bk[2 + D + d], bk[2 + 2 * D + D * (D + 1) / 2 + d]));
@@ -117,24 +127,20 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_bwd(const RcfK a) {
                             acc = fmaf(lin, v[d], acc);
                         }
                     }
-                    acc += bk[CB - 1];
-                    dm[k][j] = acc;
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const float t = r[c][k][j];
-                        r[c][k][j] = a.unbounded ? g[c] * mk : g[c] * a.dres_scale * fmaf(-t, t, 1.0f) * mk;
+                    dm[j] = fmaf(g[0][j], q0, fmaf(g[1][j], q1, acc));
+                    if (a.unbounded) {
+                        r[0][k][j] = g[0][j] * mk;
+                        r[1][k][j] = g[1][j] * mk;
+                    } else {
+                        r[0][k][j] = g[0][j] * a.dres_scale * fmaf(-t0, t0, 1.0f) * mk;
+                        r[1][k][j] = g[1][j] * a.dres_scale * fmaf(-t1, t1, 1.0f) * mk;
                     }
                 }
-            }
-            if (dmask) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) Pack<PX>::st(dmask + (long long)k * P + p, dm[k]);
-            }
-            if (dresid) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int k = 0; k < K; ++k) Pack<PX>::st(dresid + (long long)(c * K + k) * P + p, r[c][k]);
+                if (dmask) Pack<PX>::st(dmask + (long long)k * P + p, dm);
+                if (dresid) {
+                    Pack<PX>::st(dresid + (long long)k * P + p, r[0][k]);
+                    Pack<PX>::st(dresid + (long long)(K + k) * P + p, r[1][k]);
+                }
             }
         }
     }

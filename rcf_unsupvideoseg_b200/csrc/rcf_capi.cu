@@ -193,12 +193,13 @@ extern "C" int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const floa
     a.dw1 = grads->dw1; a.db1 = grads->db1; a.dw2 = grads->dw2; a.db2 = grads->db2;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     RCF_CUDA(rcf_launch_segment_bwd(a, s));
+    { ScopedTime t(RCF_TIME_BWD, s); RCF_CUDA(rcf_launch_bwd(a, vec, s)); }
     bool any_dmask = false;
     for (int i = 0; i < desc->ndir; ++i) any_dmask |= (a.dmask[i] != nullptr);
     if (desc->theta_mode == 1 && (any_dmask || any_dfeat)) {
-        { ScopedTime t(RCF_TIME_POOL_BWD, s); RCF_CUDA(rcf_launch_pool_bwd(a, vec_pool, s)); }
-        a.add_dmask = 1;
+        // adds the pooled-feature term onto dmask (read-modify-write) and writes dfeat
+        ScopedTime t(RCF_TIME_POOL_BWD, s);
+        RCF_CUDA(rcf_launch_pool_bwd(a, vec_pool, s));
     }
-    { ScopedTime t(RCF_TIME_BWD, s); RCF_CUDA(rcf_launch_bwd(a, vec, s)); }
     return RCF_OK;
 }

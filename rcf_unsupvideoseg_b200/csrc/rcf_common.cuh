@@ -127,7 +127,6 @@ struct RcfK {
     float* dmask[2]; float* dresid[2]; float* dfeat[2]; float* dtheta[2];
     long long dmask_bs[2], dresid_bs[2], dfeat_bs[2];
     float *dw1, *db1, *dw2, *db2;
-    int add_dmask;   // dmask already holds the pooled-feature term (written by k_pool_bwd)
 };
 
 #ifdef __CUDACC__
@@ -138,12 +137,17 @@ template <> struct Pack<4> {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
+    static __device__ __forceinline__ void ld_rw(float (&v)[4], const float* p) {   // coherent (buffer is also written)
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
     static __device__ __forceinline__ void st(float* p, const float (&v)[4]) {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
 };
 template <> struct Pack<1> {
     static __device__ __forceinline__ void ld(float (&v)[1], const float* p) { v[0] = __ldg(p); }
+    static __device__ __forceinline__ void ld_rw(float (&v)[1], const float* p) { v[0] = *p; }
     static __device__ __forceinline__ void st(float* p, const float (&v)[1]) { *p = v[0]; }
 };
 

@@ -8,13 +8,15 @@
 //   phi(F_c - pred_c) summed for the mean                         [:359-368]
 // and, in the same pass, the "gradient moments" sum_p w_c m_k and sum_p w_c m_k (u - mu_k)
 // (w = phi'), which is everything the per-segment backward needs, so the
-// backward never has to reduce anything.  Optionally writes the visualisation flows [:370-395].
+// backward never has to reduce anything.  VIS instantiations also write the visualisation flows [:370-395].
 //
-// HBM-bound: algorithmic bytes per pixel = 4K + 8 + 8K read (+ up to 40 written when vis is on).
+// Loop order is segment-outer / pixel-inner so that one segment's coefficients are live at a time
+// (register pressure decides occupancy here: see DESIGN.md).
+// HBM-bound: algorithmic bytes per pixel = 4K + 8 + 8K read (+ up to 40 written when VIS).
 #include "rcf_common.cuh"
 
-template <int K, int D, int PX>
-__global__ void __launch_bounds__(RCF_BLOCK) k_loss(const RcfK a) {
+template <int K, int D, int PX, bool VIS>
+__global__ void __launch_bounds__(RCF_BLOCK, (K <= 4 && D <= 2) ? 2 : 1) k_loss(const RcfK a) {
     constexpr int CF = rcf_cf(D);
     constexpr int GM = rcf_gm(K, D);
     constexpr int ITER = RCF_CHUNK_LOSS / (RCF_BLOCK * PX);
@@ -35,8 +37,6 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_loss(const RcfK a) {
     for (int i = tid; i < K * CF; i += RCF_BLOCK) cf[i] = a.coef[(size_t)fd * K * CF + i];
     __syncthreads();
 
-    const bool want_vis = (a.vis_gt != nullptr) | (a.vis_pred != nullptr) | (a.vis_agg != nullptr) |
-                          (a.vis_res != nullptr) | (a.vis_aff != nullptr);
     const long long vis_off = (long long)b * a.vis_bs + (long long)dir * a.vis_ds;
 
     float acc[GM];
@@ -60,69 +60,102 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_loss(const RcfK a) {
             float y[PX], x[PX];
             if constexpr (D > 0) px_coords<PX>(p, a, y, x);
 
-            float o_gt[2][PX], o_pred[2][PX], o_agg[2][PX], o_res[2][PX], o_aff[2][PX];
+            float pred[2][PX], agg[2][PX], aff[2][PX];
 #pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                float u[DD];
-                if constexpr (D > 0) px_feats<D>(y[j], x[j], u);
-                float agg[2] = {0.0f, 0.0f}, aff[2] = {0.0f, 0.0f}, res[2] = {0.0f, 0.0f};
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
+                for (int j = 0; j < PX; ++j) { pred[c][j] = 0.0f; agg[c][j] = 0.0f; aff[c][j] = 0.0f; }
+
+            // ---- phase 1: reconstruct (segment-outer) -------------------------------------------
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float ck[CF];
+#pragma unroll
+                for (int i = 0; i < CF; ++i) ck[i] = cf[k * CF + i];
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
                     const float mk = m[k][j];
-                    const float* ck = cf + k * CF;
+                    float u[DD];
+                    if constexpr (D > 0) px_feats<D>(y[j], x[j], u);
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        agg[c] = fmaf(mk, ck[c], agg[c]);
-                        if constexpr (D > 0) {
-                            float av = 0.0f;
-#pragma unroll
-                            for (int d = 0; d < D; ++d) av = fmaf(ck[2 + c * D + d], u[d] - ck[2 + 2 * D + d], av);
-                            aff[c] = fmaf(mk, av, aff[c]);
-                        }
                         const float t = a.unbounded ? r[c][k][j] : tanh_scaled(r[c][k][j], a.ex2_scale);
-                        res[c] = fmaf(mk, t, res[c]);
-                    }
-                }
-                float w[2];
+                        if constexpr (VIS) {
+                            agg[c][j] = fmaf(mk, ck[c], agg[c][j]);
+                            pred[c][j] = fmaf(mk, t, pred[c][j]);          // residual part (unscaled)
+                            if constexpr (D > 0) {
+                                float av = 0.0f;
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const float fc = clamp_flow(f[c][j], a.clamp_t);
-                    res[c] *= a.scale;
-                    const float pred = agg[c] + aff[c] + res[c];
-                    float phi;
-                    loss_terms(fc - pred, a, phi, w[c]);
-                    acc[0] += phi;
-                    o_gt[c][j] = fc; o_pred[c][j] = pred; o_agg[c][j] = agg[c]; o_res[c][j] = res[c]; o_aff[c][j] = aff[c];
-                }
+                                for (int d = 0; d < D; ++d) av = fmaf(ck[2 + c * D + d], u[d] - ck[2 + 2 * D + d], av);
+                                aff[c][j] = fmaf(mk, av, aff[c][j]);
+                            }
+                        } else {
+                            float q = fmaf(a.scale, t, ck[c]);
+                            if constexpr (D > 0) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const float wm = w[c] * m[k][j];
-                        acc[1 + c * K + k] += wm;
-                        if constexpr (D > 0) {
-#pragma unroll
-                            for (int d = 0; d < D; ++d)
-                                acc[1 + 2 * K + (k * 2 + c) * D + d] =
-                                    fmaf(wm, u[d] - cf[k * CF + 2 + 2 * D + d], acc[1 + 2 * K + (k * 2 + c) * D + d]);
+                                for (int d = 0; d < D; ++d) q = fmaf(ck[2 + c * D + d], u[d] - ck[2 + 2 * D + d], q);
+                            }
+                            pred[c][j] = fmaf(mk, q, pred[c][j]);
                         }
                     }
                 }
             }
-            if (want_vis) {
+            // ---- loss value and derivative weights (w overwrites f) -------------------------------
+            float o_gt[2][PX], o_res[2][PX];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    const float fc = clamp_flow(f[c][j], a.clamp_t);
+                    if constexpr (VIS) {
+                        o_gt[c][j] = fc;
+                        o_res[c][j] = pred[c][j] * a.scale;
+                        pred[c][j] = agg[c][j] + aff[c][j] + o_res[c][j];
+                    }
+                    float phi, w;
+                    loss_terms(fc - pred[c][j], a, phi, w);
+                    acc[0] += phi;
+                    f[c][j] = w;
+                }
+            // ---- phase 2: gradient moments (segment-outer) --------------------------------------
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float mu[DD];
+                if constexpr (D > 0) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) mu[d] = cf[k * CF + 2 + 2 * D + d];
+                }
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    const float wm0 = f[0][j] * m[k][j], wm1 = f[1][j] * m[k][j];
+                    acc[1 + k] += wm0;
+                    acc[1 + K + k] += wm1;
+                    if constexpr (D > 0) {
+                        float u[DD];
+                        px_feats<D>(y[j], x[j], u);
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            const float v = u[d] - mu[d];
+                            acc[1 + 2 * K + (k * 2 + 0) * D + d] = fmaf(wm0, v, acc[1 + 2 * K + (k * 2 + 0) * D + d]);
+                            acc[1 + 2 * K + (k * 2 + 1) * D + d] = fmaf(wm1, v, acc[1 + 2 * K + (k * 2 + 1) * D + d]);
+                        }
+                    }
+                }
+            }
+            if constexpr (VIS) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const float sc = a.vis_scale[c];
                     const long long o = vis_off + (long long)c * P + p;
 #pragma unroll
                     for (int j = 0; j < PX; ++j) {
-                        o_gt[c][j] *= sc; o_pred[c][j] *= sc; o_agg[c][j] *= sc; o_res[c][j] *= sc; o_aff[c][j] *= sc;
+                        o_gt[c][j] *= sc; pred[c][j] *= sc; agg[c][j] *= sc; o_res[c][j] *= sc; aff[c][j] *= sc;
                     }
                     if (a.vis_gt) Pack<PX>::st(a.vis_gt + o, o_gt[c]);
-                    if (a.vis_pred) Pack<PX>::st(a.vis_pred + o, o_pred[c]);
-                    if (a.vis_agg) Pack<PX>::st(a.vis_agg + o, o_agg[c]);
+                    if (a.vis_pred) Pack<PX>::st(a.vis_pred + o, pred[c]);
+                    if (a.vis_agg) Pack<PX>::st(a.vis_agg + o, agg[c]);
                     if (a.vis_res) Pack<PX>::st(a.vis_res + o, o_res[c]);
-                    if (D > 0 && a.vis_aff) Pack<PX>::st(a.vis_aff + o, o_aff[c]);
+                    if (D > 0 && a.vis_aff) Pack<PX>::st(a.vis_aff + o, aff[c]);
                 }
             }
         }
@@ -145,8 +178,14 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_loss(const RcfK a) {
 template <int K, int D>
 static cudaError_t launch_kd(const RcfK& a, bool vec, cudaStream_t s) {
     dim3 grid(a.nchunk2, a.nfd), block(RCF_BLOCK);
-    if (vec) k_loss<K, D, 4><<<grid, block, 0, s>>>(a);
-    else k_loss<K, D, 1><<<grid, block, 0, s>>>(a);
+    const bool vis = a.vis_gt || a.vis_pred || a.vis_agg || a.vis_res || a.vis_aff;
+    if (vis) {
+        if (vec) k_loss<K, D, 4, true><<<grid, block, 0, s>>>(a);
+        else k_loss<K, D, 1, true><<<grid, block, 0, s>>>(a);
+    } else {
+        if (vec) k_loss<K, D, 4, false><<<grid, block, 0, s>>>(a);
+        else k_loss<K, D, 1, false><<<grid, block, 0, s>>>(a);
+    }
     return cudaGetLastError();
 }
 

@@ -6,7 +6,8 @@
 // channel at a time) reuses it.  Cf x K is a skinny contraction (K <= 8): bandwidth-bound, CUDA cores.
 //
 // Backward: dG[f,p] = sum_k c[f,k] M[k,p]   and   dM[k,p] += sum_f c[f,k] G[f,p],  c = Poolbar / S.
-// Thread-per-pixel-pack mapping: G is read once, dG written once, the dM term is kept in registers.
+// Thread-per-pixel-pack mapping: G is read once, dG written once, the dM term is accumulated in registers
+// on top of what the streaming backward (k_bwd, launched before) already stored.
 #include "rcf_common.cuh"
 
 template <int K, int PX, int CHUNK>
@@ -83,8 +84,12 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         Pack<PX>::ld(m[k], mask + (long long)k * P + p);
+        if (dmask) {   // accumulate onto what k_bwd wrote earlier on this stream
+            Pack<PX>::ld_rw(dm[k], dmask + (long long)k * P + p);
+        } else {
 #pragma unroll
-        for (int j = 0; j < PX; ++j) dm[k][j] = 0.0f;
+            for (int j = 0; j < PX; ++j) dm[k][j] = 0.0f;
+        }
     }
 #pragma unroll 4
     for (int f = 0; f < Cf; ++f) {

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--robust", action="store_true")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--time", action="store_true", help="print CUDA-event time per step and per kernel")
+    ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
     a = ap.parse_args()
     dev = torch.device("cuda")
     g = torch.Generator(device=dev).manual_seed(0)
@@ -50,13 +51,35 @@ def main():
         step()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     s.record()
+    t0 = time.perf_counter()
     for _ in range(a.steps):
         step()
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / a.steps
     e.record(); torch.cuda.synchronize()
     ms = s.elapsed_time(e) / a.steps
     alg = B * 2 * P * (36 * K + 16)
-    print(f"step {ms:.4f} ms  {B / ms * 1e3:.0f} samples/s  algorithmic {alg / ms / 1e6:.0f} GB/s")
+    print(f"step {ms:.4f} ms  {B / ms * 1e3:.0f} samples/s  algorithmic {alg / ms / 1e6:.0f} GB/s  (cpu enqueue {cpu_ms:.3f} ms/step)")
+    if a.graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss_g, grads_g = step()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        s.record()
+        for _ in range(a.steps):
+            g.replay()
+        e.record(); torch.cuda.synchronize()
+        msg = s.elapsed_time(e) / a.steps
+        print(f"graph step {msg:.4f} ms  {B / msg * 1e3:.0f} samples/s  algorithmic {alg / msg / 1e6:.0f} GB/s  loss {loss_g.tolist()}")
     names = {1: ("k_moments", 4 * K + (8 if a.D else 0)), 2: ("k_loss", 12 * K + 8), 3: ("k_bwd", 24 * K + 8)}
     for which, (name, bpp) in names.items():
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
