@@ -100,7 +100,7 @@ class ClockSampler:
                 self._reasons()
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.025)
 
     def __enter__(self):
         if self.nv is not None:
@@ -223,7 +223,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # kernel timing hook: one event pair per timed step around k_bwd
+    # Timed region A (eager): K steps with the library's timing hook around k_bwd -> roofline of the dominant kernel.
+    # Timed region B (CUDA graph): the same step captured once and replayed K times -> `value`
+    # (falls back to region A's time if capture is not possible).
     ev_pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in ev_pairs:      # materialise the handles
         a.record(); b.record()
@@ -233,19 +235,59 @@ def run_ours(args):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         start.record()
+        t0 = time.perf_counter()
         for i in range(args.steps):
             lib.rcf_debug_time_kernel(3, ev_pairs[i][0].cuda_event, ev_pairs[i][1].cuda_event)
             loss, grads = step()
+        cpu_enqueue_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         end.record()
         lib.rcf_debug_time_kernel(0, None, None)
         barrier()
-    for w, _ in pending:
-        w.wait()
-    ms_total = start.elapsed_time(end)
-    t = torch.tensor([ms_total], device=dev)
+        for w, _ in pending:
+            w.wait()
+        pending.clear()
+        eager_ms = start.elapsed_time(end) / args.steps
+
+        graph_ms = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            for w, _ in pending:
+                w.wait()
+            pending.clear()
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            world_saved = world
+            with torch.cuda.graph(g_):
+                loss_g, grads_g = pkg.rcf_motion_loss(spec, masks, flows, [rfw, rbw], thetas=thetas)
+                grads_g = torch.autograd.grad(loss_g, inputs, grad_outputs=gl)
+            for _ in range(3):
+                g_.replay()
+            barrier()
+            gs_, ge_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            gs_.record()
+            for _ in range(args.steps):
+                g_.replay()
+                if world_saved > 1:      # the per-step loss all-reduce stays outside the graph, asynchronous
+                    lr = loss_g.detach().clone()
+                    pending.append((dist.all_reduce(lr, async_op=True), lr))
+            ge_.record()
+            barrier()
+            for w, _ in pending:
+                w.wait()
+            pending.clear()
+            graph_ms = gs_.elapsed_time(ge_) / args.steps
+            loss = loss_g
+        except Exception as ex:  # noqa: BLE001
+            print(f"[bench] CUDA graph capture unavailable ({type(ex).__name__}: {ex}); using eager timing", file=sys.stderr)
+    best_ms = eager_ms if graph_ms is None else min(graph_ms, eager_ms)
+    t = torch.tensor([best_ms, eager_ms, graph_ms if graph_ms is not None else -1.0], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t) / args.steps
+    ms_step, eager_ms, graph_ms = float(t[0]), float(t[1]), float(t[2])
     value = B * world / (ms_step * 1e-3)
     kb_ms = sorted(a.elapsed_time(b) for a, b in ev_pairs)
     kb_mean = sum(kb_ms) / len(kb_ms)
@@ -316,13 +358,83 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": kb_bytes},
             "step_roofline": {"algorithmic_gbs": step_gbs, "frac": step_gbs / peak,
                               "frame_directions_per_s": 2 * value},
+            "timing": {"eager_ms_per_step": eager_ms, "cuda_graph_ms_per_step": (graph_ms if graph_ms > 0 else None),
+                       "cpu_enqueue_ms_per_step": cpu_enqueue_ms,
+                       "value_from": "cuda_graph" if (graph_ms > 0 and graph_ms <= eager_ms) else "eager"},
             "loss": loss_val,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _, _ = cpu_port_time(3, 1, budget_s=30.0)
+            line["cpu_baseline"], _, _ = cpu_port_time(20, 2, budget_s=25.0)
+            if not args.no_extras:
+                line["extras"] = extras(pkg, dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _time_cuda(fn, steps, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / steps
+
+
+def extras(pkg, dev):
+    """Add-on measurements reported beside the headline (SURVEY.md 8(d) 'report separately'):
+    the same workloads through (a) the drop-in head and (b) the op-for-op PyTorch port of the reference
+    running EAGER ON THE SAME GPU (the GPU baseline the reference user has today)."""
+    import torch
+
+    from oracle.torch_port import PortedHead, synthetic_inputs
+    out = {}
+    cases = {
+        "c2_proxy_head_B16_480x854": (16, 4, 480, 854, dict(free_residual=True, clamp_flow_t=20.0, num_flow_feat_channels=2,
+                                                             flow_feat_before_agg_kernel_size=1), 10),
+        "c2_affine_proxy_head_B16_480x854": (16, 4, 480, 854, dict(free_residual_with_affine=True, clamp_flow_t=20.0,
+                                                                   num_flow_feat_channels=2,
+                                                                   flow_feat_before_agg_kernel_size=1), 10),
+        "c1_full_head_B2_480x854": (2, 4, 480, 854, dict(free_residual=True, clamp_flow_t=20.0), 5),
+        "davis_stage1_train_B8_96x96_full_head": (8, 4, 96, 96, dict(free_residual=True, clamp_flow_t=20.0), 50),
+        "stv2_stage1_train_B8_48x48_affine_full_head": (8, 4, 48, 48, dict(free_residual_with_affine=True, clamp_flow_t=20.0), 50),
+    }
+    for name, (B_, K_, H_, W_, kw, steps) in cases.items():
+        try:
+            ins = synthetic_inputs(B_, K_, H_, W_, seed=0, device=dev)
+            imgs = torch.zeros(B_, 2, 3, 8, 8)
+            res = {}
+            for impl in ("ours", "torch_eager_port"):
+                torch.manual_seed(1)
+                if impl == "ours":
+                    head = pkg.FlowAggregationHeadWithResidual(args=None, create_flownet=True, mask_layer=K_,
+                                                               mask_size=(H_, W_), **kw).to(dev)
+                else:
+                    head = PortedHead(mask_layer=K_, mask_size=(H_, W_), **kw).to(dev)
+                m = ins[0].clone().requires_grad_(True)
+                r1 = ins[3].clone().requires_grad_(True)
+                r2 = ins[4].clone().requires_grad_(True)
+                params = list(head.parameters())
+
+                def fn():
+                    _, l = head(imgs, m, ins[1], ins[2], r1, r2)
+                    torch.autograd.grad(l["seg"], [m, r1, r2, *params])
+
+                ms = _time_cuda(fn, steps)
+                res[impl] = {"ms_per_step": ms, "samples_per_s": B_ / ms * 1e3}
+                del head
+                torch.cuda.empty_cache()
+            res["speedup_vs_torch_eager"] = res["torch_eager_port"]["ms_per_step"] / res["ours"]["ms_per_step"]
+            out[name] = res
+        except Exception as ex:  # noqa: BLE001
+            out[name] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+            torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -332,6 +444,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the add-on measurements (full head, eager PyTorch on the same GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -10,11 +10,15 @@
 // HBM-bound: algorithmic bytes per pixel = 4K (+8 with the affine fit).
 #include "rcf_common.cuh"
 
+// Segments are processed in groups of KG (as many as keep KG*NS accumulators in registers); inside a
+// group the loop is pixel-outer so that all KG mask loads (+ the flow) of an iteration are in flight
+// together and the warp reductions happen once per CTA, not once per segment.
 template <int K, int D, int PX>
 __global__ void __launch_bounds__(RCF_BLOCK) k_moments(const RcfK a) {
     constexpr int NS = rcf_ns(D);
     constexpr int ITER = RCF_CHUNK_MOM / (RCF_BLOCK * PX);
     constexpr int DD = D > 0 ? D : 1;
+    constexpr int KG = (D == 0) ? K : (D == 2 ? (K < 4 ? K : 4) : 1);
     __shared__ float red[RCF_WARPS][K * NS];
 
     const int fd = blockIdx.y;
@@ -27,20 +31,26 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_moments(const RcfK a) {
     const int P = a.P;
     const int p0 = chunk * RCF_CHUNK_MOM;
 
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += KG) {
+        float acc[KG][NS];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        float acc[NS];
+        for (int k = 0; k < KG; ++k)
 #pragma unroll
-        for (int s = 0; s < NS; ++s) acc[s] = 0.0f;
+            for (int s = 0; s < NS; ++s) acc[k][s] = 0.0f;
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const int p = p0 + (it * RCF_BLOCK + tid) * PX;
             if (p < P) {
-                float m[PX];
-                Pack<PX>::ld(m, mask + (long long)k * P + p);
+                float m[KG][PX];
+#pragma unroll
+                for (int k = 0; k < KG; ++k)
+                    if (k0 + k < K) Pack<PX>::ld(m[k], mask + (long long)(k0 + k) * P + p);
                 if constexpr (D == 0) {
 #pragma unroll
-                    for (int j = 0; j < PX; ++j) acc[0] += m[j];
+                    for (int k = 0; k < KG; ++k)
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) acc[k][0] += m[k][j];
                 } else {
                     float f0[PX], f1[PX], y[PX], x[PX];
                     Pack<PX>::ld(f0, flow + p);
@@ -50,30 +60,41 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_moments(const RcfK a) {
                     for (int j = 0; j < PX; ++j) {
                         float u[DD];
                         px_feats<D>(y[j], x[j], u);
-                        const float mj = m[j];
-                        const float g0 = mj * clamp_flow(f0[j], a.clamp_t);
-                        const float g1 = mj * clamp_flow(f1[j], a.clamp_t);
-                        acc[0] += mj;
-                        acc[1] += g0;
-                        acc[2] += g1;
+                        const float c0 = clamp_flow(f0[j], a.clamp_t), c1 = clamp_flow(f1[j], a.clamp_t);
 #pragma unroll
-                        for (int d = 0; d < D; ++d) {
-                            const float mu = mj * u[d];
-                            acc[3 + d] += mu;
-                            acc[3 + D + d] = fmaf(g0, u[d], acc[3 + D + d]);
-                            acc[3 + 2 * D + d] = fmaf(g1, u[d], acc[3 + 2 * D + d]);
+                        for (int k = 0; k < KG; ++k) {
+                            if (k0 + k < K) {
+                                const float mj = m[k][j];
+                                const float g0 = mj * c0, g1 = mj * c1;
+                                acc[k][0] += mj;
+                                acc[k][1] += g0;
+                                acc[k][2] += g1;
 #pragma unroll
-                            for (int e = d; e < D; ++e)
-                                acc[3 + 3 * D + rcf_sym_idx(D, d, e)] = fmaf(mu, u[e], acc[3 + 3 * D + rcf_sym_idx(D, d, e)]);
+                                for (int d = 0; d < D; ++d) {
+                                    const float mu = mj * u[d];
+                                    acc[k][3 + d] += mu;
+                                    acc[k][3 + D + d] = fmaf(g0, u[d], acc[k][3 + D + d]);
+                                    acc[k][3 + 2 * D + d] = fmaf(g1, u[d], acc[k][3 + 2 * D + d]);
+#pragma unroll
+                                    for (int e = d; e < D; ++e)
+                                        acc[k][3 + 3 * D + rcf_sym_idx(D, d, e)] =
+                                            fmaf(mu, u[e], acc[k][3 + 3 * D + rcf_sym_idx(D, d, e)]);
+                                }
+                            }
                         }
                     }
                 }
             }
         }
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const float v = warp_sum(acc[s]);
-            if (lane == 0) red[warp][k * NS + s] = v;
+        for (int k = 0; k < KG; ++k) {
+            if (k0 + k < K) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const float v = warp_sum(acc[k][s]);
+                    if (lane == 0) red[warp][(k0 + k) * NS + s] = v;
+                }
+            }
         }
     }
     __syncthreads();

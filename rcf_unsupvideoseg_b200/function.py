@@ -62,6 +62,19 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+_SIZE_CACHE = {}
+
+
+def _sizes(lib, desc, spec, B, ndir):
+    key = (spec.K, spec.H, spec.W, spec.D, spec.Cf, B, ndir)
+    hit = _SIZE_CACHE.get(key)
+    if hit is None:
+        ctx_bytes, ws_bytes = C.c_size_t(), C.c_size_t()
+        _lib.check(lib.rcf_query_sizes(C.byref(desc), C.byref(ctx_bytes), C.byref(ws_bytes)), "rcf_query_sizes")
+        hit = _SIZE_CACHE[key] = (ctx_bytes.value, ws_bytes.value)
+    return hit
+
+
 def _make_desc(spec: LossSpec, B: int, ndir: int) -> _lib.RcfDesc:
     d = _lib.RcfDesc()
     d.B, d.K, d.H, d.W, d.Cf, d.D, d.ndir = B, spec.K, spec.H, spec.W, spec.Cf, spec.D, ndir
@@ -137,10 +150,9 @@ class RcfMotionLossFn(torch.autograd.Function):
         if spec.Cf > 0:
             inp.w1, inp.b1, inp.w2, inp.b2 = (t.data_ptr() for t in (w1c, b1c, w2c, b2c))
 
-        ctx_bytes, ws_bytes = C.c_size_t(), C.c_size_t()
-        _lib.check(lib.rcf_query_sizes(C.byref(desc), C.byref(ctx_bytes), C.byref(ws_bytes)), "rcf_query_sizes")
-        ctx_buf = torch.empty(ctx_bytes.value, dtype=torch.uint8, device=dev)
-        ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+        ctx_bytes, ws_bytes = _sizes(lib, desc, spec, B, ndir)
+        ctx_buf = torch.empty(ctx_bytes, dtype=torch.uint8, device=dev)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         loss = torch.empty(ndir, dtype=torch.float32, device=dev)
 
         vis_tensors: Tuple[torch.Tensor, ...] = ()
@@ -227,9 +239,8 @@ class RcfMotionLossFn(torch.autograd.Function):
                   torch.empty(2, Cf, 1, dtype=torch.float32, device=dev), torch.empty(2, dtype=torch.float32, device=dev)]
             grads.dw1, grads.db1, grads.dw2, grads.db2 = (t.data_ptr() for t in dw)
 
-        ctx_bytes, ws_bytes = C.c_size_t(), C.c_size_t()
-        _lib.check(lib.rcf_query_sizes(C.byref(desc), C.byref(ctx_bytes), C.byref(ws_bytes)), "rcf_query_sizes")
-        ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+        _, ws_bytes = _sizes(lib, desc, spec, B, ndir)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         gl = grad_loss.detach().to(torch.float32).contiguous()
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
