@@ -100,10 +100,11 @@ class ClockSampler:
                 self._reasons()
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.025)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         if self.nv is not None:
+            self._stop.clear()
             self._t = threading.Thread(target=self._loop, daemon=True)
             self._t.start()
         return self
@@ -112,6 +113,7 @@ class ClockSampler:
         self._stop.set()
         if self._t is not None:
             self._t.join()
+            self._t = None
 
     def summary(self):
         if not self.samples:
@@ -233,7 +235,8 @@ def run_ours(args):
         step()
     barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    clocks = ClockSampler(local_rank)
+    with clocks:
         start.record()
         t0 = time.perf_counter()
         for i in range(args.steps):
@@ -243,46 +246,45 @@ def run_ours(args):
         end.record()
         lib.rcf_debug_time_kernel(0, None, None)
         barrier()
-        for w, _ in pending:
-            w.wait()
-        pending.clear()
-        eager_ms = start.elapsed_time(end) / args.steps
+    for w, _ in pending:
+        w.wait()
+    pending.clear()
+    eager_ms = start.elapsed_time(end) / args.steps
 
-        graph_ms = None
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step()
-            torch.cuda.current_stream().wait_stream(side)
-            for w, _ in pending:
-                w.wait()
-            pending.clear()
-            torch.cuda.synchronize()
-            g_ = torch.cuda.CUDAGraph()
-            world_saved = world
-            with torch.cuda.graph(g_):
-                loss_g, grads_g = pkg.rcf_motion_loss(spec, masks, flows, [rfw, rbw], thetas=thetas)
-                grads_g = torch.autograd.grad(loss_g, inputs, grad_outputs=gl)
-            for _ in range(3):
-                g_.replay()
-            barrier()
-            gs_, ge_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    graph_ms = None
+    try:   # capture with the NVML sampler thread stopped; only the replay loop is sampled
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            pkg.rcf_motion_loss(spec, masks, flows, [rfw, rbw], thetas=thetas)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_, capture_error_mode="thread_local"):
+            loss_g, _ = pkg.rcf_motion_loss(spec, masks, flows, [rfw, rbw], thetas=thetas)
+            grads_g = torch.autograd.grad(loss_g, inputs, grad_outputs=gl)
+        for _ in range(3):
+            g_.replay()
+        barrier()
+        gs_, ge_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with clocks:
             gs_.record()
             for _ in range(args.steps):
                 g_.replay()
-                if world_saved > 1:      # the per-step loss all-reduce stays outside the graph, asynchronous
+                if world > 1:      # the per-step loss all-reduce stays outside the graph, asynchronous
                     lr = loss_g.detach().clone()
                     pending.append((dist.all_reduce(lr, async_op=True), lr))
             ge_.record()
             barrier()
-            for w, _ in pending:
-                w.wait()
-            pending.clear()
-            graph_ms = gs_.elapsed_time(ge_) / args.steps
-            loss = loss_g
-        except Exception as ex:  # noqa: BLE001
-            print(f"[bench] CUDA graph capture unavailable ({type(ex).__name__}: {ex}); using eager timing", file=sys.stderr)
+        for w, _ in pending:
+            w.wait()
+        pending.clear()
+        graph_ms = gs_.elapsed_time(ge_) / args.steps
+        loss = loss_g
+    except Exception as ex:  # noqa: BLE001
+        print(f"[bench] CUDA graph capture unavailable ({type(ex).__name__}: {str(ex)[:300]}); using eager timing",
+              file=sys.stderr)
+        torch.cuda.synchronize()
     best_ms = eager_ms if graph_ms is None else min(graph_ms, eager_ms)
     t = torch.tensor([best_ms, eager_ms, graph_ms if graph_ms is not None else -1.0], device=dev)
     if world > 1:

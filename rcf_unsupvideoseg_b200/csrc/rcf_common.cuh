@@ -162,6 +162,45 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+// Deterministic warp reduction of a vector of N accumulators in ~N shuffles instead of 5N:
+// recursive halving (each lane keeps half of its values and sends the other half to its partner at
+// lane distance OFF), then plain butterflies once a lane is down to one value.
+template <int C, int OFF>
+__device__ __forceinline__ float warp_reduce_pow2(const float (&v)[C], int lane) {
+    if constexpr (C == 1) {
+        float x = v[0];
+#pragma unroll
+        for (int o = OFF; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        return x;
+    } else {
+        float h[C / 2];
+        const bool upper = (lane & OFF) != 0;
+#pragma unroll
+        for (int i = 0; i < C / 2; ++i) {
+            const float send = upper ? v[i] : v[i + C / 2];
+            const float keep = upper ? v[i + C / 2] : v[i];
+            h[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        return warp_reduce_pow2<C / 2, OFF / 2>(h, lane);
+    }
+}
+// Reduce acc[0..N) over the warp and store total i to dst[i] (one lane per value writes).
+template <int N, int BASE = 0>
+__device__ __forceinline__ void warp_reduce_store(const float (&acc)[N], int lane, float* dst) {
+    if constexpr (BASE < N) {
+        constexpr int REM = N - BASE;
+        constexpr int C = REM > 16 ? 32 : REM > 8 ? 16 : REM > 4 ? 8 : REM > 2 ? 4 : REM > 1 ? 2 : 1;
+        constexpr int SH = C == 32 ? 0 : C == 16 ? 1 : C == 8 ? 2 : C == 4 ? 3 : C == 2 ? 4 : 5;
+        float v[C];
+#pragma unroll
+        for (int i = 0; i < C; ++i) v[i] = (BASE + i < N) ? acc[BASE + i] : 0.0f;
+        const float tot = warp_reduce_pow2<C, 16>(v, lane);
+        const int idx = lane >> SH;
+        if ((lane & ((1 << SH) - 1)) == 0 && BASE + idx < N) dst[BASE + idx] = tot;
+        warp_reduce_store<N, BASE + 32>(acc, lane, dst);
+    }
+}
+
 __device__ __forceinline__ float fast_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

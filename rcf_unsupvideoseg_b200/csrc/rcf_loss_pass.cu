@@ -161,11 +161,7 @@ __global__ void __launch_bounds__(RCF_BLOCK, (K <= 4 && D <= 2) ? 2 : 1) k_loss(
         }
     }
 
-#pragma unroll
-    for (int s = 0; s < GM; ++s) {
-        const float v = warp_sum(acc[s]);
-        if (lane == 0) red[warp][s] = v;
-    }
+    warp_reduce_store<GM>(acc, lane, red[warp]);
     __syncthreads();
     for (int i = tid; i < GM; i += RCF_BLOCK) {
         float v = 0.0f;

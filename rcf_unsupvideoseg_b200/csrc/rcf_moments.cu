@@ -33,24 +33,27 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_moments(const RcfK a) {
 
 #pragma unroll 1
     for (int k0 = 0; k0 < K; k0 += KG) {
-        float acc[KG][NS];
+        float acc[KG * NS];
 #pragma unroll
-        for (int k = 0; k < KG; ++k)
-#pragma unroll
-            for (int s = 0; s < NS; ++s) acc[k][s] = 0.0f;
+        for (int i = 0; i < KG * NS; ++i) acc[i] = 0.0f;
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const int p = p0 + (it * RCF_BLOCK + tid) * PX;
             if (p < P) {
                 float m[KG][PX];
 #pragma unroll
-                for (int k = 0; k < KG; ++k)
+                for (int k = 0; k < KG; ++k) {
                     if (k0 + k < K) Pack<PX>::ld(m[k], mask + (long long)(k0 + k) * P + p);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) m[k][j] = 0.0f;
+                    }
+                }
                 if constexpr (D == 0) {
 #pragma unroll
                     for (int k = 0; k < KG; ++k)
 #pragma unroll
-                        for (int j = 0; j < PX; ++j) acc[k][0] += m[k][j];
+                        for (int j = 0; j < PX; ++j) acc[k] += m[k][j];
                 } else {
                     float f0[PX], f1[PX], y[PX], x[PX];
                     Pack<PX>::ld(f0, flow + p);
@@ -58,41 +61,41 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_moments(const RcfK a) {
                     px_coords<PX>(p, a, y, x);
 #pragma unroll
                     for (int j = 0; j < PX; ++j) {
-                        float u[DD];
+                        // z = (1, F0, F1, u, F0*u, F1*u, u_d*u_e): shared by all segments, then acc += m_k * z
+                        float z[NS], u[DD];
                         px_feats<D>(y[j], x[j], u);
-                        const float c0 = clamp_flow(f0[j], a.clamp_t), c1 = clamp_flow(f1[j], a.clamp_t);
+                        z[0] = 1.0f;
+                        z[1] = clamp_flow(f0[j], a.clamp_t);
+                        z[2] = clamp_flow(f1[j], a.clamp_t);
+#pragma unroll
+                        for (int d = 0; d < D; ++d) {
+                            z[3 + d] = u[d];
+                            z[3 + D + d] = z[1] * u[d];
+                            z[3 + 2 * D + d] = z[2] * u[d];
+#pragma unroll
+                            for (int e = d; e < D; ++e) z[3 + 3 * D + rcf_sym_idx(D, d, e)] = u[d] * u[e];
+                        }
 #pragma unroll
                         for (int k = 0; k < KG; ++k) {
-                            if (k0 + k < K) {
-                                const float mj = m[k][j];
-                                const float g0 = mj * c0, g1 = mj * c1;
-                                acc[k][0] += mj;
-                                acc[k][1] += g0;
-                                acc[k][2] += g1;
+                            acc[k * NS] += m[k][j];
 #pragma unroll
-                                for (int d = 0; d < D; ++d) {
-                                    const float mu = mj * u[d];
-                                    acc[k][3 + d] += mu;
-                                    acc[k][3 + D + d] = fmaf(g0, u[d], acc[k][3 + D + d]);
-                                    acc[k][3 + 2 * D + d] = fmaf(g1, u[d], acc[k][3 + 2 * D + d]);
-#pragma unroll
-                                    for (int e = d; e < D; ++e)
-                                        acc[k][3 + 3 * D + rcf_sym_idx(D, d, e)] =
-                                            fmaf(mu, u[e], acc[k][3 + 3 * D + rcf_sym_idx(D, d, e)]);
-                                }
-                            }
+                            for (int s2 = 1; s2 < NS; ++s2) acc[k * NS + s2] = fmaf(m[k][j], z[s2], acc[k * NS + s2]);
                         }
                     }
                 }
             }
         }
+        // one vector reduction per group; rows past K (padding of the last group) are never stored
+        if (k0 + KG <= K) {
+            warp_reduce_store<KG * NS>(acc, lane, &red[warp][k0 * NS]);
+        } else {
 #pragma unroll
-        for (int k = 0; k < KG; ++k) {
-            if (k0 + k < K) {
+            for (int k = 0; k < KG; ++k) {
+                if (k0 + k < K) {
+                    float one[NS];
 #pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const float v = warp_sum(acc[k][s]);
-                    if (lane == 0) red[warp][(k0 + k) * NS + s] = v;
+                    for (int s2 = 0; s2 < NS; ++s2) one[s2] = acc[k * NS + s2];
+                    warp_reduce_store<NS>(one, lane, &red[warp][(k0 + k) * NS]);
                 }
             }
         }
