@@ -28,7 +28,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -65,62 +64,57 @@ def read_peaks():
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons through NVML (what nvidia-smi reads).  Sampling is done from the main
+    thread AFTER a timed region's work has been enqueued and WHILE the GPU is still executing it
+    (`poll_until(end_event)`): NVML queries from a second thread during the enqueue loop were measured to
+    stall kernel launches (driver lock) and to distort a CPU-sensitive loop."""
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+             0x80: "hw_power_brake_slowdown"}
+
     def __init__(self, index):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
-        self._t = None
+        self.samples, self.reasons, self.max_mhz = [], set(), None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.sample(record=False)      # first NVML queries are slow: pay for them outside the timed regions
         except Exception:  # noqa: BLE001
             self.nv = None
 
-    def _reasons(self):
-        nv = self.nv
+    def sample(self, record=True):
+        if self.nv is None:
+            return
         try:
-            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+            try:
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:  # noqa: BLE001
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            if record:
+                self.samples.append(mhz)
+                for bit, name in self.NAMES.items():
+                    if mask & bit:
+                        self.reasons.add(name)
         except Exception:  # noqa: BLE001
-            try:
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-            except Exception:  # noqa: BLE001
+            pass
+
+    def poll_until(self, end_event, period_s=0.01):
+        """Sample while the GPU drains the enqueued region; returns when `end_event` has completed."""
+        while True:
+            self.sample()
+            if end_event.query():
                 return
-        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
-                 0x80: "hw_power_brake_slowdown"}
-        for bit, name in names.items():
-            if mask & bit:
-                self.reasons.add(name)
-
-    def _loop(self):
-        while not self._stop.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                self._reasons()
-            except Exception:  # noqa: BLE001
-                pass
-            self._stop.wait(0.05)
-
-    def __enter__(self):
-        if self.nv is not None:
-            self._stop.clear()
-            self._t = threading.Thread(target=self._loop, daemon=True)
-            self._t.start()
-        return self
-
-    def __exit__(self, *a):
-        self._stop.set()
-        if self._t is not None:
-            self._t.join()
-            self._t = None
+            time.sleep(period_s)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "how": "NVML, sampled under load between enqueue and completion of each timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,51 +230,63 @@ def run_ours(args):
     barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks = ClockSampler(local_rank)
-    with clocks:
-        start.record()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            lib.rcf_debug_time_kernel(3, ev_pairs[i][0].cuda_event, ev_pairs[i][1].cuda_event)
-            loss, grads = step()
-        cpu_enqueue_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-        end.record()
-        lib.rcf_debug_time_kernel(0, None, None)
-        barrier()
+    barrier()
+    start.record()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        lib.rcf_debug_time_kernel(3, ev_pairs[i][0].cuda_event, ev_pairs[i][1].cuda_event)
+        loss, grads = step()
+    cpu_enqueue_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    end.record()
+    lib.rcf_debug_time_kernel(0, None, None)
+    clocks.poll_until(end)
+    barrier()
     for w, _ in pending:
         w.wait()
     pending.clear()
     eager_ms = start.elapsed_time(end) / args.steps
+    loss_val = [float(x) for x in loss.detach().cpu()]
+    # Drop every reference to the eager steps before capturing: tensors freed while a capture is open make the
+    # caching allocator poll its stream-use events (cudaEventQuery), which invalidates the capture.
+    del loss, grads
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
 
     graph_ms = None
-    try:   # capture with the NVML sampler thread stopped; only the replay loop is sampled
+    try:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            pkg.rcf_motion_loss(spec, masks, flows, [rfw, rbw], thetas=thetas)
+            step()
         torch.cuda.current_stream().wait_stream(side)
+        for w, _ in pending:
+            w.wait()
+        pending.clear()
+        gc.collect()
         torch.cuda.synchronize()
         g_ = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_, capture_error_mode="thread_local"):
+        with torch.cuda.graph(g_):
             loss_g, _ = pkg.rcf_motion_loss(spec, masks, flows, [rfw, rbw], thetas=thetas)
             grads_g = torch.autograd.grad(loss_g, inputs, grad_outputs=gl)
         for _ in range(3):
             g_.replay()
         barrier()
         gs_, ge_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with clocks:
-            gs_.record()
-            for _ in range(args.steps):
-                g_.replay()
-                if world > 1:      # the per-step loss all-reduce stays outside the graph, asynchronous
-                    lr = loss_g.detach().clone()
-                    pending.append((dist.all_reduce(lr, async_op=True), lr))
-            ge_.record()
-            barrier()
+        gs_.record()
+        for _ in range(args.steps):
+            g_.replay()
+            if world > 1:      # the per-step loss all-reduce stays outside the graph, asynchronous
+                lr = loss_g.detach().clone()
+                pending.append((dist.all_reduce(lr, async_op=True), lr))
+        ge_.record()
+        clocks.poll_until(ge_)
+        barrier()
         for w, _ in pending:
             w.wait()
         pending.clear()
         graph_ms = gs_.elapsed_time(ge_) / args.steps
-        loss = loss_g
+        loss_val = [float(x) for x in loss_g.detach().cpu()]
     except Exception as ex:  # noqa: BLE001
         print(f"[bench] CUDA graph capture unavailable ({type(ex).__name__}: {str(ex)[:300]}); using eager timing",
               file=sys.stderr)
@@ -293,7 +299,6 @@ def run_ours(args):
     value = B * world / (ms_step * 1e-3)
     kb_ms = sorted(a.elapsed_time(b) for a, b in ev_pairs)
     kb_mean = sum(kb_ms) / len(kb_ms)
-    loss_val = [float(x) for x in loss.detach().cpu()]
 
     # e2e through the drop-in module, pinned host buffers in / loss + grads out
     torch.manual_seed(1)
@@ -301,39 +306,67 @@ def run_ours(args):
     head.return_flows = False
     head._inv_n_override = inv_n
     pin = [t.pin_memory() for t in (masks_h, fw_h, bw_h, rfw_h, rbw_h)]
-    d_in = [torch.empty_like(t, device=dev) for t in pin]
     out_pin = [torch.empty(2, dtype=torch.float32).pin_memory(), torch.empty_like(masks_h).pin_memory(),
                torch.empty_like(rfw_h).pin_memory(), torch.empty_like(rbw_h).pin_memory()]
     imgs = torch.zeros(B, 2, 3, 8, 8)
     h2d = sum(t.numel() * 4 for t in pin)
     d2h = sum(t.numel() * 4 for t in out_pin)
+    # Three streams, double-buffered device inputs: the H2D copy of step i+1 and the D2H copy of step i-1 overlap
+    # the compute of step i (PCIe is full duplex; both copy engines busy).  Every step still moves all of its
+    # inputs host->device and all of its results device->host inside the timed region.
+    s_in, s_out, s_cmp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
+    NBUF = 2
+    d_in = [[torch.empty_like(t, device=dev) for t in pin] for _ in range(NBUF)]
+    ev_in = [torch.cuda.Event() for _ in range(NBUF)]
+    ev_free = [torch.cuda.Event() for _ in range(NBUF)]      # compute finished reading buffer b
+    ev_out_done = torch.cuda.Event()
+    keep = []
 
-    def e2e_step():
-        for d, s in zip(d_in, pin):
-            d.copy_(s, non_blocking=True)
-        m = d_in[0].requires_grad_(True)
-        r1 = d_in[3].requires_grad_(True)
-        r2 = d_in[4].requires_grad_(True)
-        _, fl = head(imgs, m, d_in[1], d_in[2], r1, r2)
-        lvec = torch.stack([fl["seg_fw"], fl["seg_bw"]])
+    def e2e_step(i):
+        bsel = i % NBUF
+        with torch.cuda.stream(s_in):
+            if i >= NBUF:
+                s_in.wait_event(ev_free[bsel])
+            for d, src in zip(d_in[bsel], pin):
+                d.copy_(src, non_blocking=True)
+            ev_in[bsel].record(s_in)
+        s_cmp.wait_event(ev_in[bsel])
+        m = d_in[bsel][0].requires_grad_(True)
+        r1 = d_in[bsel][3].requires_grad_(True)
+        r2 = d_in[bsel][4].requires_grad_(True)
+        _, fl = head(imgs, m, d_in[bsel][1], d_in[bsel][2], r1, r2)
+        lvec = torch.stack([fl["seg_fw"], fl["seg_bw"]]).detach()
         gm, g1, g2 = torch.autograd.grad(fl["seg"], [m, r1, r2])
-        out_pin[0].copy_(lvec.detach(), non_blocking=True)
-        out_pin[1].copy_(gm, non_blocking=True)
-        out_pin[2].copy_(g1, non_blocking=True)
-        out_pin[3].copy_(g2, non_blocking=True)
-        for t_ in (d_in[0], d_in[3], d_in[4]):
+        ev_free[bsel].record(s_cmp)
+        ev_cmp = torch.cuda.Event()
+        ev_cmp.record(s_cmp)
+        for t_ in (d_in[bsel][0], d_in[bsel][3], d_in[bsel][4]):
             t_.requires_grad_(False)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_cmp)
+            for dst, src in zip(out_pin, (lvec, gm, g1, g2)):
+                dst.copy_(src, non_blocking=True)
+                src.record_stream(s_out)
+            ev_out_done.record(s_out)
+        keep.append((lvec, gm, g1, g2))
+        if len(keep) > 2:
+            keep.pop(0)
 
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(3):
-        e2e_step()
+    for i in range(4):
+        e2e_step(i)
+    s_cmp.wait_event(ev_out_done)
     barrier()
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    s_cmp.wait_stream(s_out)
+    s_cmp.wait_stream(s_in)
     e2.record()
+    clocks.poll_until(e2)
     barrier()
+    keep.clear()
     t2 = torch.tensor([s2.elapsed_time(e2)], device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
@@ -352,7 +385,9 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "steps": e2e_steps},
+                    "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "pcie_gbs_each_way": [h2d / e2e_ms / 1e6, d2h / e2e_ms / 1e6],
+                    "note": "PCIe-bound; copies of neighbouring steps overlap compute on 3 streams"},
             "gpu_launches": 7 * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_bwd<K=4,D=0,PX=4> (streaming backward)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
