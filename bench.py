@@ -456,7 +456,9 @@ def extras(pkg, dev):
                 m = ins[0].clone().requires_grad_(True)
                 r1 = ins[3].clone().requires_grad_(True)
                 r2 = ins[4].clone().requires_grad_(True)
-                params = list(head.parameters())
+                # parameter gradients only for real heads: cuDNN's wgrad for the degenerate 2->2 1x1 proxy convs
+                # over 6.5M pixels takes ~16 ms in BOTH arms and would hide everything else
+                params = list(head.parameters()) if kw.get("num_flow_feat_channels", 64) > 2 else []
 
                 def fn():
                     _, l = head(imgs, m, ins[1], ins[2], r1, r2)

@@ -93,23 +93,23 @@ class RcfMotionLossFn(torch.autograd.Function):
 
     Inputs (all fp32 CUDA):
       masks  [B, ndir, K, H, W]           (grad)
+      feat   [ndir, B, Cf, H, W]          (grad)  + w1,b1,w2,b2 (grad)      when spec.Cf > 0
+             (direction-major, i.e. the conv output of the concatenated [fw; bw] flow batch, viewed 5-D)
       flows  tuple of ndir  [B, 2, H, W]  (no grad; the clamp is applied inside the kernels)
       resids tuple of ndir  [B, 2K, H, W] (grad)
-      feats  tuple of ndir  [B, Cf, H, W] (grad)  + w1,b1,w2,b2 (grad)      when spec.Cf > 0
       thetas tuple of ndir  [B, 2, K]     (grad)                            when spec.Cf == 0
     Returns loss [ndir] and, when spec.want_vis, the un-differentiable tensors
     (gt, pred, agg, res[, aff]) each [B, 2*ndir, H, W].
     """
 
     @staticmethod
-    def forward(ctx, spec: LossSpec, masks, w1, b1, w2, b2, *per_dir):
+    def forward(ctx, spec: LossSpec, masks, feat, w1, b1, w2, b2, *per_dir):
         lib = _lib.load_library()
         ndir = masks.shape[1]
-        assert len(per_dir) == 4 * ndir
+        assert len(per_dir) == 3 * ndir
         flows = per_dir[0:ndir]
         resids = per_dir[ndir:2 * ndir]
-        feats = per_dir[2 * ndir:3 * ndir]
-        thetas = per_dir[3 * ndir:4 * ndir]
+        thetas = per_dir[2 * ndir:3 * ndir]
         if not masks.is_cuda:
             raise RuntimeError("RcfMotionLossFn needs CUDA tensors: the loss has no CPU implementation")
         B, _, K, H, W = masks.shape
@@ -120,15 +120,17 @@ class RcfMotionLossFn(torch.autograd.Function):
         masks_v = masks if (masks.dtype == torch.float32 and _inner_dense(masks, 3)) else masks.float().contiguous()
         flows_v = [_as_dir_view(f) for f in flows]
         resids_v = [_as_dir_view(r) for r in resids]
-        feats_v = [_as_dir_view(g) if g is not None else None for g in feats]
+        feat_v = None
+        if spec.Cf > 0:
+            assert feat is not None and tuple(feat.shape) == (ndir, B, spec.Cf, H, W), \
+                f"feature map shape {None if feat is None else tuple(feat.shape)}"
+            feat_v = feat if (feat.dtype == torch.float32 and _inner_dense(feat, 3)) else feat.float().contiguous()
         thetas_v = [t.float().contiguous() if t is not None else None for t in thetas]
         for f in flows_v:
             assert f.shape == (B, 2, H, W), f"flow shape {tuple(f.shape)}"
         for r in resids_v:
             assert r.shape == (B, 2 * K, H, W), f"residual shape {tuple(r.shape)}"
         if spec.Cf > 0:
-            for g in feats_v:
-                assert g is not None and g.shape == (B, spec.Cf, H, W), "feature map shape"
             w1c, b1c, w2c, b2c = (t.detach().float().contiguous() for t in (w1, b1, w2, b2))
             assert w1c.numel() == spec.Cf * spec.Cf and w2c.numel() == 2 * spec.Cf
         else:
@@ -144,7 +146,7 @@ class RcfMotionLossFn(torch.autograd.Function):
             inp.flow[i] = flows_v[i].data_ptr(); desc.flow_bstride[i] = flows_v[i].stride(0)
             inp.resid[i] = resids_v[i].data_ptr(); desc.resid_bstride[i] = resids_v[i].stride(0)
             if spec.Cf > 0:
-                inp.feat[i] = feats_v[i].data_ptr(); desc.feat_bstride[i] = feats_v[i].stride(0)
+                inp.feat[i] = feat_v.data_ptr() + i * feat_v.stride(0) * 4; desc.feat_bstride[i] = feat_v.stride(1)
             else:
                 inp.theta[i] = thetas_v[i].data_ptr()
         if spec.Cf > 0:
@@ -175,7 +177,7 @@ class RcfMotionLossFn(torch.autograd.Function):
         ctx.spec, ctx.ndir, ctx.B = spec, ndir, B
         ctx.masks_shape = tuple(masks.shape)
         ctx.save_for_backward(masks_v, ctx_buf, *flows_v, *resids_v,
-                              *[g for g in feats_v if g is not None], *[t for t in thetas_v if t is not None],
+                              *([feat_v] if feat_v is not None else []), *[t for t in thetas_v if t is not None],
                               *([w1c, b1c, w2c, b2c] if spec.Cf > 0 else []))
         ctx.mark_non_differentiable(*vis_tensors)
         return (loss, *vis_tensors)
@@ -192,26 +194,29 @@ class RcfMotionLossFn(torch.autograd.Function):
         resids_v = saved[2 + ndir:2 + 2 * ndir]
         rest = saved[2 + 2 * ndir:]
         dev = masks_v.device
-        # needs_input_grad: (spec, masks, w1, b1, w2, b2, *flows, *resids, *feats, *thetas)
+        # needs_input_grad: (spec, masks, feat, w1, b1, w2, b2, *flows, *resids, *thetas)
         need = ctx.needs_input_grad
         need_masks = need[1]
-        need_w = any(need[2:6])
-        need_resid = [need[6 + ndir + i] for i in range(ndir)]
-        need_feat = [need[6 + 2 * ndir + i] for i in range(ndir)]
-        need_theta = [need[6 + 3 * ndir + i] for i in range(ndir)]
+        need_feat = need[2]
+        need_w = any(need[3:7])
+        need_resid = [need[7 + ndir + i] for i in range(ndir)]
+        need_theta = [need[7 + 2 * ndir + i] for i in range(ndir)]
 
         desc = _make_desc(spec, B, ndir)
         inp = _lib.RcfInputs()
         grads = _lib.RcfGrads()
+        d_feat = None
         if Cf > 0:
-            feats_v = rest[0:ndir]
-            w1c, b1c, w2c, b2c = rest[ndir:ndir + 4]
+            feat_v = rest[0]
+            w1c, b1c, w2c, b2c = rest[1:5]
             inp.w1, inp.b1, inp.w2, inp.b2 = (t.data_ptr() for t in (w1c, b1c, w2c, b2c))
+            if need_feat:
+                d_feat = torch.empty(ndir, B, Cf, H, W, dtype=torch.float32, device=dev)
         else:
             thetas_v = rest[0:ndir]
 
         d_masks = torch.empty(ctx.masks_shape, dtype=torch.float32, device=dev) if need_masks else None
-        d_resids, d_feats, d_thetas = [None] * ndir, [None] * ndir, [None] * ndir
+        d_resids, d_thetas = [None] * ndir, [None] * ndir
         for i in range(ndir):
             inp.mask[i] = masks_v.data_ptr() + i * masks_v.stride(1) * 4
             desc.mask_bstride[i] = masks_v.stride(0)
@@ -224,10 +229,9 @@ class RcfMotionLossFn(torch.autograd.Function):
                 d_resids[i] = torch.empty(B, 2 * K, H, W, dtype=torch.float32, device=dev)
                 grads.dresid[i] = d_resids[i].data_ptr(); desc.dresid_bstride[i] = d_resids[i].stride(0)
             if Cf > 0:
-                inp.feat[i] = feats_v[i].data_ptr(); desc.feat_bstride[i] = feats_v[i].stride(0)
-                if need_feat[i]:
-                    d_feats[i] = torch.empty(B, Cf, H, W, dtype=torch.float32, device=dev)
-                    grads.dfeat[i] = d_feats[i].data_ptr(); desc.dfeat_bstride[i] = d_feats[i].stride(0)
+                inp.feat[i] = feat_v.data_ptr() + i * feat_v.stride(0) * 4; desc.feat_bstride[i] = feat_v.stride(1)
+                if d_feat is not None:
+                    grads.dfeat[i] = d_feat.data_ptr() + i * d_feat.stride(0) * 4; desc.dfeat_bstride[i] = d_feat.stride(1)
             else:
                 inp.theta[i] = thetas_v[i].data_ptr()
                 if need_theta[i]:
@@ -246,7 +250,7 @@ class RcfMotionLossFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.rcf_backward(C.byref(desc), C.byref(inp), gl.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
                                         C.byref(grads), stream), "rcf_backward")
-        return (None, d_masks, *dw, *([None] * ndir), *d_resids, *d_feats, *d_thetas)
+        return (None, d_masks, d_feat, *dw, *([None] * ndir), *d_resids, *d_thetas)
 
 
 def rcf_motion_loss(spec: LossSpec, masks: torch.Tensor, flows: Sequence[torch.Tensor],
@@ -255,16 +259,20 @@ def rcf_motion_loss(spec: LossSpec, masks: torch.Tensor, flows: Sequence[torch.T
     """Functional entry point.  masks [B,ndir,K,H,W]; flows/resids (and feats or thetas) per direction.
 
     Returns (loss [ndir], vis tuple).  Exactly one of (feats + mlp weights) or thetas must be given,
-    consistently with spec.Cf.
+    consistently with spec.Cf.  `feats` is either the direction-major 5-D tensor [ndir,B,Cf,H,W] (preferred:
+    one conv call over the concatenated directions, no copies) or a sequence of per-direction [B,Cf,H,W] tensors
+    (stacked here, which costs a copy).
     """
     ndir = masks.shape[1]
+    feat = None
     if spec.Cf > 0:
         assert feats is not None and mlp is not None and len(mlp) == 4
         w1, b1, w2, b2 = mlp
-        per_dir = (*flows, *resids, *feats, *([None] * ndir))
+        feat = feats if torch.is_tensor(feats) else torch.stack(list(feats), 0)
+        per_dir = (*flows, *resids, *([None] * ndir))
     else:
         assert thetas is not None
         w1 = b1 = w2 = b2 = None
-        per_dir = (*flows, *resids, *([None] * ndir), *thetas)
-    out = RcfMotionLossFn.apply(spec, masks, w1, b1, w2, b2, *per_dir)
+        per_dir = (*flows, *resids, *thetas)
+    out = RcfMotionLossFn.apply(spec, masks, feat, w1, b1, w2, b2, *per_dir)
     return out[0], tuple(out[1:])

@@ -193,18 +193,20 @@ class FlowAggregationHeadWithResidual(nn.Module):
         B, ndir, K, H, W = masks5.shape
         with torch.autocast(device_type="cuda", enabled=False):
             masks5 = masks5.float()
-            k_flows, feats, rs = [], [], []
+            k_flows, c_flows, rs = [], [], []
             fused = True
             for flow, resid in zip(flows, resids):
                 kf, cf_, fused_i, r = self._prepare(flow.float(), resid.float(), H, W)
                 fused = fused and fused_i
-                feat = self.flow_feat_before_agg(cf_)
-                assert feat.shape[2:] == masks5.shape[3:], \
-                    f"{feat.shape[2:]} != {masks5.shape[3:]} (should match on spatial dimension)"   # :247-248
                 assert r.shape[-2:] == (H, W), f"residual spatial size {tuple(r.shape[-2:])} != mask size {(H, W)}"
-                k_flows.append(kf.detach()); feats.append(feat); rs.append(r)
+                k_flows.append(kf.detach()); c_flows.append(cf_); rs.append(r)
+            # one pass of the conv branch over both directions (batch-concatenated), then a free 5-D view
+            feat = self.flow_feat_before_agg(torch.cat(c_flows, 0) if ndir > 1 else c_flows[0])
+            assert feat.shape[2:] == masks5.shape[3:], \
+                f"{feat.shape[2:]} != {masks5.shape[3:]} (should match on spatial dimension)"   # :247-248
+            feat = feat.view(ndir, B, *feat.shape[1:])
             spec = self._spec(K, H, W, want_vis=want_vis, vis_norm=vis_norm, inv_n=inv_n, clamp_fused=fused)
-            loss, vis = rcf_motion_loss(spec, masks5, k_flows, rs, feats=feats, mlp=self._mlp_params())
+            loss, vis = rcf_motion_loss(spec, masks5, k_flows, rs, feats=feat, mlp=self._mlp_params())
         return loss, vis
 
     # ------------------------------------------------------------------------------------------
@@ -233,7 +235,8 @@ class FlowAggregationHeadWithResidual(nn.Module):
             feat = self.flow_feat_before_agg(flow)
             assert feat.shape[2:] == mask.shape[2:], f"{feat.shape[2:]} != {mask.shape[2:]} (should match on spatial dimension)"
             spec = self._spec(K, H, W, want_vis=True, vis_norm=False, clamp_fused=False)
-            _, vis = rcf_motion_loss(spec, mask.float().unsqueeze(1), [flow], [resid], feats=[feat], mlp=self._mlp_params())
+            _, vis = rcf_motion_loss(spec, mask.float().unsqueeze(1), [flow], [resid], feats=feat.unsqueeze(0),
+                                     mlp=self._mlp_params())
         return vis[1], vis[2], vis[3], (vis[4] if len(vis) > 4 else None)
 
     def forward(self, imgs, masks, gt_fw_flows, gt_bw_flows, all_pred_residual_fw, all_pred_residual_bw):
