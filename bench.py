@@ -186,6 +186,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout clean for the one JSON line: NCCL's banner / debug output goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/rcf_bench_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     lib = pkg.load_library(build_if_missing=False)
 
@@ -286,7 +288,10 @@ def run_ours(args):
             w.wait()
         pending.clear()
         graph_ms = gs_.elapsed_time(ge_) / args.steps
-        loss_val = [float(x) for x in loss_g.detach().cpu()]
+        lfin = loss_g.detach().clone()
+        if world > 1:
+            dist.all_reduce(lfin)
+        loss_val = [float(x) for x in lfin.cpu()]
     except Exception as ex:  # noqa: BLE001
         print(f"[bench] CUDA graph capture unavailable ({type(ex).__name__}: {str(ex)[:300]}); using eager timing",
               file=sys.stderr)

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--W", type=int, default=854)
     ap.add_argument("--D", type=int, default=0)
     ap.add_argument("--robust", action="store_true")
+    ap.add_argument("--Cf", type=int, default=0, help=">0: Scope H, pool a random [B,Cf,H,W] feature map + segment MLP")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--time", action="store_true", help="print CUDA-event time per step and per kernel")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
@@ -32,11 +33,21 @@ def main():
     flows = [torch.randn(B, 2, H, W, device=dev, generator=g) * 8 for _ in range(2)]
     resids = [(torch.randn(B, 2 * K, H, W, device=dev, generator=g) * 5).requires_grad_(True) for _ in range(2)]
     thetas = [torch.randn(B, 2, K, device=dev, generator=g).requires_grad_(True) for _ in range(2)]
-    spec = pkg.LossSpec(K=K, H=H, W=W, D=a.D, Cf=0, clamp_t=20.0, robust=a.robust)
+    spec = pkg.LossSpec(K=K, H=H, W=W, D=a.D, Cf=a.Cf, clamp_t=20.0, robust=a.robust)
     gl = torch.ones(2, device=dev)
     lib = pkg.load_library()
+    Cf = a.Cf
+    if Cf > 0:
+        feat = torch.randn(2, B, Cf, H, W, device=dev, generator=g).requires_grad_(True)
+        mlp = [(torch.randn(Cf, Cf, 1, device=dev, generator=g) / Cf ** 0.5).requires_grad_(True),
+               torch.zeros(Cf, device=dev).requires_grad_(True),
+               (torch.randn(2, Cf, 1, device=dev, generator=g) / Cf ** 0.5).requires_grad_(True),
+               torch.zeros(2, device=dev).requires_grad_(True)]
 
     def step():
+        if Cf > 0:
+            loss, _ = pkg.rcf_motion_loss(spec, masks, flows, resids, feats=feat, mlp=mlp)
+            return loss, torch.autograd.grad(loss, [masks, *resids, feat, *mlp], grad_outputs=gl)
         loss, _ = pkg.rcf_motion_loss(spec, masks, flows, resids, thetas=thetas)
         return loss, torch.autograd.grad(loss, [masks, *resids, *thetas], grad_outputs=gl)
 
@@ -59,7 +70,7 @@ def main():
     cpu_ms = (time.perf_counter() - t0) * 1e3 / a.steps
     e.record(); torch.cuda.synchronize()
     ms = s.elapsed_time(e) / a.steps
-    alg = B * 2 * P * (36 * K + 16)
+    alg = B * 2 * P * (36 * K + 16 + 12 * Cf + (16 * K if Cf else 0))
     print(f"step {ms:.4f} ms  {B / ms * 1e3:.0f} samples/s  algorithmic {alg / ms / 1e6:.0f} GB/s  (cpu enqueue {cpu_ms:.3f} ms/step)")
     if a.graph:
         side = torch.cuda.Stream()
@@ -81,6 +92,9 @@ def main():
         msg = s.elapsed_time(e) / a.steps
         print(f"graph step {msg:.4f} ms  {B / msg * 1e3:.0f} samples/s  algorithmic {alg / msg / 1e6:.0f} GB/s  loss {loss_g.tolist()}")
     names = {1: ("k_moments", 4 * K + (8 if a.D else 0)), 2: ("k_loss", 12 * K + 8), 3: ("k_bwd", 24 * K + 8)}
+    if Cf > 0:
+        names[4] = ("k_pool", 4 * Cf + 4 * K)
+        names[5] = ("k_pool_bwd", 8 * Cf + 12 * K)
     for which, (name, bpp) in names.items():
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
         for x, y in evs:
