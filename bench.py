@@ -471,6 +471,20 @@ def extras(pkg, dev):
 
                 ms = _time_cuda(fn, steps)
                 res[impl] = {"ms_per_step": ms, "samples_per_s": B_ / ms * 1e3}
+                if impl == "ours" and H_ * W_ <= 128 * 128:
+                    # launch-bound regime: the same head captured once into CUDA graphs (fwd graph + bwd graph)
+                    try:
+                        from rcf_unsupvideoseg_b200.graphed import make_graphed_head
+                        gh = make_graphed_head(head, (imgs, m, ins[1], ins[2], r1, r2))
+
+                        def gfn():
+                            l = gh(m, ins[1], ins[2], r1, r2)
+                            torch.autograd.grad(l["seg"], [m, r1, r2, *params])
+
+                        ms_g = _time_cuda(gfn, steps)
+                        res["ours_cuda_graph"] = {"ms_per_step": ms_g, "samples_per_s": B_ / ms_g * 1e3}
+                    except Exception as ex:  # noqa: BLE001
+                        res["ours_cuda_graph"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
                 del head
                 torch.cuda.empty_cache()
             res["speedup_vs_torch_eager"] = res["torch_eager_port"]["ms_per_step"] / res["ours"]["ms_per_step"]

@@ -10,8 +10,12 @@
 // on top of what the streaming backward (k_bwd, launched before) already stored.
 #include "rcf_common.cuh"
 
+// blockIdx.z splits the feature channels (more CTAs for small frames: 96x96 training shapes would otherwise
+// launch only 80 CTAs on 148 SMs).  A warp handles FB feature channels at once so that one shared-memory read of
+// the mask tile feeds FB global loads (LDS bandwidth, not HBM, was the limiter with FB = 1).
 template <int K, int PX, int CHUNK>
-__global__ void __launch_bounds__(RCF_BLOCK) k_pool(const RcfK a) {
+__global__ void __launch_bounds__(RCF_BLOCK) k_pool(const RcfK a, int f_per_cta) {
+    constexpr int FB = 4;
     __shared__ __align__(16) float ms[K][CHUNK];
     const int fd = blockIdx.y;
     const int dir = fd / a.B;
@@ -20,6 +24,8 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool(const RcfK a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.P, Cf = a.Cf;
     const int p0 = chunk * CHUNK;
+    const int f_begin = blockIdx.z * f_per_cta;
+    const int f_end = min(Cf, f_begin + f_per_cta);
     const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
     const float* __restrict__ feat = a.feat[dir] + (long long)b * a.feat_bs[dir];
 
@@ -38,27 +44,44 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool(const RcfK a) {
     }
     __syncthreads();
 
-    for (int f = warp; f < Cf; f += RCF_WARPS) {
-        const float* __restrict__ g = feat + (long long)f * P + p0;
-        float acc[K];
+    for (int f0 = f_begin + warp * FB; f0 < f_end; f0 += RCF_WARPS * FB) {
+        float acc[FB * K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = 0.0f;
-#pragma unroll 4
+        for (int i = 0; i < FB * K; ++i) acc[i] = 0.0f;
+#pragma unroll 2
         for (int i = lane * PX; i < CHUNK; i += 32 * PX) {
             if (p0 + i < P) {
-                float gv[PX];
-                Pack<PX>::ld(gv, g + i);
+                float gv[FB][PX];
 #pragma unroll
-                for (int k = 0; k < K; ++k)
+                for (int q = 0; q < FB; ++q) {
+                    if (f0 + q < f_end) Pack<PX>::ld(gv[q], feat + (long long)(f0 + q) * P + p0 + i);
+                    else {
 #pragma unroll
-                    for (int j = 0; j < PX; ++j) acc[k] = fmaf(gv[j], ms[k][i + j], acc[k]);
+                        for (int j = 0; j < PX; ++j) gv[q][j] = 0.0f;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float mv[PX];
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) mv[j] = ms[k][i + j];
+#pragma unroll
+                    for (int q = 0; q < FB; ++q)
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) acc[q * K + k] = fmaf(gv[q][j], mv[j], acc[q * K + k]);
+                }
             }
         }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float v = warp_sum(acc[k]);
-            if (lane == 0) a.partp[((size_t)fd * Cf * K + (size_t)f * K + k) * a.nchunkp + chunk] = v;
+        // FB*K totals; partp layout [fd][f*K + k][chunk]
+        __shared__ float red[RCF_WARPS][FB * K];
+        warp_reduce_store<FB * K>(acc, lane, red[warp]);
+        __syncwarp();
+        if (lane < FB * K) {
+            const int q = lane / K, k = lane - q * K;
+            if (f0 + q < f_end)
+                a.partp[((size_t)fd * Cf * K + (size_t)(f0 + q) * K + k) * a.nchunkp + chunk] = red[warp][lane];
         }
+        __syncwarp();
     }
 }
 
@@ -117,14 +140,21 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
 template <int K>
 static cudaError_t launch_pool_k(const RcfK& a, bool vec, cudaStream_t s) {
     constexpr int CHUNK = K <= 4 ? 2048 : 1024;
-    dim3 grid(a.nchunkp, a.nfd), block(RCF_BLOCK);
-    if (vec) k_pool<K, 4, CHUNK><<<grid, block, 0, s>>>(a);
-    else k_pool<K, 1, CHUNK><<<grid, block, 0, s>>>(a);
+    // split the channels over blockIdx.z until the grid has a few CTAs per SM (each CTA keeps >= 4 channels/warp-pass)
+    int fsplit = 1;
+    const long long base = (long long)a.nchunkp * a.nfd;
+    while (base * fsplit < 4 * 148 && a.Cf / (fsplit * 2) >= 4) fsplit *= 2;
+    const int f_per_cta = (a.Cf + fsplit - 1) / fsplit;
+    dim3 grid(a.nchunkp, a.nfd, (a.Cf + f_per_cta - 1) / f_per_cta), block(RCF_BLOCK);
+    if (vec) k_pool<K, 4, CHUNK><<<grid, block, 0, s>>>(a, f_per_cta);
+    else k_pool<K, 1, CHUNK><<<grid, block, 0, s>>>(a, f_per_cta);
     return cudaGetLastError();
 }
 
 template <int K>
 static cudaError_t launch_pool_bwd_k(const RcfK& a, bool vec, cudaStream_t s) {
+    // small frames: one pixel per thread gives 4x the CTAs (the loop over Cf channels is serial per thread)
+    if (vec && (long long)((a.P + RCF_BLOCK * 4 - 1) / (RCF_BLOCK * 4)) * a.nfd < 2 * 148) vec = false;
     const int px = vec ? 4 : 1;
     dim3 grid((a.P + RCF_BLOCK * px - 1) / (RCF_BLOCK * px), a.nfd), block(RCF_BLOCK);
     const size_t smem = (size_t)a.Cf * K * sizeof(float);

@@ -1,0 +1,45 @@
+"""CUDA-graph capture of the head's forward+backward for fixed shapes (the 48x48 / 96x96 training regime is
+launch-bound: ~40 kernels of a few microseconds each; one graph launch replaces them).
+
+    graphed = make_graphed_head(head, (imgs, masks, gt_fw, gt_bw, res_fw, res_bw))
+    flow_loss = graphed(masks, gt_fw, gt_bw, res_fw, res_bw)        # {'seg_fw','seg_bw','seg'}; .backward() works
+
+Uses torch.cuda.make_graphed_callables (streams + graphs, no tracing compiler).  The visualisation flows are
+not produced on this path (they are only needed every `log_interval` iterations, models/rcf_model.py:456-460 --
+call the plain head then).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+
+class _LossOnly(nn.Module):
+    def __init__(self, head, imgs_shape):
+        super().__init__()
+        self.head = head
+        self._imgs = torch.zeros(imgs_shape)      # only .shape is read by forward (reference :322-324)
+
+    def forward(self, masks, gt_fw, gt_bw, res_fw, res_bw):
+        prev = self.head.return_flows
+        self.head.return_flows = False
+        try:
+            _, fl = self.head(self._imgs, masks, gt_fw, gt_bw, res_fw, res_bw)
+        finally:
+            self.head.return_flows = prev
+        return torch.stack([fl["seg_fw"], fl["seg_bw"]])
+
+
+def make_graphed_head(head, sample_inputs, num_warmup_iters: int = 3):
+    """sample_inputs = (imgs, masks, gt_fw_flows, gt_bw_flows, res_fw, res_bw) with the shapes/dtypes/devices and
+    requires_grad flags of the real calls.  Returns a callable(masks, gt_fw, gt_bw, res_fw, res_bw) -> dict."""
+    imgs, masks, gt_fw, gt_bw, res_fw, res_bw = sample_inputs
+    mod = _LossOnly(head, tuple(imgs.shape))
+    samples = tuple(t.detach().clone().requires_grad_(t.requires_grad) for t in (masks, gt_fw, gt_bw, res_fw, res_bw))
+    graphed = torch.cuda.make_graphed_callables(mod, samples, num_warmup_iters=num_warmup_iters)
+
+    def call(masks, gt_fw, gt_bw, res_fw, res_bw):
+        l2 = graphed(masks, gt_fw, gt_bw, res_fw, res_bw)
+        return {"seg_fw": l2[0], "seg_bw": l2[1], "seg": l2[0] + l2[1]}
+
+    return call

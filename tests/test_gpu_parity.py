@@ -275,3 +275,46 @@ def test_helper_methods_vs_oracle(rcf):
     assert rel_l2(aff.cpu().numpy().reshape(B, 2, -1), c.aff) < 2e-5
     aff2 = head.get_demean_affine_flow(torch.from_numpy(masks[:, 0]).cuda(), flow_prepared)
     assert rel_l2(aff2.cpu().numpy().reshape(B, 2, -1), c.aff) < 2e-5
+
+
+def test_graphed_head_matches_eager(rcf):
+    """CUDA-graph capture of the whole head (fwd + bwd) reproduces the eager call bit for bit."""
+    from rcf_unsupvideoseg_b200.graphed import make_graphed_head
+    g = Golden("affine_l1")
+    head = build_head(rcf, g)
+    masks, fw, bw, rfw, rbw = [torch.from_numpy(a).cuda() for a in g.inputs]
+    masks.requires_grad_(True); rfw.requires_grad_(True); rbw.requires_grad_(True)
+    imgs = torch.zeros(masks.shape[0], 2, 3, 8, 8)
+    _, le = head(imgs, masks, fw, bw, rfw, rbw)
+    ge = torch.autograd.grad(le["seg"], [masks, rfw, rbw, *head.parameters()])
+    gh = make_graphed_head(head, (imgs, masks, fw, bw, rfw, rbw))
+    lg = gh(masks, fw, bw, rfw, rbw)
+    gg = torch.autograd.grad(lg["seg"], [masks, rfw, rbw, *head.parameters()])
+    torch.cuda.synchronize()
+    assert torch.equal(lg["seg"], le["seg"])
+    for a, b in zip(ge[:3], gg[:3]):
+        assert torch.equal(a, b)
+    for a, b in zip(ge[3:], gg[3:]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-7)    # cuDNN may pick different conv algorithms under capture
+
+
+def test_scope_h_large_feature_map_vs_oracle(rcf):
+    """Masked pooling + segment MLP inside the library (theta_mode 1) at a size where the channel split,
+    multi-chunk partials and both pool kernels' vector paths are exercised."""
+    B, K, H, W, Cf = 2, 4, 64, 96, 64
+    cfg = O.OracleConfig(mask_layer=K, mask_size=(H, W), num_flow_feat_channels=Cf, clamp_flow_t=20.0,
+                         free_residual_with_affine=True)
+    params = O.init_params(cfg, seed=5)
+    masks, fw, bw, rfw, rbw = O.synthetic_inputs(B, K, H, W, seed=21)
+    _, loss_o, caches = O.head_forward(masks, fw, bw, rfw, rbw, params, cfg)
+    g_o = O.head_backward(caches, params, gbar=1.0)
+    head = rcf.FlowAggregationHeadWithResidual(args=None, create_flownet=True, mask_layer=K, mask_size=(H, W),
+                                               num_flow_feat_channels=Cf, clamp_flow_t=20.0,
+                                               free_residual_with_affine=True).cuda()
+    head.load_state_dict({k: torch.from_numpy(v.astype(np.float32)) for k, v in params.items()})
+    flows, loss, grads = run_head(head, (masks, fw, bw, rfw, rbw), 1.0)
+    assert abs(float(loss["seg"]) - loss_o["seg"]) <= LOSS_RTOL * loss_o["seg"]
+    assert rel_l2(grads["d_masks"].cpu().numpy(), g_o["d_masks"]) <= GRAD_RTOL
+    assert rel_l2(grads["d_resid_fw"].cpu().numpy(), g_o["d_resid_fw"]) <= GRAD_RTOL
+    for k, p in head.named_parameters():
+        assert rel_l2(p.grad.cpu().numpy(), g_o["params"][k]) <= 3e-4, k
