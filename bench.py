@@ -235,8 +235,9 @@ def run_ours(args):
     barrier()
     start.record()
     t0 = time.perf_counter()
+    ev_handles = [(a.cuda_event, b.cuda_event) for a, b in ev_pairs]
     for i in range(args.steps):
-        lib.rcf_debug_time_kernel(3, ev_pairs[i][0].cuda_event, ev_pairs[i][1].cuda_event)
+        lib.rcf_debug_time_kernel(3, ev_handles[i][0], ev_handles[i][1])
         loss, grads = step()
     cpu_enqueue_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     end.record()
@@ -248,8 +249,8 @@ def run_ours(args):
     pending.clear()
     eager_ms = start.elapsed_time(end) / args.steps
     loss_val = [float(x) for x in loss.detach().cpu()]
-    # Drop every reference to the eager steps before capturing: tensors freed while a capture is open make the
-    # caching allocator poll its stream-use events (cudaEventQuery), which invalidates the capture.
+    # Drop every reference to the eager steps before capturing: a live autograd graph pins the leaves'
+    # AccumulateGrad nodes to the default stream, and the engine's stream hand-off then invalidates the capture.
     del loss, grads
     import gc
     gc.collect()

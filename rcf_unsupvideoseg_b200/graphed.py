@@ -6,7 +6,9 @@ launch-bound: ~40 kernels of a few microseconds each; one graph launch replaces 
 
 Uses torch.cuda.make_graphed_callables (streams + graphs, no tracing compiler).  The visualisation flows are
 not produced on this path (they are only needed every `log_interval` iterations, models/rcf_model.py:456-460 --
-call the plain head then).
+call the plain head then).  As with any torch CUDA-graph capture, no autograd graph involving the head's
+parameters may be alive while capturing (a live graph pins the parameters' AccumulateGrad nodes to the default
+stream and the capture is invalidated): capture before training starts or after `loss.backward()` + `del loss`.
 """
 from __future__ import annotations
 

@@ -287,7 +287,9 @@ def test_graphed_head_matches_eager(rcf):
     imgs = torch.zeros(masks.shape[0], 2, 3, 8, 8)
     _, le = head(imgs, masks, fw, bw, rfw, rbw)
     ge = torch.autograd.grad(le["seg"], [masks, rfw, rbw, *head.parameters()])
-    gh = make_graphed_head(head, (imgs, masks, fw, bw, rfw, rbw))
+    le = {k: v.detach().clone() for k, v in le.items()}     # free the eager autograd graph before capturing:
+    torch.cuda.synchronize()                                # a live graph pins the parameters' AccumulateGrad
+    gh = make_graphed_head(head, (imgs, masks, fw, bw, rfw, rbw))   # nodes to the default stream (torch rule)
     lg = gh(masks, fw, bw, rfw, rbw)
     gg = torch.autograd.grad(lg["seg"], [masks, rfw, rbw, *head.parameters()])
     torch.cuda.synchronize()
