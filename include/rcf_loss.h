@@ -140,6 +140,22 @@ RCF_API int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss, v
 RCF_API int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const float* grad_loss, const void* ctx,
                  void* ws, const RcfGrads* grads, void* stream);
 
+/* ---- utils/warp_utils.py sampling ops (reference :27-94; used by the AMD baseline, not by the RCF head) ----
+ * All tensors dense NCHW fp32 device pointers.  pad_border: 0 = padding_mode 'zeros', 1 = 'border'. */
+
+/* flow_warp (utils/warp_utils.py:84-94): out[b,c,y,x] = bilinear sample of x[b,c] at (x + flow[b,0], y + flow[b,1]),
+ * i.e. grid_sample(..., mode='bilinear', align_corners=True).  x,out [B,C,H,W]; flow [B,2,H,W]. */
+RCF_API int rcf_flow_warp_forward(const float* x, const float* flow, float* out, int B, int C, int H, int W,
+                                  int pad_border, void* stream);
+
+/* Backward of flow_warp.  grad_x (zero-filled here, then bilinear scatter with atomics) and/or grad_flow may be NULL. */
+RCF_API int rcf_flow_warp_backward(const float* x, const float* flow, const float* grad_out, float* grad_x,
+                                   float* grad_flow, int B, int C, int H, int W, int pad_border, void* stream);
+
+/* get_corresponding_map (utils/warp_utils.py:27-81): bilinear forward splat of ones at `coords` [B,2,H,W]
+ * (absolute x,y positions) into out [B,1,H,W]; scratch_u64 = B*H*W 64-bit words (order-independent fixed-point sums). */
+RCF_API int rcf_corresponding_map(const float* coords, float* out, void* scratch_u64, int B, int H, int W, void* stream);
+
 /* Measurement hook (bench.py): record the two caller-owned cudaEvent_t handles immediately before and
  * after the launch of streaming kernel `which` in the following rcf_forward / rcf_backward calls of this
  * process (on the stream those calls are given).  which: 0 off, 1 k_moments, 2 k_loss, 3 k_bwd,
