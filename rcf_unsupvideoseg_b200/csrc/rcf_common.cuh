@@ -145,6 +145,19 @@ template <> struct Pack<4> {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
 };
+template <> struct Pack<2> {   // 64-bit accesses: used for K > 4 where four pixels per thread would not fit in registers
+    static __device__ __forceinline__ void ld(float (&v)[2], const float* p) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void ld_rw(float (&v)[2], const float* p) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    }
+    static __device__ __forceinline__ void st(float* p, const float (&v)[2]) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    }
+};
 template <> struct Pack<1> {
     static __device__ __forceinline__ void ld(float (&v)[1], const float* p) { v[0] = __ldg(p); }
     static __device__ __forceinline__ void ld_rw(float (&v)[1], const float* p) { v[0] = *p; }

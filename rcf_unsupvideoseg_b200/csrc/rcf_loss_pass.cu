@@ -16,7 +16,7 @@
 #include "rcf_common.cuh"
 
 template <int K, int D, int PX, bool VIS>
-__global__ void __launch_bounds__(RCF_BLOCK, (K <= 4 && D <= 2) ? 2 : 1) k_loss(const RcfK a) {
+__global__ void __launch_bounds__(RCF_BLOCK, (D <= 2) ? 2 : 1) k_loss(const RcfK a) {
     constexpr int CF = rcf_cf(D);
     constexpr int GM = rcf_gm(K, D);
     constexpr int ITER = RCF_CHUNK_LOSS / (RCF_BLOCK * PX);
@@ -175,11 +175,12 @@ template <int K, int D>
 static cudaError_t launch_kd(const RcfK& a, bool vec, cudaStream_t s) {
     dim3 grid(a.nchunk2, a.nfd), block(RCF_BLOCK);
     const bool vis = a.vis_gt || a.vis_pred || a.vis_agg || a.vis_res || a.vis_aff;
+    constexpr int VPX = K <= 4 ? 4 : 2;     // pixels per thread on the vector path (register budget)
     if (vis) {
-        if (vec) k_loss<K, D, 4, true><<<grid, block, 0, s>>>(a);
+        if (vec) k_loss<K, D, VPX, true><<<grid, block, 0, s>>>(a);
         else k_loss<K, D, 1, true><<<grid, block, 0, s>>>(a);
     } else {
-        if (vec) k_loss<K, D, 4, false><<<grid, block, 0, s>>>(a);
+        if (vec) k_loss<K, D, VPX, false><<<grid, block, 0, s>>>(a);
         else k_loss<K, D, 1, false><<<grid, block, 0, s>>>(a);
     }
     return cudaGetLastError();

@@ -14,7 +14,7 @@
 // group the loop is pixel-outer so that all KG mask loads (+ the flow) of an iteration are in flight
 // together and the warp reductions happen once per CTA, not once per segment.
 template <int K, int D, int PX>
-__global__ void __launch_bounds__(RCF_BLOCK) k_moments(const RcfK a) {
+__global__ void __launch_bounds__(RCF_BLOCK, (D == 2 && K <= 4) ? 3 : 1) k_moments(const RcfK a) {
     constexpr int NS = rcf_ns(D);
     constexpr int ITER = RCF_CHUNK_MOM / (RCF_BLOCK * PX);
     constexpr int DD = D > 0 ? D : 1;

@@ -20,18 +20,23 @@ struct Tap {
     float sx, sy;        // d(position)/d(flow): 0 where 'border' clamped the coordinate
 };
 
-__device__ __forceinline__ Tap make_tap(float ix, float iy, int H, int W, int border) {
+// Sampling position = (col + fx, row + fy).  The integer cell and the fractional weights are derived from the
+// FLOW's own floor/frac (exact), not from the rounded sum: at column 800 an fp32 sum has an ulp of 6e-5 pixels,
+// which is what limits the reference's own fp32 grid_sample.
+__device__ __forceinline__ Tap make_tap(int col, int row, float fx, float fy, int H, int W, int border) {
     Tap t;
     t.sx = 1.0f; t.sy = 1.0f;
-    if (border) {
-        if (!(ix > 0.0f)) { ix = 0.0f; t.sx = 0.0f; }
-        else if (ix >= (float)(W - 1)) { ix = (float)(W - 1); t.sx = 0.0f; }
-        if (!(iy > 0.0f)) { iy = 0.0f; t.sy = 0.0f; }
-        else if (iy >= (float)(H - 1)) { iy = (float)(H - 1); t.sy = 0.0f; }
+    const float ffx = floorf(fx), ffy = floorf(fy);
+    t.wx = fx - ffx; t.wy = fy - ffy;
+    // clamp the integer part so that (int) conversion cannot overflow for wild flows
+    t.x0 = col + (int)fminf(fmaxf(ffx, -2.0e9f), 2.0e9f - 4096.0f - (float)col) ;
+    t.y0 = row + (int)fminf(fmaxf(ffy, -2.0e9f), 2.0e9f - 4096.0f - (float)row);
+    if (border) {   // clip_coordinates + zero gradient where clipped (position <= 0 or >= size-1)
+        if (t.x0 < 0 || (t.x0 == 0 && t.wx == 0.0f)) { t.x0 = 0; t.wx = 0.0f; t.sx = 0.0f; }
+        else if (t.x0 >= W - 1) { t.x0 = W - 1; t.wx = 0.0f; t.sx = 0.0f; }
+        if (t.y0 < 0 || (t.y0 == 0 && t.wy == 0.0f)) { t.y0 = 0; t.wy = 0.0f; t.sy = 0.0f; }
+        else if (t.y0 >= H - 1) { t.y0 = H - 1; t.wy = 0.0f; t.sy = 0.0f; }
     }
-    const float fx = floorf(ix), fy = floorf(iy);
-    t.x0 = (int)fx; t.y0 = (int)fy;
-    t.wx = ix - fx; t.wy = iy - fy;
     return t;
 }
 
@@ -45,7 +50,7 @@ __global__ void __launch_bounds__(256) k_flow_warp_fwd(const float* __restrict__
     if (p >= P) return;
     const int row = p / W, col = p - row * W;
     const float* fl = flow + (size_t)b * 2 * P;
-    const Tap t = make_tap((float)col + __ldg(fl + p), (float)row + __ldg(fl + P + p), H, W, border);
+    const Tap t = make_tap(col, row, __ldg(fl + p), __ldg(fl + P + p), H, W, border);
     const float w00 = (1.0f - t.wx) * (1.0f - t.wy), w10 = t.wx * (1.0f - t.wy);
     const float w01 = (1.0f - t.wx) * t.wy, w11 = t.wx * t.wy;
     const bool b00 = inb(t.x0, t.y0, H, W), b10 = inb(t.x0 + 1, t.y0, H, W);
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(256) k_flow_warp_bwd(const float* __restrict__
     if (p >= P) return;
     const int row = p / W, col = p - row * W;
     const float* fl = flow + (size_t)b * 2 * P;
-    const Tap t = make_tap((float)col + __ldg(fl + p), (float)row + __ldg(fl + P + p), H, W, border);
+    const Tap t = make_tap(col, row, __ldg(fl + p), __ldg(fl + P + p), H, W, border);
     const float w00 = (1.0f - t.wx) * (1.0f - t.wy), w10 = t.wx * (1.0f - t.wy);
     const float w01 = (1.0f - t.wx) * t.wy, w11 = t.wx * t.wy;
     const bool b00 = inb(t.x0, t.y0, H, W), b10 = inb(t.x0 + 1, t.y0, H, W);
