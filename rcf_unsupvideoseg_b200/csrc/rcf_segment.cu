@@ -12,16 +12,25 @@
 // One CTA per frame-direction; cost is O(K * (NS*nchunk + Cf^2)) -- microseconds.
 #include "rcf_common.cuh"
 
-// sum `nchunk` fp32 partials of each of `nstat` statistics ([stat][chunk] layout); warp per stat,
-// lanes stride over chunks, butterfly in fp64: the order is fixed by (nchunk) only.
+// Sum `nchunk` fp32 partials of each of `nstat` statistics ([stat][chunk] layout) in fp64.  LPS lanes cooperate on
+// one statistic (LPS = smallest power of two >= nchunk, capped at 32) so that small frames (few chunks) reduce
+// 32/LPS statistics per warp at once instead of paying one global-load latency per statistic.  The summation order
+// depends on nchunk only => bit-reproducible.  Loads bypass L1 (partials were written by other SMs).
 __device__ static void reduce_partials(const float* __restrict__ part, int nstat, int nchunk, double* out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int s = warp; s < nstat; s += nw) {
-        const float* p = part + (size_t)s * nchunk;
+    int lps = 1;
+    while (lps < nchunk && lps < 32) lps <<= 1;
+    const int tid = threadIdx.x;
+    const int sub = tid & (lps - 1);
+    const int per_pass = blockDim.x / lps;
+    for (int s0 = 0; s0 < nstat; s0 += per_pass) {     // uniform trip count: shuffles stay convergent
+        const int s = s0 + tid / lps;
         double v = 0.0;
-        for (int c = lane; c < nchunk; c += 32) v += (double)p[c];
-        v = warp_sum_d(v);
-        if (lane == 0) out[s] = v;
+        if (s < nstat) {
+            const float* p = part + (size_t)s * nchunk;
+            for (int c = sub; c < nchunk; c += lps) v += (double)__ldcg(p + c);
+        }
+        for (int o = lps >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (sub == 0 && s < nstat) out[s] = v;
     }
 }
 
@@ -318,37 +327,55 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
     }
 }
 
-// grid = Cf + 1 blocks.  Block i < Cf: row i of dW1 and db1[i].  Block Cf: dW2, db2.
-__global__ void k_mlp_param_grad(const RcfK a) {
+// grid = Cf + 1 blocks of 256 threads.  Block i < Cf: row i of dW1 and db1[i].  Block Cf: dW2, db2.
+// The segment sum is split over G = 256/64 thread groups (fixed partition) and combined through shared memory
+// in group order: deterministic, and 4x shorter dependent chains than one thread per output.
+__global__ void __launch_bounds__(256) k_mlp_param_grad(const RcfK a) {
     const int Cf = a.Cf, K = a.K, nseg = a.nfd * K;
     const int i = blockIdx.x;
-    if (i < Cf) {
-        for (int j = threadIdx.x; j < Cf; j += blockDim.x) {
-            double v = 0.0;
-            for (int s = 0; s < nseg; ++s)
-                v += a.dh[(size_t)s * Cf + i] * a.mlp[(size_t)s * 2 * Cf + j];
-            a.dw1[(size_t)i * Cf + j] = (float)v;
-        }
-        if (threadIdx.x == 0) {
-            double v = 0.0;
-            for (int s = 0; s < nseg; ++s) v += a.dh[(size_t)s * Cf + i];
-            a.db1[i] = (float)v;
-        }
-    } else {
-        for (int t = threadIdx.x; t < 2 * Cf; t += blockDim.x) {
-            const int c = t / Cf, j = t - c * Cf;
-            double v = 0.0;
-            for (int s = 0; s < nseg; ++s) {
-                const double hp = a.mlp[(size_t)s * 2 * Cf + Cf + j];
-                v += a.thbar[(size_t)s * 2 + c] * (hp >= 0.0 ? hp : 0.1 * hp);
+    __shared__ double part[256];
+    const int nout = (i < Cf) ? Cf + 1 : 2 * Cf + 2;        // outputs of this block (weights + bias)
+    int groups = 256 / ((nout + 31) / 32 * 32);
+    if (groups < 1) groups = 1;
+    const int lanes = 256 / groups;                          // threads per group (>= nout when groups > 1)
+    const int grp = threadIdx.x / lanes, t0 = threadIdx.x - grp * lanes;
+    const int s_lo = (int)((long long)nseg * grp / groups), s_hi = (int)((long long)nseg * (grp + 1) / groups);
+    for (int o0 = 0; o0 < nout; o0 += lanes) {
+        const int o = o0 + t0;
+        double v = 0.0;
+        if (o < nout && grp < groups) {
+            if (i < Cf) {
+                if (o < Cf) {
+                    for (int s = s_lo; s < s_hi; ++s) v += a.dh[(size_t)s * Cf + i] * a.mlp[(size_t)s * 2 * Cf + o];
+                } else {
+                    for (int s = s_lo; s < s_hi; ++s) v += a.dh[(size_t)s * Cf + i];
+                }
+            } else if (o < 2 * Cf) {
+                const int c = o / Cf, j = o - c * Cf;
+                for (int s = s_lo; s < s_hi; ++s) {
+                    const double hp = a.mlp[(size_t)s * 2 * Cf + Cf + j];
+                    v += a.thbar[(size_t)s * 2 + c] * (hp >= 0.0 ? hp : 0.1 * hp);
+                }
+            } else {
+                const int c = o - 2 * Cf;
+                for (int s = s_lo; s < s_hi; ++s) v += a.thbar[(size_t)s * 2 + c];
             }
-            a.dw2[(size_t)c * Cf + j] = (float)v;
         }
-        if (threadIdx.x < 2) {
-            double v = 0.0;
-            for (int s = 0; s < nseg; ++s) v += a.thbar[(size_t)s * 2 + threadIdx.x];
-            a.db2[threadIdx.x] = (float)v;
+        part[threadIdx.x] = v;
+        __syncthreads();
+        if (grp == 0 && o < nout) {
+            double tot = 0.0;
+            for (int g = 0; g < groups; ++g) tot += part[g * lanes + t0];
+            if (i < Cf) {
+                if (o < Cf) a.dw1[(size_t)i * Cf + o] = (float)tot;
+                else a.db1[i] = (float)tot;
+            } else if (o < 2 * Cf) {
+                a.dw2[o] = (float)tot;
+            } else {
+                a.db2[o - 2 * Cf] = (float)tot;
+            }
         }
+        __syncthreads();
     }
 }
 
@@ -383,7 +410,7 @@ cudaError_t rcf_launch_segment_bwd(const RcfK& a, cudaStream_t s) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (a.theta_mode == 1 && a.dw1 && a.db1 && a.dw2 && a.db2) {
-        k_mlp_param_grad<<<a.Cf + 1, 128, 0, s>>>(a);
+        k_mlp_param_grad<<<a.Cf + 1, 256, 0, s>>>(a);
         e = cudaGetLastError();
     }
     return e;
