@@ -159,8 +159,9 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_fwd(const RcfK a) {
         for (int t = tid; t < Cf * K; t += blockDim.x) {
             const int i = t / K, k = t - i * K;
             double v = (double)a.b1[i];
-            const float* w = a.w1 + (size_t)i * Cf;
-            for (int j = 0; j < Cf; ++j) v += (double)w[j] * pool[j * K + k];
+            const float* __restrict__ w = a.w1 + (size_t)i * Cf;
+#pragma unroll 8
+            for (int j = 0; j < Cf; ++j) v += (double)__ldg(w + j) * pool[j * K + k];
             hpre[t] = v;
             mlp[(size_t)k * 2 * Cf + Cf + i] = v;
             mlp[(size_t)k * 2 * Cf + i] = pool[t];
@@ -169,10 +170,11 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_fwd(const RcfK a) {
         if (tid < 2 * K) {
             const int c = tid / K, k = tid - c * K;
             double v = (double)a.b2[c];
-            const float* w = a.w2 + (size_t)c * Cf;
+            const float* __restrict__ w = a.w2 + (size_t)c * Cf;
+#pragma unroll 8
             for (int i = 0; i < Cf; ++i) {
                 const double h = hpre[i * K + k];
-                v += (double)w[i] * (h >= 0.0 ? h : 0.1 * h);
+                v += (double)__ldg(w + i) * (h >= 0.0 ? h : 0.1 * h);
             }
             theta_s[c * K + k] = v;
         }
@@ -309,7 +311,8 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
         for (int t = tid; t < Cf * K; t += blockDim.x) {
             const int k = t / Cf, j = t - k * Cf;       // consecutive threads -> consecutive j (coalesced w1 reads)
             double v = 0.0;
-            for (int i = 0; i < Cf; ++i) v += (double)a.w1[(size_t)i * Cf + j] * dh[i * K + k];
+#pragma unroll 8
+            for (int i = 0; i < Cf; ++i) v += (double)__ldg(a.w1 + (size_t)i * Cf + j) * dh[i * K + k];
             pbar[j * K + k] = v;
             a.poolbar[((size_t)fd * Cf + j) * K + k] = (float)(v / sd[k * SEGD]);
         }
@@ -333,6 +336,9 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
 __global__ void __launch_bounds__(256) k_mlp_param_grad(const RcfK a) {
     const int Cf = a.Cf, K = a.K, nseg = a.nfd * K;
     const int i = blockIdx.x;
+    const double* __restrict__ dh = a.dh;
+    const double* __restrict__ mlp = a.mlp;
+    const double* __restrict__ thbar = a.thbar;
     __shared__ double part[256];
     const int nout = (i < Cf) ? Cf + 1 : 2 * Cf + 2;        // outputs of this block (weights + bias)
     int groups = 256 / ((nout + 31) / 32 * 32);
@@ -346,19 +352,23 @@ __global__ void __launch_bounds__(256) k_mlp_param_grad(const RcfK a) {
         if (o < nout && grp < groups) {
             if (i < Cf) {
                 if (o < Cf) {
-                    for (int s = s_lo; s < s_hi; ++s) v += a.dh[(size_t)s * Cf + i] * a.mlp[(size_t)s * 2 * Cf + o];
+#pragma unroll 8
+                    for (int s = s_lo; s < s_hi; ++s) v += __ldg(dh + (size_t)s * Cf + i) * __ldg(mlp + (size_t)s * 2 * Cf + o);
                 } else {
-                    for (int s = s_lo; s < s_hi; ++s) v += a.dh[(size_t)s * Cf + i];
+#pragma unroll 8
+                    for (int s = s_lo; s < s_hi; ++s) v += __ldg(dh + (size_t)s * Cf + i);
                 }
             } else if (o < 2 * Cf) {
                 const int c = o / Cf, j = o - c * Cf;
+#pragma unroll 8
                 for (int s = s_lo; s < s_hi; ++s) {
-                    const double hp = a.mlp[(size_t)s * 2 * Cf + Cf + j];
-                    v += a.thbar[(size_t)s * 2 + c] * (hp >= 0.0 ? hp : 0.1 * hp);
+                    const double hp = __ldg(mlp + (size_t)s * 2 * Cf + Cf + j);
+                    v += __ldg(thbar + (size_t)s * 2 + c) * (hp >= 0.0 ? hp : 0.1 * hp);
                 }
             } else {
                 const int c = o - 2 * Cf;
-                for (int s = s_lo; s < s_hi; ++s) v += a.thbar[(size_t)s * 2 + c];
+#pragma unroll 8
+                for (int s = s_lo; s < s_hi; ++s) v += __ldg(thbar + (size_t)s * 2 + c);
             }
         }
         part[threadIdx.x] = v;
