@@ -52,6 +52,19 @@ def workload_config(n_gpus):
     }
 
 
+def read_traffic(kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    try:
+        with open(p) as f:
+            for name, rec in json.load(f).items():
+                if kernel_prefix in name:
+                    return rec["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -396,7 +409,7 @@ def run_ours(args):
                     "note": "PCIe-bound; copies of neighbouring steps overlap compute on 3 streams"},
             "gpu_launches": 7 * args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_bwd<K=4,D=0,PX=4> (streaming backward)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": read_traffic("k_bwd<4, 0, 4>"),
                          "peak_source": peak_src, "kernel_ms": kb_mean, "kernel_ms_min": kb_ms[0],
                          "algorithmic_bytes_per_launch": kb_bytes},
             "step_roofline": {"algorithmic_gbs": step_gbs, "frac": step_gbs / peak,

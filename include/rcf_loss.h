@@ -84,6 +84,10 @@ typedef struct RcfDesc {
     int64_t vis_bstride;
     int64_t vis_dstride;
     float vis_scale[2];
+    /* LeakyReLU fused into the feature loads: when feat holds the PRE-activation of the last conv of
+       flow_feat_before_agg (reference :89-92), set the negative slope here (0.1) and the library applies the
+       activation on load and its derivative to dfeat; 0 or 1 means feat is used as it is. */
+    float feat_lrelu_slope;
 } RcfDesc;
 
 typedef struct RcfInputs {

@@ -40,6 +40,7 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.inv_n = d.inv_n > 0.0f ? d.inv_n : (float)(1.0 / ((double)d.B * 2.0 * d.H * d.W));
     a.cy = 0.5f * (float)(d.H - 1); a.cx = 0.5f * (float)(d.W - 1);
     a.sy = 1.0f / fmaxf(a.cy, 1.0f); a.sx = 1.0f / fmaxf(a.cx, 1.0f);
+    a.feat_slope = (d.feat_lrelu_slope > 0.0f) ? d.feat_lrelu_slope : 1.0f;
     for (int i = 0; i < 2; ++i) {
         a.mask[i] = in.mask[i]; a.flow[i] = in.flow[i]; a.resid[i] = in.resid[i];
         a.feat[i] = in.feat[i]; a.theta[i] = in.theta[i];

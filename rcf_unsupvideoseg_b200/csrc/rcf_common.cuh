@@ -95,6 +95,7 @@ struct RcfK {
     float clamp_t;      // <0: none
     float inv_n;
     float cy, cx, sy, sx;  // coordinate centring / scaling (u = ((row-cy)*sy, (col-cx)*sx))
+    float feat_slope;      // LeakyReLU slope applied to feat on load (1 = none)
     const float* mask[2];
     const float* flow[2];
     const float* resid[2];

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool(const RcfK a, int f_per_cta)
     const int f_end = min(Cf, f_begin + f_per_cta);
     const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
     const float* __restrict__ feat = a.feat[dir] + (long long)b * a.feat_bs[dir];
+    const float slope = a.feat_slope;     // fused LeakyReLU of the last conv (1 = feat already activated)
 
 #pragma unroll
     for (int k = 0; k < K; ++k) {
@@ -54,8 +55,11 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool(const RcfK a, int f_per_cta)
                 float gv[FB][PX];
 #pragma unroll
                 for (int q = 0; q < FB; ++q) {
-                    if (f0 + q < f_end) Pack<PX>::ld(gv[q], feat + (long long)(f0 + q) * P + p0 + i);
-                    else {
+                    if (f0 + q < f_end) {
+                        Pack<PX>::ld(gv[q], feat + (long long)(f0 + q) * P + p0 + i);
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) gv[q][j] = gv[q][j] >= 0.0f ? gv[q][j] : slope * gv[q][j];
+                    } else {
 #pragma unroll
                         for (int j = 0; j < PX; ++j) gv[q][j] = 0.0f;
                     }
@@ -100,6 +104,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
 
     for (int i = tid; i < Cf * K; i += RCF_BLOCK) cs[i] = a.poolbar[(size_t)fd * Cf * K + i];
     __syncthreads();
+    const float slope = a.feat_slope;
 
     const int p = (blockIdx.x * RCF_BLOCK + tid) * PX;
     if (p >= P) return;
@@ -118,8 +123,13 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
     for (int f = 0; f < Cf; ++f) {
         float gv[PX], dg[PX];
         Pack<PX>::ld(gv, feat + (long long)f * P + p);
+        float dact[PX];      // d lrelu(pre) / d pre
 #pragma unroll
-        for (int j = 0; j < PX; ++j) dg[j] = 0.0f;
+        for (int j = 0; j < PX; ++j) {
+            dact[j] = gv[j] >= 0.0f ? 1.0f : slope;
+            gv[j] *= dact[j];
+            dg[j] = 0.0f;
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const float c = cs[f * K + k];
@@ -129,7 +139,11 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
                 dg[j] = fmaf(c, m[k][j], dg[j]);
             }
         }
-        if (dfeat) Pack<PX>::st(dfeat + (long long)f * P + p, dg);
+        if (dfeat) {
+#pragma unroll
+            for (int j = 0; j < PX; ++j) dg[j] *= dact[j];
+            Pack<PX>::st(dfeat + (long long)f * P + p, dg);
+        }
     }
     if (dmask) {
 #pragma unroll

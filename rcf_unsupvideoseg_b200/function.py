@@ -33,6 +33,7 @@ class LossSpec:
     inv_n: float = 0.0              # 0 => 1/(B*2*H*W); set for batch-sharded (multi-GPU) use
     want_vis: bool = False
     vis_scale: Tuple[float, float] = (1.0, 1.0)
+    feat_lrelu_slope: float = 1.0   # 0.1: `feat` is the pre-activation of the last conv, LeakyReLU fused into the kernels
 
     @property
     def theta_mode(self) -> int:
@@ -85,6 +86,7 @@ def _make_desc(spec: LossSpec, B: int, ndir: int) -> _lib.RcfDesc:
     d.resid_scale, d.pred_div = spec.resid_scale, spec.pred_div
     d.clamp_t = -1.0 if spec.clamp_t is None else float(spec.clamp_t)
     d.inv_n = spec.inv_n
+    d.feat_lrelu_slope = spec.feat_lrelu_slope
     return d
 
 

@@ -159,6 +159,13 @@ class FlowAggregationHeadWithResidual(nn.Module):
             # the reference reaches `return ..., residual_adjustment, ...` with the name unbound (:305-310)
             raise UnboundLocalError("local variable 'residual_adjustment' referenced before assignment")
 
+    def _features_preact(self, flow):
+        """conv -> LeakyReLU -> conv of flow_feat_before_agg (reference :84-91); the trailing LeakyReLU (:92) is applied
+        inside the pooling kernels (and its derivative inside the pooling backward), which saves one full read+write
+        of the [B,Cf,H,W] map in forward and one read + one read+write in backward."""
+        seq = self.flow_feat_before_agg
+        return seq[2](seq[1](seq[0](flow)))
+
     def _spec(self, K, H, W, *, want_vis, vis_norm, inv_n=0.0, clamp_fused=True) -> LossSpec:
         unbounded = bool(self.free_residual and self.residual_adjustment_scale == -1.)
         return LossSpec(K=K, H=H, W=W, D=self._D, Cf=self.num_flow_feat_channels,
@@ -166,7 +173,8 @@ class FlowAggregationHeadWithResidual(nn.Module):
                         resid_scale=float(self.residual_adjustment_scale), pred_div=float(self.pred_div_coeff),
                         clamp_t=(self.clamp_flow_t if clamp_fused else None), unbounded_residual=unbounded,
                         inv_n=inv_n, want_vis=want_vis,
-                        vis_scale=((2.0 / H, 2.0 / W) if vis_norm else (1.0, 1.0)))
+                        vis_scale=((2.0 / H, 2.0 / W) if vis_norm else (1.0, 1.0)),
+                        feat_lrelu_slope=float(self.flow_feat_before_agg[3].negative_slope))
 
     def _prepare(self, flow, resid, H, W):
         """Returns (flow for the kernels, flow for the conv branch, clamp_fused, residual at mask_size)."""
@@ -201,7 +209,7 @@ class FlowAggregationHeadWithResidual(nn.Module):
                 assert r.shape[-2:] == (H, W), f"residual spatial size {tuple(r.shape[-2:])} != mask size {(H, W)}"
                 k_flows.append(kf.detach()); c_flows.append(cf_); rs.append(r)
             # one pass of the conv branch over both directions (batch-concatenated), then a free 5-D view
-            feat = self.flow_feat_before_agg(torch.cat(c_flows, 0) if ndir > 1 else c_flows[0])
+            feat = self._features_preact(torch.cat(c_flows, 0) if ndir > 1 else c_flows[0])
             assert feat.shape[2:] == masks5.shape[3:], \
                 f"{feat.shape[2:]} != {masks5.shape[3:]} (should match on spatial dimension)"   # :247-248
             feat = feat.view(ndir, B, *feat.shape[1:])
@@ -232,7 +240,7 @@ class FlowAggregationHeadWithResidual(nn.Module):
         if self.allow_residual_resize and tuple(resid.shape[-2:]) != self.mask_size:
             resid = F.interpolate(resid, self.mask_size, mode='bilinear')
         with torch.no_grad(), torch.autocast(device_type="cuda", enabled=False):
-            feat = self.flow_feat_before_agg(flow)
+            feat = self._features_preact(flow)
             assert feat.shape[2:] == mask.shape[2:], f"{feat.shape[2:]} != {mask.shape[2:]} (should match on spatial dimension)"
             spec = self._spec(K, H, W, want_vis=True, vis_norm=False, clamp_fused=False)
             _, vis = rcf_motion_loss(spec, mask.float().unsqueeze(1), [flow], [resid], feats=feat.unsqueeze(0),

@@ -320,3 +320,61 @@ def test_scope_h_large_feature_map_vs_oracle(rcf):
     assert rel_l2(grads["d_resid_fw"].cpu().numpy(), g_o["d_resid_fw"]) <= GRAD_RTOL
     for k, p in head.named_parameters():
         assert rel_l2(p.grad.cpu().numpy(), g_o["params"][k]) <= 3e-4, k
+
+
+@pytest.mark.parametrize("B,K,H,W,D,robust,unbounded", [
+    (1, 1, 1, 5, 0, False, False),       # single row, single segment
+    (2, 3, 5, 7, 2, False, False),       # odd sizes -> scalar path, one partial chunk
+    (1, 4, 1, 64, 0, True, False),
+    (3, 7, 9, 11, 0, False, True),       # residual_adjustment_scale == -1
+    (1, 6, 17, 4, 5, False, False),      # quadratic fit, K > 4 (64-bit packs not applicable: P % 4 == 0 but tiny)
+    (2, 5, 33, 65, 2, True, False),      # spans several chunks of every kernel on the scalar path
+    (300, 2, 4, 4, 0, False, False),     # many frame-directions (grid.y = 600)
+    (2, 8, 48, 48, 2, False, False),     # STv2 training shape with K = 8: 64-bit vector path
+])
+def test_edge_shapes_vs_oracle(rcf, B, K, H, W, D, robust, unbounded):
+    cfg = O.OracleConfig(mask_layer=K, mask_size=(H, W), num_flow_feat_channels=2, flow_feat_before_agg_kernel_size=1,
+                         clamp_flow_t=20.0, outlier_robust_loss=robust, free_residual=(D == 0),
+                         free_residual_with_affine=(D > 0), free_residual_with_affine_quadratic=(D == 5),
+                         residual_adjustment_scale=(-1.0 if unbounded else 10.0))
+    params = O.init_params(cfg, seed=8)
+    params["flow_feat_after_agg.2.weight"] = np.zeros_like(params["flow_feat_after_agg.2.weight"])
+    params["flow_feat_after_agg.2.bias"] = np.array([0.75, -1.5])
+    masks, fw, bw, rfw, rbw = O.synthetic_inputs(B, K, H, W, seed=31)
+    _, loss_o, caches = O.head_forward(masks, fw, bw, rfw, rbw, params, cfg)
+    g_o = O.head_backward(caches, params, gbar=1.0)
+    spec = rcf.LossSpec(K=K, H=H, W=W, D=D, Cf=0, robust=robust, clamp_t=20.0, unbounded_residual=unbounded,
+                        resid_scale=(-1.0 if unbounded else 10.0))
+    tm = torch.from_numpy(masks).cuda().requires_grad_(True)
+    flows = [torch.from_numpy(fw[:, 0]).cuda(), torch.from_numpy(bw[:, 0]).cuda()]
+    resids = [torch.from_numpy(rfw).cuda().requires_grad_(True), torch.from_numpy(rbw).cuda().requires_grad_(True)]
+    thetas = [torch.tensor([0.75, -1.5], device="cuda").view(1, 2, 1).expand(B, 2, K).contiguous() for _ in range(2)]
+    loss, _ = rcf.rcf_motion_loss(spec, tm, flows, resids, thetas=thetas)
+    loss.sum().backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss.sum()) - loss_o["seg"]) <= LOSS_RTOL * loss_o["seg"]
+    tol = GRAD_RTOL if D < 5 else 5e-3
+    assert rel_l2(tm.grad.cpu().numpy(), g_o["d_masks"]) <= tol
+    assert rel_l2(resids[0].grad.cpu().numpy(), g_o["d_resid_fw"]) <= tol
+    assert rel_l2(resids[1].grad.cpu().numpy(), g_o["d_resid_bw"]) <= tol
+
+
+def test_single_direction_and_detached_inputs(rcf):
+    """ndir = 1 calls and inputs that do not need gradients (NULL gradient pointers in the C ABI)."""
+    B, K, H, W = 2, 4, 16, 16
+    masks, fw, bw, rfw, rbw = _torch_inputs(B, K, H, W, seed=2)
+    spec = rcf.LossSpec(K=K, H=H, W=W, D=2, Cf=0, clamp_t=20.0)
+    th = [torch.randn(B, 2, K, device="cuda") for _ in range(2)]
+    both, _ = rcf.rcf_motion_loss(spec, masks, [fw[:, 0], bw[:, 0]], [rfw, rbw], thetas=th)
+    one, _ = rcf.rcf_motion_loss(spec, masks[:, 1:2], [bw[:, 0]], [rbw], thetas=[th[1]])
+    assert torch.equal(one[0], both[1])
+    m = masks.clone().requires_grad_(True)
+    loss, _ = rcf.rcf_motion_loss(spec, m, [fw[:, 0], bw[:, 0]], [rfw, rbw], thetas=th)     # residuals detached
+    loss.sum().backward()
+    r = rfw.clone().requires_grad_(True)
+    loss2, _ = rcf.rcf_motion_loss(spec, masks, [fw[:, 0], bw[:, 0]], [r, rbw], thetas=th)  # masks detached
+    loss2.sum().backward()
+    mm = masks.clone().requires_grad_(True); rr = rfw.clone().requires_grad_(True)
+    loss3, _ = rcf.rcf_motion_loss(spec, mm, [fw[:, 0], bw[:, 0]], [rr, rbw], thetas=th)
+    loss3.sum().backward()
+    assert torch.equal(m.grad, mm.grad) and torch.equal(r.grad, rr.grad)

@@ -78,5 +78,23 @@ def full(path):
         print()
 
 
+def traffic(path):
+    """JSON {kernel name: dram bytes read+written per launch} (mean over captured launches) for bench.py's roofline.traffic."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = collections.defaultdict(list)
+    for r in data:
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[idx[k]].replace(",", "")) * scale[units[idx[k]]]
+        acc[r[idx["Kernel Name"]]].append(tot)
+    print(json.dumps({k: {"dram_bytes_per_launch": sum(v) / len(v), "launches": len(v), "source": path} for k, v in acc.items()},
+                     indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
