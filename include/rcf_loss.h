@@ -172,6 +172,12 @@ RCF_API int rcf_corresponding_map(const float* coords, float* out, void* scratch
 #define RCF_TIME_POOL_BWD 5
 RCF_API int rcf_debug_time_kernel(int which, void* start_event, void* stop_event);
 
+/* Implementation switches for A/B measurements (process-wide; results are bit-identical either way).
+ * RCF_OPT_FUSED_FORWARD (default 1): theta_mode 0 on the vector path runs pass 1, the per-segment solve and pass 2 as
+ * one ticket-ordered launch so that pass 2 re-reads the masks from L2; 0 = three separate launches. */
+#define RCF_OPT_FUSED_FORWARD 1
+RCF_API int rcf_debug_set_option(int option, int value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,7 +55,8 @@ class RcfGrads(C.Structure):
 
 
 EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "rcf_forward", "rcf_backward",
-                    "rcf_debug_time_kernel", "rcf_flow_warp_forward", "rcf_flow_warp_backward", "rcf_corresponding_map")
+                    "rcf_debug_time_kernel", "rcf_flow_warp_forward", "rcf_flow_warp_backward", "rcf_corresponding_map",
+                    "rcf_debug_set_option")
 
 _lib = None
 _lock = threading.Lock()
@@ -107,6 +108,8 @@ def load_library(build_if_missing: bool = True):
                                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.rcf_corresponding_map.restype = C.c_int
         lib.rcf_corresponding_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.rcf_debug_set_option.restype = C.c_int
+        lib.rcf_debug_set_option.argtypes = [C.c_int, C.c_int]
         if lib.rcf_abi_version() != RCF_ABI_VERSION:
             raise RcfLibraryError(f"ABI mismatch: library {lib.rcf_abi_version()} vs binding {RCF_ABI_VERSION}")
         _lib = lib

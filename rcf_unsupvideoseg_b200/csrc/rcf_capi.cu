@@ -62,6 +62,8 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.poolbar = reinterpret_cast<float*>(w + L.w_poolbar);
     a.dh = reinterpret_cast<double*>(w + L.w_dh);
     a.thbar = reinterpret_cast<double*>(w + L.w_thbar);
+    a.sync = reinterpret_cast<int*>(w + L.w_sync);
+    a.lag = 2;
     a.nchunk1 = L.nchunk1; a.nchunk2 = L.nchunk2; a.nchunkb = L.nchunkb; a.nchunkp = L.nchunkp;
 }
 
@@ -87,6 +89,8 @@ bool vec_ok_inputs(const RcfDesc& d, const RcfInputs& in, bool with_feat) {
     return true;
 }
 
+int g_fused_forward = 1;   // rcf_debug_set_option(RCF_OPT_FUSED_FORWARD, 0/1)
+
 struct TimeHook { int which = 0; cudaEvent_t start = nullptr, stop = nullptr; };
 TimeHook g_hook;   // process-wide: autograd runs rcf_backward on its own device thread
 
@@ -106,6 +110,11 @@ extern "C" int rcf_debug_time_kernel(int which, void* start_event, void* stop_ev
     g_hook.start = static_cast<cudaEvent_t>(start_event);
     g_hook.stop = static_cast<cudaEvent_t>(stop_event);
     return RCF_OK;
+}
+
+extern "C" int rcf_debug_set_option(int option, int value) {
+    if (option == RCF_OPT_FUSED_FORWARD) { g_fused_forward = value ? 1 : 0; return RCF_OK; }
+    return RCF_ERR_MODE;
 }
 
 extern "C" int rcf_abi_version(void) { return RCF_ABI_VERSION; }
@@ -156,10 +165,16 @@ extern "C" int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss
             if (p && (!aligned16(p) || desc->vis_bstride % 4 || desc->vis_dstride % 4)) vec = false;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    { ScopedTime t(RCF_TIME_MOMENTS, s); RCF_CUDA(rcf_launch_moments(a, vec, s)); }
-    if (desc->theta_mode == 1) { ScopedTime t(RCF_TIME_POOL, s); RCF_CUDA(rcf_launch_pool(a, vec_ok_inputs(*desc, *in, true), s)); }
-    RCF_CUDA(rcf_launch_segment_fwd(a, s));
-    { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_loss(a, vec, s)); }
+    if (desc->theta_mode == 0 && vec && g_fused_forward) {
+        // one launch: pass 1, per-segment solve and pass 2, ordered for L2 reuse of the masks (rcf_forward_fused.cu)
+        RCF_CUDA(cudaMemsetAsync(a.sync, 0, (size_t)(1 + 2 * L.nfd) * sizeof(int), s));
+        { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_forward_fused(a, s)); }
+    } else {
+        { ScopedTime t(RCF_TIME_MOMENTS, s); RCF_CUDA(rcf_launch_moments(a, vec, s)); }
+        if (desc->theta_mode == 1) { ScopedTime t(RCF_TIME_POOL, s); RCF_CUDA(rcf_launch_pool(a, vec_ok_inputs(*desc, *in, true), s)); }
+        RCF_CUDA(rcf_launch_segment_fwd(a, s));
+        { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_loss(a, vec, s)); }
+    }
     RCF_CUDA(rcf_launch_finalize(a, s));
     return RCF_OK;
 }

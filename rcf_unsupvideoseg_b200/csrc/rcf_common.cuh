@@ -45,7 +45,7 @@ struct RcfLayout {
     // ctx (bytes offsets)
     size_t c_segd, c_coef, c_mlp, c_gm, c_bytes;
     // ws
-    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_bytes;
+    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_sync, w_bytes;
 };
 
 static inline size_t rcf_align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -80,6 +80,7 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.w_poolbar = o; o = rcf_align256(o + nseg * d.Cf * sizeof(float));
     L.w_dh = o;      o = rcf_align256(o + nseg * d.Cf * sizeof(double));
     L.w_thbar = o;   o = rcf_align256(o + nseg * 2 * sizeof(double));
+    L.w_sync = o;    o = rcf_align256(o + (size_t)(1 + 2 * L.nfd) * sizeof(int));   // ticket, pass-1 counters, ready flags
     L.w_bytes = o ? o : 256;
     return L;
 }
@@ -118,6 +119,8 @@ struct RcfK {
     double* dh;
     double* thbar;
     int nchunk1, nchunk2, nchunkb, nchunkp;
+    int* sync;     // fused forward: [0] ticket, [1..nfd] pass-1 arrival counters, [1+nfd..] ready flags
+    int lag;       // fused forward: pass 2 of frame-direction t is scheduled LAG slots after its pass 1
     // forward outputs
     float* loss;
     float* vis_gt; float* vis_pred; float* vis_agg; float* vis_res; float* vis_aff;
@@ -274,6 +277,7 @@ __device__ __forceinline__ void loss_terms(float d, const RcfK& a, float& phi, f
 
 // launchers (one translation unit each)
 cudaError_t rcf_launch_moments(const RcfK& a, bool vec, cudaStream_t s);
+cudaError_t rcf_launch_forward_fused(const RcfK& a, cudaStream_t s);
 cudaError_t rcf_launch_pool(const RcfK& a, bool vec, cudaStream_t s);
 cudaError_t rcf_launch_segment_fwd(const RcfK& a, cudaStream_t s);
 cudaError_t rcf_launch_loss(const RcfK& a, bool vec, cudaStream_t s);

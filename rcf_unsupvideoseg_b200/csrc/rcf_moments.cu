@@ -8,105 +8,12 @@
 // converts them to the de-meaned covariances in fp64.
 //
 // HBM-bound: algorithmic bytes per pixel = 4K (+8 with the affine fit).
-#include "rcf_common.cuh"
+#include "rcf_moments_dev.cuh"
 
-// Segments are processed in groups of KG (as many as keep KG*NS accumulators in registers); inside a
-// group the loop is pixel-outer so that all KG mask loads (+ the flow) of an iteration are in flight
-// together and the warp reductions happen once per CTA, not once per segment.
 template <int K, int D, int PX>
 __global__ void __launch_bounds__(RCF_BLOCK, (D == 2 && K <= 4) ? 3 : 1) k_moments(const RcfK a) {
-    constexpr int NS = rcf_ns(D);
-    constexpr int ITER = RCF_CHUNK_MOM / (RCF_BLOCK * PX);
-    constexpr int DD = D > 0 ? D : 1;
-    constexpr int KG = (D == 0) ? K : (D == 2 ? (K < 4 ? K : 4) : 1);
-    __shared__ float red[RCF_WARPS][K * NS];
-
-    const int fd = blockIdx.y;
-    const int dir = fd / a.B;
-    const int b = fd - dir * a.B;
-    const int chunk = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
-    const float* __restrict__ flow = a.flow[dir] + (long long)b * a.flow_bs[dir];
-    const int P = a.P;
-    const int p0 = chunk * RCF_CHUNK_MOM;
-
-#pragma unroll 1
-    for (int k0 = 0; k0 < K; k0 += KG) {
-        float acc[KG * NS];
-#pragma unroll
-        for (int i = 0; i < KG * NS; ++i) acc[i] = 0.0f;
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int p = p0 + (it * RCF_BLOCK + tid) * PX;
-            if (p < P) {
-                float m[KG][PX];
-#pragma unroll
-                for (int k = 0; k < KG; ++k) {
-                    if (k0 + k < K) Pack<PX>::ld(m[k], mask + (long long)(k0 + k) * P + p);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < PX; ++j) m[k][j] = 0.0f;
-                    }
-                }
-                if constexpr (D == 0) {
-#pragma unroll
-                    for (int k = 0; k < KG; ++k)
-#pragma unroll
-                        for (int j = 0; j < PX; ++j) acc[k] += m[k][j];
-                } else {
-                    float f0[PX], f1[PX], y[PX], x[PX];
-                    Pack<PX>::ld(f0, flow + p);
-                    Pack<PX>::ld(f1, flow + P + p);
-                    px_coords<PX>(p, a, y, x);
-#pragma unroll
-                    for (int j = 0; j < PX; ++j) {
-                        // z = (1, F0, F1, u, F0*u, F1*u, u_d*u_e): shared by all segments, then acc += m_k * z
-                        float z[NS], u[DD];
-                        px_feats<D>(y[j], x[j], u);
-                        z[0] = 1.0f;
-                        z[1] = clamp_flow(f0[j], a.clamp_t);
-                        z[2] = clamp_flow(f1[j], a.clamp_t);
-#pragma unroll
-                        for (int d = 0; d < D; ++d) {
-                            z[3 + d] = u[d];
-                            z[3 + D + d] = z[1] * u[d];
-                            z[3 + 2 * D + d] = z[2] * u[d];
-#pragma unroll
-                            for (int e = d; e < D; ++e) z[3 + 3 * D + rcf_sym_idx(D, d, e)] = u[d] * u[e];
-                        }
-#pragma unroll
-                        for (int k = 0; k < KG; ++k) {
-                            acc[k * NS] += m[k][j];
-#pragma unroll
-                            for (int s2 = 1; s2 < NS; ++s2) acc[k * NS + s2] = fmaf(m[k][j], z[s2], acc[k * NS + s2]);
-                        }
-                    }
-                }
-            }
-        }
-        // one vector reduction per group; rows past K (padding of the last group) are never stored
-        if (k0 + KG <= K) {
-            warp_reduce_store<KG * NS>(acc, lane, &red[warp][k0 * NS]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < KG; ++k) {
-                if (k0 + k < K) {
-                    float one[NS];
-#pragma unroll
-                    for (int s2 = 0; s2 < NS; ++s2) one[s2] = acc[k * NS + s2];
-                    warp_reduce_store<NS>(one, lane, &red[warp][(k0 + k) * NS]);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < K * NS; i += RCF_BLOCK) {
-        float v = 0.0f;
-#pragma unroll
-        for (int w = 0; w < RCF_WARPS; ++w) v += red[w][i];
-        a.part1[((size_t)fd * (K * NS) + i) * a.nchunk1 + chunk] = v;
-    }
+    __shared__ float red[RCF_WARPS][K * rcf_ns(D)];
+    moments_tile<K, D, PX>(a, blockIdx.y, blockIdx.x, red);
 }
 
 template <int K, int D>
