@@ -173,9 +173,12 @@ RCF_API int rcf_corresponding_map(const float* coords, float* out, void* scratch
 RCF_API int rcf_debug_time_kernel(int which, void* start_event, void* stop_event);
 
 /* Implementation switches for A/B measurements (process-wide; results are bit-identical either way).
- * RCF_OPT_FUSED_FORWARD (default 1): theta_mode 0 on the vector path runs pass 1, the per-segment solve and pass 2 as
- * one ticket-ordered launch so that pass 2 re-reads the masks from L2; 0 = three separate launches. */
+ * RCF_OPT_FUSED_FORWARD (default 0): theta_mode 0 on the vector path runs pass 1, the per-segment solve and pass 2 as
+ * one persistent, ticket-ordered launch so that pass 2 re-reads the masks from L2 (DRAM traffic -18 % in forward,
+ * but measured ~6 % slower on B200 at 2 CTAs/SM: kept as an experiment); 0 = three separate launches. */
 #define RCF_OPT_FUSED_FORWARD 1
+#define RCF_OPT_FUSED_LAG 2      /* slots between pass 1 and pass 2 of a frame-direction (1..64) */
+#define RCF_OPT_L2_HINTS 3       /* evict-first streaming loads in pass 2 of the fused forward */
 RCF_API int rcf_debug_set_option(int option, int value);
 
 #ifdef __cplusplus

@@ -8,6 +8,10 @@
 
 namespace {
 
+int g_fused_forward = 0;   // rcf_debug_set_option(RCF_OPT_FUSED_FORWARD, 0/1); off: measured slower, see DESIGN.md
+int g_fused_lag = 4;       // RCF_OPT_FUSED_LAG
+int g_l2_hints = 1;        // RCF_OPT_L2_HINTS
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
@@ -63,7 +67,8 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.dh = reinterpret_cast<double*>(w + L.w_dh);
     a.thbar = reinterpret_cast<double*>(w + L.w_thbar);
     a.sync = reinterpret_cast<int*>(w + L.w_sync);
-    a.lag = 2;
+    a.lag = g_fused_lag;
+    a.l2_hints = 0;
     a.nchunk1 = L.nchunk1; a.nchunk2 = L.nchunk2; a.nchunkb = L.nchunkb; a.nchunkp = L.nchunkp;
 }
 
@@ -89,8 +94,6 @@ bool vec_ok_inputs(const RcfDesc& d, const RcfInputs& in, bool with_feat) {
     return true;
 }
 
-int g_fused_forward = 1;   // rcf_debug_set_option(RCF_OPT_FUSED_FORWARD, 0/1)
-
 struct TimeHook { int which = 0; cudaEvent_t start = nullptr, stop = nullptr; };
 TimeHook g_hook;   // process-wide: autograd runs rcf_backward on its own device thread
 
@@ -114,6 +117,8 @@ extern "C" int rcf_debug_time_kernel(int which, void* start_event, void* stop_ev
 
 extern "C" int rcf_debug_set_option(int option, int value) {
     if (option == RCF_OPT_FUSED_FORWARD) { g_fused_forward = value ? 1 : 0; return RCF_OK; }
+    if (option == RCF_OPT_FUSED_LAG && value >= 1 && value <= 64) { g_fused_lag = value; return RCF_OK; }
+    if (option == RCF_OPT_L2_HINTS) { g_l2_hints = value ? 1 : 0; return RCF_OK; }
     return RCF_ERR_MODE;
 }
 
@@ -168,6 +173,7 @@ extern "C" int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss
     if (desc->theta_mode == 0 && vec && g_fused_forward) {
         // one launch: pass 1, per-segment solve and pass 2, ordered for L2 reuse of the masks (rcf_forward_fused.cu)
         RCF_CUDA(cudaMemsetAsync(a.sync, 0, (size_t)(1 + 2 * L.nfd) * sizeof(int), s));
+        a.l2_hints = g_l2_hints;
         { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_forward_fused(a, s)); }
     } else {
         { ScopedTime t(RCF_TIME_MOMENTS, s); RCF_CUDA(rcf_launch_moments(a, vec, s)); }

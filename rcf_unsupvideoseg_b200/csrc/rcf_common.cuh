@@ -121,6 +121,7 @@ struct RcfK {
     int nchunk1, nchunk2, nchunkb, nchunkp;
     int* sync;     // fused forward: [0] ticket, [1..nfd] pass-1 arrival counters, [1+nfd..] ready flags
     int lag;       // fused forward: pass 2 of frame-direction t is scheduled LAG slots after its pass 1
+    int l2_hints;  // pass 2 streams flow/residual with an L2 evict-first policy (keeps the masks resident)
     // forward outputs
     float* loss;
     float* vis_gt; float* vis_pred; float* vis_agg; float* vis_res; float* vis_aff;
@@ -149,6 +150,24 @@ template <> struct Pack<4> {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     }
 };
+// streaming loads that should not displace L2-resident data (evict-first policy, no L1 allocation)
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void ld_evict_first(float (&v)[4], const float* p, unsigned long long pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void ld_evict_first(float (&v)[2], const float* p, unsigned long long pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
+                 : "=f"(v[0]), "=f"(v[1]) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void ld_evict_first(float (&v)[1], const float* p, unsigned long long pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v[0]) : "l"(p), "l"(pol));
+}
+
 template <> struct Pack<2> {   // 64-bit accesses: used for K > 4 where four pixels per thread would not fit in registers
     static __device__ __forceinline__ void ld(float (&v)[2], const float* p) {
         const float2 t = __ldg(reinterpret_cast<const float2*>(p));

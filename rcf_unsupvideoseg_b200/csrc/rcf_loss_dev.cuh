@@ -34,12 +34,22 @@ __device__ __forceinline__ void loss_tile(const RcfK& a, int fd, int chunk, floa
             float m[K][PX], r[2][K][PX], f[2][PX];
 #pragma unroll
             for (int k = 0; k < K; ++k) Pack<PX>::ld(m[k], mask + (long long)k * P + p);
-            Pack<PX>::ld(f[0], flow + p);
-            Pack<PX>::ld(f[1], flow + P + p);
+            if (a.l2_hints) {
+                const unsigned long long pol = l2_policy_evict_first();
+                ld_evict_first(f[0], flow + p, pol);
+                ld_evict_first(f[1], flow + P + p, pol);
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
-                for (int k = 0; k < K; ++k) Pack<PX>::ld(r[c][k], resid + (long long)(c * K + k) * P + p);
+                    for (int k = 0; k < K; ++k) ld_evict_first(r[c][k], resid + (long long)(c * K + k) * P + p, pol);
+            } else {
+                Pack<PX>::ld(f[0], flow + p);
+                Pack<PX>::ld(f[1], flow + P + p);
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) Pack<PX>::ld(r[c][k], resid + (long long)(c * K + k) * P + p);
+            }
             float y[PX], x[PX];
             if constexpr (D > 0) px_coords<PX>(p, a, y, x);
 

@@ -10,7 +10,7 @@ __device__ __forceinline__ void moments_tile(const RcfK& a, int fd, int chunk, f
     constexpr int NS = rcf_ns(D);
     constexpr int ITER = RCF_CHUNK_MOM / (RCF_BLOCK * PX);
     constexpr int DD = D > 0 ? D : 1;
-    constexpr int KG = (D == 0) ? K : (D == 2 ? (K < 4 ? K : 4) : 1);
+    constexpr int KG = (D == 5) ? 1 : (K < 4 ? K : 4);
 
     const int dir = fd / a.B;
     const int b = fd - dir * a.B;
@@ -25,6 +25,29 @@ __device__ __forceinline__ void moments_tile(const RcfK& a, int fd, int chunk, f
         float acc[KG * NS];
 #pragma unroll
         for (int i = 0; i < KG * NS; ++i) acc[i] = 0.0f;
+        if constexpr (D == 0) {
+            // mask sums only: issue every load of the tile (ITER*K 128-bit loads per thread) before the first add,
+            // so the tile runs at full memory-level parallelism even at 2 CTAs/SM inside the fused forward kernel
+            float mm[ITER][KG][PX];
+#pragma unroll
+            for (int it = 0; it < ITER; ++it) {
+                const int p = p0 + (it * RCF_BLOCK + tid) * PX;
+#pragma unroll
+                for (int k = 0; k < KG; ++k) {
+                    if (p < P) Pack<PX>::ld(mm[it][k], mask + (long long)(k0 + k) * P + p);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) mm[it][k][j] = 0.0f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < ITER; ++it)
+#pragma unroll
+                for (int k = 0; k < KG; ++k)
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) acc[k] += mm[it][k][j];
+        } else {
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const int p = p0 + (it * RCF_BLOCK + tid) * PX;
@@ -74,6 +97,7 @@ __device__ __forceinline__ void moments_tile(const RcfK& a, int fd, int chunk, f
                 }
             }
         }
+        }   // D > 0
         // one vector reduction per group; rows past K (padding of the last group) are never stored
         if (k0 + KG <= K) {
             warp_reduce_store<KG * NS>(acc, lane, &red[warp][k0 * NS]);

@@ -403,5 +403,5 @@ def test_fused_forward_is_bit_identical_to_three_kernel_path(rcf):
                 assert torch.equal(a_, b_)
             outs.append(res[0][0])
     finally:
-        lib.rcf_debug_set_option(1, 1)
+        lib.rcf_debug_set_option(1, 0)
     assert lib.rcf_debug_set_option(99, 0) == -5

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--time", action="store_true", help="print CUDA-event time per step and per kernel")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
+    ap.add_argument("--opt", type=str, default="", help="comma list of option=value for rcf_debug_set_option, e.g. 1=0,2=6")
     a = ap.parse_args()
     dev = torch.device("cuda")
     g = torch.Generator(device=dev).manual_seed(0)
@@ -36,6 +37,9 @@ def main():
     spec = pkg.LossSpec(K=K, H=H, W=W, D=a.D, Cf=a.Cf, clamp_t=20.0, robust=a.robust)
     gl = torch.ones(2, device=dev)
     lib = pkg.load_library()
+    for kv in filter(None, a.opt.split(",")):
+        o, v = kv.split("=")
+        assert lib.rcf_debug_set_option(int(o), int(v)) == 0
     Cf = a.Cf
     if Cf > 0:
         feat = torch.randn(2, B, Cf, H, W, device=dev, generator=g).requires_grad_(True)
