@@ -178,7 +178,7 @@ RCF_API int rcf_debug_time_kernel(int which, void* start_event, void* stop_event
  * but measured ~6 % slower on B200 at 2 CTAs/SM: kept as an experiment); 0 = three separate launches. */
 #define RCF_OPT_FUSED_FORWARD 1
 #define RCF_OPT_FUSED_LAG 2      /* slots between pass 1 and pass 2 of a frame-direction (1..64) */
-#define RCF_OPT_L2_HINTS 3       /* evict-first streaming loads in pass 2 of the fused forward */
+#define RCF_OPT_L2_HINTS 3       /* evict-first streaming loads of flow/residual in pass 2 (default 1) */
 RCF_API int rcf_debug_set_option(int option, int value);
 
 #ifdef __cplusplus

@@ -68,7 +68,7 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.thbar = reinterpret_cast<double*>(w + L.w_thbar);
     a.sync = reinterpret_cast<int*>(w + L.w_sync);
     a.lag = g_fused_lag;
-    a.l2_hints = 0;
+    a.l2_hints = g_l2_hints;   // pass 2 streams flow/residual evict-first so the masks of pass 1 survive in L2
     a.nchunk1 = L.nchunk1; a.nchunk2 = L.nchunk2; a.nchunkb = L.nchunkb; a.nchunkp = L.nchunkp;
 }
 
@@ -173,7 +173,6 @@ extern "C" int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss
     if (desc->theta_mode == 0 && vec && g_fused_forward) {
         // one launch: pass 1, per-segment solve and pass 2, ordered for L2 reuse of the masks (rcf_forward_fused.cu)
         RCF_CUDA(cudaMemsetAsync(a.sync, 0, (size_t)(1 + 2 * L.nfd) * sizeof(int), s));
-        a.l2_hints = g_l2_hints;
         { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_forward_fused(a, s)); }
     } else {
         { ScopedTime t(RCF_TIME_MOMENTS, s); RCF_CUDA(rcf_launch_moments(a, vec, s)); }

@@ -19,7 +19,10 @@ template <int K, int D, int PX, bool VIS>
 __global__ void __launch_bounds__(RCF_BLOCK, (D <= 2) ? 2 : 1) k_loss(const RcfK a) {
     __shared__ float cf[K * rcf_cf(D)];
     __shared__ float red[RCF_WARPS][rcf_gm(K, D)];
-    loss_tile<K, D, PX, VIS>(a, blockIdx.y, blockIdx.x, cf, red);
+    // Traverse in the REVERSE order of pass 1 (k_moments runs fd 0..n-1, chunks ascending): the masks read last by
+    // pass 1 are still in the 126 MB L2 and are consumed first.  k_bwd then runs in ascending order again, i.e. the
+    // reverse of this kernel, for the same reason.
+    loss_tile<K, D, PX, VIS>(a, a.nfd - 1 - (int)blockIdx.y, a.nchunk2 - 1 - (int)blockIdx.x, cf, red);
 }
 
 template <int K, int D>
