@@ -11,6 +11,7 @@ namespace {
 int g_fused_forward = 0;   // rcf_debug_set_option(RCF_OPT_FUSED_FORWARD, 0/1); off: measured slower, see DESIGN.md
 int g_fused_lag = 4;       // RCF_OPT_FUSED_LAG
 int g_l2_hints = 1;        // RCF_OPT_L2_HINTS
+int g_single_pass = 1;     // RCF_OPT_SINGLE_PASS
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
@@ -119,6 +120,7 @@ extern "C" int rcf_debug_set_option(int option, int value) {
     if (option == RCF_OPT_FUSED_FORWARD) { g_fused_forward = value ? 1 : 0; return RCF_OK; }
     if (option == RCF_OPT_FUSED_LAG && value >= 1 && value <= 64) { g_fused_lag = value; return RCF_OK; }
     if (option == RCF_OPT_L2_HINTS) { g_l2_hints = value ? 1 : 0; return RCF_OK; }
+    if (option == RCF_OPT_SINGLE_PASS) { g_single_pass = value ? 1 : 0; return RCF_OK; }
     return RCF_ERR_MODE;
 }
 
@@ -170,7 +172,12 @@ extern "C" int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss
             if (p && (!aligned16(p) || desc->vis_bstride % 4 || desc->vis_dstride % 4)) vec = false;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (desc->theta_mode == 0 && vec && g_fused_forward) {
+    a.single_pass = (desc->theta_mode == 0 && desc->D == 0 && g_single_pass) ? 1 : 0;
+    if (a.single_pass) {
+        // theta supplied, no affine fit: nothing in pass 2 depends on pass 1, so the forward reads every input once
+        RCF_CUDA(rcf_launch_segment_fwd(a, s));
+        { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_loss(a, vec, s)); }
+    } else if (desc->theta_mode == 0 && vec && g_fused_forward) {
         // one launch: pass 1, per-segment solve and pass 2, ordered for L2 reuse of the masks (rcf_forward_fused.cu)
         RCF_CUDA(cudaMemsetAsync(a.sync, 0, (size_t)(1 + 2 * L.nfd) * sizeof(int), s));
         { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_forward_fused(a, s)); }

@@ -25,8 +25,10 @@
 //   [3+D .. 3+3D) sum m*F_c*u_d (c*D+d), [3+3D ..) sum m*u_d*u_e packed d<=e
 RCF_HD constexpr int rcf_ns(int D) { return D == 0 ? 1 : 3 + 3 * D + D * (D + 1) / 2; }
 // pass-2 gradient moments per fd: [0] sum phi, [1 + c*K + k] sum w_c m_k,
-//   [1 + 2K + (k*2+c)*D + d] sum w_c m_k (u_d - mu_kd)
-RCF_HD constexpr int rcf_gm(int K, int D) { return 1 + 2 * K + 2 * K * D; }
+//   D > 0: [1 + 2K + (k*2+c)*D + d] sum w_c m_k (u_d - mu_kd)
+//   D = 0: [1 + 2K + k] sum m_k  (the mask sums S_k ride along for free: with theta supplied and no affine fit
+//          nothing in pass 2 depends on S_k, so the forward is a single pass and S_k is only needed by the backward)
+RCF_HD constexpr int rcf_gm(int K, int D) { return D == 0 ? 1 + 3 * K : 1 + 2 * K + 2 * K * D; }
 // forward coefficients per (fd,k) (fp32): theta[2], A[2][D], mu_u[D]
 RCF_HD constexpr int rcf_cf(int D) { return 2 + 3 * D; }
 // backward coefficients per (fd,k) (fp32), all pre-divided by S_k:
@@ -122,6 +124,7 @@ struct RcfK {
     int* sync;     // fused forward: [0] ticket, [1..nfd] pass-1 arrival counters, [1+nfd..] ready flags
     int lag;       // fused forward: pass 2 of frame-direction t is scheduled LAG slots after its pass 1
     int l2_hints;  // pass 2 streams flow/residual with an L2 evict-first policy (keeps the masks resident)
+    int single_pass;  // theta supplied and D == 0: no pass 1; S_k comes out of pass 2 (k_finalize stores it)
     // forward outputs
     float* loss;
     float* vis_gt; float* vis_pred; float* vis_agg; float* vis_res; float* vis_aff;

@@ -123,6 +123,7 @@ __device__ __forceinline__ void loss_tile(const RcfK& a, int fd, int chunk, floa
                     const float wm0 = f[0][j] * m[k][j], wm1 = f[1][j] * m[k][j];
                     acc[1 + k] += wm0;
                     acc[1 + K + k] += wm1;
+                    if constexpr (D == 0) acc[1 + 2 * K + k] += m[k][j];      // S_k (see rcf_gm)
                     if constexpr (D > 0) {
                         float u[DD];
                         px_feats<D>(y[j], x[j], u);

@@ -22,7 +22,11 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_fwd(const RcfK a) {
     const int fd = blockIdx.x, K = a.K, Cf = a.Cf, tid = threadIdx.x;
     const int dir = fd / a.B, b = fd - dir * a.B;
 
-    reduce_partials(a.part1 + (size_t)fd * K * NS * a.nchunk1, K * NS, a.nchunk1, stat);
+    if (a.single_pass) {          // D == 0, theta supplied: S_k is produced by pass 2 (k_finalize overwrites segd[0])
+        if (tid < K * NS) stat[tid] = 1.0;
+    } else {
+        reduce_partials(a.part1 + (size_t)fd * K * NS * a.nchunk1, K * NS, a.nchunk1, stat);
+    }
     __syncthreads();
     double* sd = a.segd + (size_t)fd * K * SEGD;
     if (tid < K) seg_affine_fwd<D>(stat + tid * NS, sd + tid * SEGD);
@@ -78,10 +82,12 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_fwd(const RcfK a) {
 
 __global__ void __launch_bounds__(RCF_BLOCK) k_finalize(const RcfK a, int GM) {
     const int fd = blockIdx.x;
-    __shared__ double out[1 + 2 * RCF_MAX_K + 2 * RCF_MAX_K * 5];
+    __shared__ double out[1 + 3 * RCF_MAX_K + 2 * RCF_MAX_K * 5];
     reduce_partials(a.part2 + (size_t)fd * GM * a.nchunk2, GM, a.nchunk2, out);
     __syncthreads();
     for (int i = threadIdx.x; i < GM; i += blockDim.x) a.gm[(size_t)fd * GM + i] = out[i];
+    if (a.single_pass && threadIdx.x < a.K)      // D == 0: segd record is {S, -, -}
+        a.segd[((size_t)fd * a.K + threadIdx.x) * rcf_segd(0)] = out[1 + 2 * a.K + threadIdx.x];
 }
 
 __global__ void k_loss_sum(const RcfK a, int GM) {
