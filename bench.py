@@ -190,7 +190,6 @@ def run_ours(args):
     import torch.distributed as dist
 
     import rcf_unsupvideoseg_b200 as pkg
-    from rcf_unsupvideoseg_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

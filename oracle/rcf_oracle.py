@@ -22,7 +22,7 @@ flows).  The reference repo ships no tests or golden vectors of its own for this
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
 import numpy as np

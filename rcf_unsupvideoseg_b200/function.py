@@ -59,10 +59,6 @@ def _as_dir_view(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else t.data_ptr()
-
-
 _SIZE_CACHE = {}
 
 
