@@ -322,7 +322,7 @@ def run_ours(args):
     torch.manual_seed(1)
     head = pkg.FlowAggregationHeadWithResidual(args=None, create_flownet=True, **HEAD_KW).to(dev)
     head.return_flows = False
-    head._inv_n_override = inv_n
+    head.loss_inv_n = inv_n
     pin = [t.pin_memory() for t in (masks_h, fw_h, bw_h, rfw_h, rbw_h)]
     out_pin = [torch.empty(2, dtype=torch.float32).pin_memory(), torch.empty_like(masks_h).pin_memory(),
                torch.empty_like(rfw_h).pin_memory(), torch.empty_like(rbw_h).pin_memory()]

@@ -88,6 +88,10 @@ typedef struct RcfDesc {
        flow_feat_before_agg (reference :89-92), set the negative slope here (0.1) and the library applies the
        activation on load and its derivative to dfeat; 0 or 1 means feat is used as it is. */
     float feat_lrelu_slope;
+    /* 0: feat / dfeat are [B,Cf,H,W] planes (NCHW);  1: channels-last, element (b,f,p) at b*bstride + p*Cf + f (what
+       cuDNN's tensor-core convolutions produce natively; avoids its NCHW<->NHWC transposes).  Requires Cf % 4 == 0,
+       Cf <= 128 and 256 % (Cf/4) == 0. */
+    int32_t feat_nhwc;
 } RcfDesc;
 
 typedef struct RcfInputs {

@@ -31,7 +31,7 @@ class RcfDesc(C.Structure):
         ("mask_bstride", _i64x2), ("flow_bstride", _i64x2), ("resid_bstride", _i64x2), ("feat_bstride", _i64x2),
         ("dmask_bstride", _i64x2), ("dresid_bstride", _i64x2), ("dfeat_bstride", _i64x2),
         ("vis_bstride", C.c_int64), ("vis_dstride", C.c_int64), ("vis_scale", C.c_float * 2),
-        ("feat_lrelu_slope", C.c_float),
+        ("feat_lrelu_slope", C.c_float), ("feat_nhwc", C.c_int32),
     ]
 
 

@@ -29,6 +29,7 @@ int validate_desc(const RcfDesc* d) {
     if (d->theta_mode == 0 && d->Cf != 0) return RCF_ERR_MODE;
     if (d->unbounded_residual && d->D != 0) return RCF_ERR_MODE;   // reference :279-286 only in free_residual
     if (!(d->pred_div != 0.0f)) return RCF_ERR_MODE;
+    if (d->feat_nhwc && (d->theta_mode != 1 || d->Cf % 4 || d->Cf > 128 || 256 % (d->Cf / 4))) return RCF_ERR_MODE;
     return RCF_OK;
 }
 
@@ -46,6 +47,7 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.cy = 0.5f * (float)(d.H - 1); a.cx = 0.5f * (float)(d.W - 1);
     a.sy = 1.0f / fmaxf(a.cy, 1.0f); a.sx = 1.0f / fmaxf(a.cx, 1.0f);
     a.feat_slope = (d.feat_lrelu_slope > 0.0f) ? d.feat_lrelu_slope : 1.0f;
+    a.feat_nhwc = d.feat_nhwc ? 1 : 0;
     for (int i = 0; i < 2; ++i) {
         a.mask[i] = in.mask[i]; a.flow[i] = in.flow[i]; a.resid[i] = in.resid[i];
         a.feat[i] = in.feat[i]; a.theta[i] = in.theta[i];

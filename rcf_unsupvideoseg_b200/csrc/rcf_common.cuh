@@ -38,7 +38,8 @@ RCF_HD constexpr int rcf_cb(int D) { return 3 + 3 * D + D * (D + 1) / 2; }
 RCF_HD constexpr int rcf_segd(int D) { return 3 + 5 * D + 2 * D * D; }
 RCF_HD constexpr int rcf_sym_idx(int D, int d, int e) { return d * D - d * (d - 1) / 2 + (e - d); }
 
-RCF_HD int rcf_pool_chunk(int K) { return K <= 4 ? 2048 : 1024; }
+#define RCF_POOL_CHUNK_NHWC 512
+RCF_HD int rcf_pool_chunk(int K, int nhwc) { return nhwc ? RCF_POOL_CHUNK_NHWC : (K <= 4 ? 2048 : 1024); }
 
 // ---- memory plan ------------------------------------------------------------------------------
 struct RcfLayout {
@@ -64,7 +65,7 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.nchunk1 = (L.P + RCF_CHUNK_MOM - 1) / RCF_CHUNK_MOM;
     L.nchunk2 = (L.P + RCF_CHUNK_LOSS - 1) / RCF_CHUNK_LOSS;
     L.nchunkb = (L.P + RCF_CHUNK_BWD - 1) / RCF_CHUNK_BWD;
-    const int pc = rcf_pool_chunk(d.K);
+    const int pc = rcf_pool_chunk(d.K, d.feat_nhwc);
     L.nchunkp = (L.P + pc - 1) / pc;
     const size_t nseg = (size_t)L.nfd * d.K;
     size_t o = 0;
@@ -99,6 +100,7 @@ struct RcfK {
     float inv_n;
     float cy, cx, sy, sx;  // coordinate centring / scaling (u = ((row-cy)*sy, (col-cx)*sx))
     float feat_slope;      // LeakyReLU slope applied to feat on load (1 = none)
+    int feat_nhwc;         // feat / dfeat are channels-last
     const float* mask[2];
     const float* flow[2];
     const float* resid[2];

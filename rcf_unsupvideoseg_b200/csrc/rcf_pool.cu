@@ -151,6 +151,166 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
     }
 }
 
+// ---- channels-last feature map (what cuDNN's tensor-core convolutions produce without layout transposes) ---------
+// Element (f, p) of a frame sits at p*Cf + f.  A thread owns 4 consecutive channels (one float4) and walks pixels;
+// 256/(Cf/4) pixel groups work side by side, so a warp reads 2 pixels = 512 contiguous bytes (Cf = 64).
+// Forward: per-thread accumulators acc[4 channels][K], no shuffles; the groups are combined through shared memory.
+template <int K>
+__global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
+    constexpr int CHUNK = RCF_POOL_CHUNK_NHWC;
+    extern __shared__ float sm[];
+    float* msT = sm;                         // [CHUNK][K]   mask tile, pixel-major
+    float* redn = sm + CHUNK * K;            // [groups][Cf*K]
+    const int fd = blockIdx.y;
+    const int dir = fd / a.B;
+    const int b = fd - dir * a.B;
+    const int chunk = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int P = a.P, Cf = a.Cf;
+    const int nf4 = Cf >> 2, groups = RCF_BLOCK / nf4;
+    const int c4 = tid % nf4, grp = tid / nf4;
+    const int p0 = chunk * CHUNK;
+    const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
+    const float* __restrict__ feat = a.feat[dir] + (long long)b * a.feat_bs[dir];
+    const float slope = a.feat_slope;
+
+    for (int i = tid; i < CHUNK * K; i += RCF_BLOCK) {
+        const int k = i / CHUNK, p = i - k * CHUNK;                  // coalesced along pixels per plane
+        msT[p * K + k] = (p0 + p < P) ? __ldg(mask + (long long)k * P + p0 + p) : 0.0f;
+    }
+    __syncthreads();
+
+    float acc[4][K];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[j][k] = 0.0f;
+    const int pend = min(CHUNK, P - p0);
+#pragma unroll 4
+    for (int p = grp; p < pend; p += groups) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(feat + (long long)(p0 + p) * Cf) + c4);
+        float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gv[j] = gv[j] >= 0.0f ? gv[j] : slope * gv[j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float m = msT[p * K + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][k] = fmaf(gv[j], m, acc[j][k]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < K; ++k) redn[grp * Cf * K + (c4 * 4 + j) * K + k] = acc[j][k];
+    __syncthreads();
+    for (int o = tid; o < Cf * K; o += RCF_BLOCK) {
+        float v = 0.0f;
+        for (int g2 = 0; g2 < groups; ++g2) v += redn[g2 * Cf * K + o];      // fixed order
+        a.partp[((size_t)fd * Cf * K + o) * a.nchunkp + chunk] = v;
+    }
+}
+
+// Backward, channels-last: dG[p][f] = dact * sum_k c[f][k] M[k][p] (float4 store) and dM[k][p] += sum_f c[f][k] G[p][f],
+// the latter reduced over the Cf/4 threads of a pixel with shuffles and accumulated in a shared tile that is written
+// back to the NCHW gradient planes with coalesced stores.
+template <int K>
+__global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
+    constexpr int TP = 256;                  // pixels per CTA
+    extern __shared__ float sm[];
+    float* msT = sm;                         // [TP][K]
+    float* dms = sm + TP * K;                // [TP][K]
+    const int fd = blockIdx.y;
+    const int dir = fd / a.B;
+    const int b = fd - dir * a.B;
+    const int tid = threadIdx.x;
+    const int P = a.P, Cf = a.Cf;
+    const int nf4 = Cf >> 2, groups = RCF_BLOCK / nf4;
+    const int c4 = tid % nf4, grp = tid / nf4;
+    const int p0 = blockIdx.x * TP;
+    const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
+    const float* __restrict__ feat = a.feat[dir] + (long long)b * a.feat_bs[dir];
+    float* dmask = a.dmask[dir] ? a.dmask[dir] + (long long)b * a.dmask_bs[dir] : nullptr;
+    float* __restrict__ dfeat = a.dfeat[dir] ? a.dfeat[dir] + (long long)b * a.dfeat_bs[dir] : nullptr;
+    const float slope = a.feat_slope;
+
+    for (int i = tid; i < TP * K; i += RCF_BLOCK) {
+        const int k = i / TP, p = i - k * TP;
+        const bool in = p0 + p < P;
+        msT[p * K + k] = in ? __ldg(mask + (long long)k * P + p0 + p) : 0.0f;
+        dms[p * K + k] = (in && dmask) ? dmask[(long long)k * P + p0 + p] : 0.0f;    // accumulate onto k_bwd's result
+    }
+    float c[4][K];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < K; ++k) c[j][k] = a.poolbar[(size_t)fd * Cf * K + (c4 * 4 + j) * K + k];
+    __syncthreads();
+
+    const int pend = min(TP, P - p0);
+    const int iters = (TP + groups - 1) / groups;      // uniform trip count: shuffles below stay convergent
+    for (int it = 0; it < iters; ++it) {
+        const int p = grp + it * groups;
+        const bool live = p < pend;
+        float part[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) part[k] = 0.0f;
+        if (live) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(feat + (long long)(p0 + p) * Cf) + c4);
+            float gv[4] = {g.x, g.y, g.z, g.w}, dact[4], dg[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                dact[j] = gv[j] >= 0.0f ? 1.0f : slope;
+                gv[j] *= dact[j];
+                dg[j] = 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float m = msT[p * K + k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    part[k] = fmaf(c[j][k], gv[j], part[k]);
+                    dg[j] = fmaf(c[j][k], m, dg[j]);
+                }
+            }
+            if (dfeat)
+                reinterpret_cast<float4*>(dfeat + (long long)(p0 + p) * Cf)[c4] =
+                    make_float4(dg[0] * dact[0], dg[1] * dact[1], dg[2] * dact[2], dg[3] * dact[3]);
+        }
+        // reduce over the nf4 (<= 32, power of two) consecutive lanes that share this pixel
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            for (int o = nf4 >> 1; o > 0; o >>= 1) part[k] += __shfl_xor_sync(0xffffffffu, part[k], o);
+        if (live && c4 == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) dms[p * K + k] += part[k];       // one group per pixel: no conflicts
+        }
+    }
+    __syncthreads();
+    if (dmask) {
+        for (int i = tid; i < TP * K; i += RCF_BLOCK) {
+            const int k = i / TP, p = i - k * TP;
+            if (p0 + p < P) dmask[(long long)k * P + p0 + p] = dms[p * K + k];
+        }
+    }
+}
+
+template <int K>
+static cudaError_t launch_pool_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
+    const int groups = RCF_BLOCK / (a.Cf / 4);
+    const size_t smem = ((size_t)RCF_POOL_CHUNK_NHWC * K + (size_t)groups * a.Cf * K) * sizeof(float);
+    dim3 grid(a.nchunkp, a.nfd), block(RCF_BLOCK);
+    k_pool_nhwc<K><<<grid, block, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int K>
+static cudaError_t launch_pool_bwd_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
+    dim3 grid((a.P + 255) / 256, a.nfd), block(RCF_BLOCK);
+    k_pool_bwd_nhwc<K><<<grid, block, (size_t)2 * 256 * K * sizeof(float), s>>>(a);
+    return cudaGetLastError();
+}
+
 template <int K>
 static cudaError_t launch_pool_k(const RcfK& a, bool vec, cudaStream_t s) {
     constexpr int CHUNK = K <= 4 ? 2048 : 1024;
@@ -190,5 +350,11 @@ static cudaError_t launch_pool_bwd_k(const RcfK& a, bool vec, cudaStream_t s) {
     }                                                      \
     return cudaErrorInvalidValue;
 
-cudaError_t rcf_launch_pool(const RcfK& a, bool vec, cudaStream_t s) { RCF_K_SWITCH(launch_pool_k) }
-cudaError_t rcf_launch_pool_bwd(const RcfK& a, bool vec, cudaStream_t s) { RCF_K_SWITCH(launch_pool_bwd_k) }
+cudaError_t rcf_launch_pool(const RcfK& a, bool vec, cudaStream_t s) {
+    if (a.feat_nhwc) { RCF_K_SWITCH(launch_pool_nhwc_k) }
+    RCF_K_SWITCH(launch_pool_k)
+}
+cudaError_t rcf_launch_pool_bwd(const RcfK& a, bool vec, cudaStream_t s) {
+    if (a.feat_nhwc) { RCF_K_SWITCH(launch_pool_bwd_nhwc_k) }
+    RCF_K_SWITCH(launch_pool_bwd_k)
+}

@@ -59,11 +59,25 @@ def _as_dir_view(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def _feat_layout(feat: torch.Tensor, Cf: int, H: int, W: int):
+    """feat [ndir,B,Cf,H,W] fp32: returns (tensor, nhwc) with either dense [Cf,H,W] planes or dense channels-last
+    frames (what cuDNN returns for channels_last inputs); anything else is made plane-contiguous (one copy)."""
+    if feat.dtype != torch.float32:
+        feat = feat.float()
+    st = feat.stride()
+    if Cf % 4 == 0 and Cf <= 128 and 256 % (Cf // 4) == 0 and st[2] == 1 and st[4] == Cf and st[3] == W * Cf \
+            and st[1] % 4 == 0 and st[0] % 4 == 0 and feat.data_ptr() % 16 == 0:
+        return feat, True
+    if _inner_dense(feat, 3):
+        return feat, False
+    return feat.contiguous(), False
+
+
 _SIZE_CACHE = {}
 
 
 def _sizes(lib, desc, spec, B, ndir):
-    key = (spec.K, spec.H, spec.W, spec.D, spec.Cf, B, ndir)
+    key = (spec.K, spec.H, spec.W, spec.D, spec.Cf, B, ndir, int(desc.feat_nhwc))
     hit = _SIZE_CACHE.get(key)
     if hit is None:
         ctx_bytes, ws_bytes = C.c_size_t(), C.c_size_t()
@@ -118,11 +132,11 @@ class RcfMotionLossFn(torch.autograd.Function):
         masks_v = masks if (masks.dtype == torch.float32 and _inner_dense(masks, 3)) else masks.float().contiguous()
         flows_v = [_as_dir_view(f) for f in flows]
         resids_v = [_as_dir_view(r) for r in resids]
-        feat_v = None
+        feat_v, nhwc = None, False
         if spec.Cf > 0:
             assert feat is not None and tuple(feat.shape) == (ndir, B, spec.Cf, H, W), \
                 f"feature map shape {None if feat is None else tuple(feat.shape)}"
-            feat_v = feat if (feat.dtype == torch.float32 and _inner_dense(feat, 3)) else feat.float().contiguous()
+            feat_v, nhwc = _feat_layout(feat, spec.Cf, H, W)
         thetas_v = [t.float().contiguous() if t is not None else None for t in thetas]
         for f in flows_v:
             assert f.shape == (B, 2, H, W), f"flow shape {tuple(f.shape)}"
@@ -137,6 +151,7 @@ class RcfMotionLossFn(torch.autograd.Function):
             w1c = b1c = w2c = b2c = None
 
         desc = _make_desc(spec, B, ndir)
+        desc.feat_nhwc = int(nhwc)
         inp = _lib.RcfInputs()
         for i in range(ndir):
             inp.mask[i] = masks_v.data_ptr() + i * masks_v.stride(1) * 4
@@ -172,7 +187,7 @@ class RcfMotionLossFn(torch.autograd.Function):
             _lib.check(lib.rcf_forward(C.byref(desc), C.byref(inp), loss.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
                                        C.byref(vis_struct) if vis_struct is not None else None, stream), "rcf_forward")
 
-        ctx.spec, ctx.ndir, ctx.B = spec, ndir, B
+        ctx.spec, ctx.ndir, ctx.B, ctx.nhwc = spec, ndir, B, nhwc
         ctx.masks_shape = tuple(masks.shape)
         ctx.save_for_backward(masks_v, ctx_buf, *flows_v, *resids_v,
                               *([feat_v] if feat_v is not None else []), *[t for t in thetas_v if t is not None],
@@ -201,6 +216,7 @@ class RcfMotionLossFn(torch.autograd.Function):
         need_theta = [need[7 + 2 * ndir + i] for i in range(ndir)]
 
         desc = _make_desc(spec, B, ndir)
+        desc.feat_nhwc = int(ctx.nhwc)
         inp = _lib.RcfInputs()
         grads = _lib.RcfGrads()
         d_feat = None
@@ -209,7 +225,11 @@ class RcfMotionLossFn(torch.autograd.Function):
             w1c, b1c, w2c, b2c = rest[1:5]
             inp.w1, inp.b1, inp.w2, inp.b2 = (t.data_ptr() for t in (w1c, b1c, w2c, b2c))
             if need_feat:
-                d_feat = torch.empty(ndir, B, Cf, H, W, dtype=torch.float32, device=dev)
+                if ctx.nhwc:    # gradient in the layout of the feature map (cuDNN's backward then needs no transposes either)
+                    d_feat = torch.empty((ndir * B, Cf, H, W), dtype=torch.float32, device=dev,
+                                         memory_format=torch.channels_last).view(ndir, B, Cf, H, W)
+                else:
+                    d_feat = torch.empty(ndir, B, Cf, H, W, dtype=torch.float32, device=dev)
         else:
             thetas_v = rest[0:ndir]
 

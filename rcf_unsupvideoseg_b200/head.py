@@ -130,8 +130,14 @@ class FlowAggregationHeadWithResidual(nn.Module):
             f"Only one of {self.free_residual}, {self.free_residual_with_affine}, {self.object_free_residual}, " \
             f"{self.free_scale}, {self.affine_residual}"
         self.allow_residual_resize = allow_residual_resize
-        # benchmark switch: skip the visualisation tensors (the reference always builds them, :370-395)
+        # Extensions (not constructor arguments, so YAML configs of the reference keep working):
+        #   return_flows=False skips the 4-5 visualisation tensors (the reference always builds them, :370-395);
+        #   loss_inv_n > 0 replaces the mean's 1/(B*2*H*W) -- set it to 1/(B_global*2*H*W) when the batch is sharded
+        #   by hand and the per-rank losses are meant to be SUMMED (distributed.global_inv_n); under DDP leave it 0.
+        #   channels_last_features=False keeps the conv branch in NCHW (default: channels-last, see _features_preact).
         self.return_flows = True
+        self.loss_inv_n = 0.0
+        self.channels_last_features = True
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -164,6 +170,11 @@ class FlowAggregationHeadWithResidual(nn.Module):
         inside the pooling kernels (and its derivative inside the pooling backward), which saves one full read+write
         of the [B,Cf,H,W] map in forward and one read + one read+write in backward."""
         seq = self.flow_feat_before_agg
+        Cf = self.num_flow_feat_channels
+        if self.channels_last_features and Cf % 4 == 0 and Cf <= 128 and 256 % (Cf // 4) == 0:
+            # cuDNN's tensor-core convolutions are channels-last natively: feeding them channels-last tensors removes
+            # their NCHW<->NHWC transposes (27 of ~70 launches per step at 96x96); the pooling kernels read that layout
+            flow = flow.contiguous(memory_format=torch.channels_last)
         return seq[2](seq[1](seq[0](flow)))
 
     def _spec(self, K, H, W, *, want_vis, vis_norm, inv_n=0.0, clamp_fused=True) -> LossSpec:
@@ -258,7 +269,7 @@ class FlowAggregationHeadWithResidual(nn.Module):
         gt_fw_flow = gt_fw_flows[:, 0, ...]
         gt_bw_flow = gt_bw_flows[:, 0, ...]
         loss, vis = self._run(masks, [gt_fw_flow, gt_bw_flow], [all_pred_residual_fw, all_pred_residual_bw],
-                              want_vis=self.return_flows, vis_norm=True, inv_n=getattr(self, "_inv_n_override", 0.0))
+                              want_vis=self.return_flows, vis_norm=True, inv_n=float(self.loss_inv_n))
         flow_loss['seg_fw'] = loss[0]
         flow_loss['seg_bw'] = loss[1]
         if self.return_flows:

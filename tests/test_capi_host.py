@@ -51,7 +51,7 @@ int main(void) {
   F(RcfDesc,robust); F(RcfDesc,unbounded_residual); F(RcfDesc,eps); F(RcfDesc,q); F(RcfDesc,resid_scale); F(RcfDesc,pred_div);
   F(RcfDesc,clamp_t); F(RcfDesc,inv_n); F(RcfDesc,mask_bstride); F(RcfDesc,flow_bstride); F(RcfDesc,resid_bstride);
   F(RcfDesc,feat_bstride); F(RcfDesc,dmask_bstride); F(RcfDesc,dresid_bstride); F(RcfDesc,dfeat_bstride);
-  F(RcfDesc,vis_bstride); F(RcfDesc,vis_dstride); F(RcfDesc,vis_scale); F(RcfDesc,feat_lrelu_slope);
+  F(RcfDesc,vis_bstride); F(RcfDesc,vis_dstride); F(RcfDesc,vis_scale); F(RcfDesc,feat_lrelu_slope); F(RcfDesc,feat_nhwc);
   F(RcfInputs,mask); F(RcfInputs,flow); F(RcfInputs,resid); F(RcfInputs,feat); F(RcfInputs,theta); F(RcfInputs,w1); F(RcfInputs,b1); F(RcfInputs,w2); F(RcfInputs,b2);
   F(RcfVisOut,gt); F(RcfVisOut,pred); F(RcfVisOut,agg); F(RcfVisOut,res); F(RcfVisOut,aff);
   F(RcfGrads,dmask); F(RcfGrads,dresid); F(RcfGrads,dfeat); F(RcfGrads,dtheta); F(RcfGrads,dw1); F(RcfGrads,db1); F(RcfGrads,dw2); F(RcfGrads,db2);

@@ -405,3 +405,21 @@ def test_fused_forward_is_bit_identical_to_three_kernel_path(rcf):
     finally:
         lib.rcf_debug_set_option(1, 0)
     assert lib.rcf_debug_set_option(99, 0) == -5
+
+
+@pytest.mark.parametrize("name", ["free_l1", "affine_robust", "free_k8_k1conv"])
+def test_channels_last_feature_path_matches_nchw(rcf, name):
+    """The conv branch runs channels-last by default (k_pool_nhwc / k_pool_bwd_nhwc); planes (NCHW) must agree."""
+    g = Golden(name)
+    res = []
+    for cl in (True, False):
+        head = build_head(rcf, g)
+        head.channels_last_features = cl
+        flows, loss, grads = run_head(head, g.inputs, g.gbar)
+        res.append((loss["seg"].detach(), grads["d_masks"], grads["d_resid_fw"],
+                    [p.grad.clone() for p in head.parameters()]))
+    assert abs(float(res[0][0]) - float(res[1][0])) <= 1e-6 * abs(float(res[1][0]))
+    assert rel_l2(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) < 2e-5
+    assert rel_l2(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) < 2e-5
+    for a_, b_ in zip(res[0][3], res[1][3]):
+        assert rel_l2(a_.cpu().numpy(), b_.cpu().numpy()) < 2e-4
