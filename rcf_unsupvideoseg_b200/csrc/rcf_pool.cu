@@ -186,9 +186,11 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[j][k] = 0.0f;
     const int pend = min(CHUNK, P - p0);
-#pragma unroll 4
+    const float4* __restrict__ gp = reinterpret_cast<const float4*>(feat + (long long)p0 * Cf) + c4;
+    const int nf4s = nf4;    // float4 stride between consecutive pixels
+#pragma unroll 8
     for (int p = grp; p < pend; p += groups) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(feat + (long long)(p0 + p) * Cf) + c4);
+        const float4 g = __ldg(gp + (long long)p * nf4s);
         float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) gv[j] = gv[j] >= 0.0f ? gv[j] : slope * gv[j];
@@ -249,14 +251,28 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
 
     const int pend = min(TP, P - p0);
     const int iters = (TP + groups - 1) / groups;      // uniform trip count: shuffles below stay convergent
+    const float4* __restrict__ gp = reinterpret_cast<const float4*>(feat + (long long)p0 * Cf) + c4;
+    float4* __restrict__ dgp = dfeat ? reinterpret_cast<float4*>(dfeat + (long long)p0 * Cf) + c4 : nullptr;
+    // fast reduction when 16 lanes share a pixel and K == 4 (Cf = 64, the reference default): recursive halving
+    // (2 + 1 shuffles) then two butterflies, instead of 4 x 4 butterflies
+    const bool fast = (K == 4) && (nf4 == 16);
+    const int kown = ((c4 >> 3) & 1) * 2 + ((c4 >> 2) & 1);
+    // software pipeline: the loads of the next two pixels are in flight while the current one is processed
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 g0 = (grp < pend) ? __ldg(gp + (long long)grp * nf4) : zero4;
+    float4 g1 = (grp + groups < pend) ? __ldg(gp + (long long)(grp + groups) * nf4) : zero4;
+#pragma unroll 2
     for (int it = 0; it < iters; ++it) {
         const int p = grp + it * groups;
         const bool live = p < pend;
+        const int p2 = p + 2 * groups;
+        const float4 g2 = (p2 < pend) ? __ldg(gp + (long long)p2 * nf4) : zero4;
+        const float4 g = g0;
+        g0 = g1; g1 = g2;
         float part[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) part[k] = 0.0f;
         if (live) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(feat + (long long)(p0 + p) * Cf) + c4);
             float gv[4] = {g.x, g.y, g.z, g.w}, dact[4], dg[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -273,17 +289,28 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
                     dg[j] = fmaf(c[j][k], m, dg[j]);
                 }
             }
-            if (dfeat)
-                reinterpret_cast<float4*>(dfeat + (long long)(p0 + p) * Cf)[c4] =
-                    make_float4(dg[0] * dact[0], dg[1] * dact[1], dg[2] * dact[2], dg[3] * dact[3]);
+            if (dgp) dgp[(long long)p * nf4] = make_float4(dg[0] * dact[0], dg[1] * dact[1], dg[2] * dact[2], dg[3] * dact[3]);
         }
-        // reduce over the nf4 (<= 32, power of two) consecutive lanes that share this pixel
+        if (fast) {
+            if constexpr (K == 4) {
+                const bool up8 = (c4 & 8) != 0, up4 = (c4 & 4) != 0;
+                const float s0 = up8 ? part[0] : part[2], s1 = up8 ? part[1] : part[3];
+                const float k0 = up8 ? part[2] : part[0], k1 = up8 ? part[3] : part[1];
+                const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
+                const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
+                float v = (up4 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up4 ? a0 : a1, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (live && (c4 & 3) == 0) dms[p * K + kown] += v;        // 4 lanes per pixel, one per k
+            }
+        } else {
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-            for (int o = nf4 >> 1; o > 0; o >>= 1) part[k] += __shfl_xor_sync(0xffffffffu, part[k], o);
-        if (live && c4 == 0) {
+            for (int k = 0; k < K; ++k)
+                for (int o = nf4 >> 1; o > 0; o >>= 1) part[k] += __shfl_xor_sync(0xffffffffu, part[k], o);
+            if (live && c4 == 0) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) dms[p * K + k] += part[k];       // one group per pixel: no conflicts
+                for (int k = 0; k < K; ++k) dms[p * K + k] += part[k];   // one group per pixel: no conflicts
+            }
         }
     }
     __syncthreads();

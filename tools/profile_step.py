@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--D", type=int, default=0)
     ap.add_argument("--robust", action="store_true")
     ap.add_argument("--Cf", type=int, default=0, help=">0: Scope H, pool a random [B,Cf,H,W] feature map + segment MLP")
+    ap.add_argument("--nhwc", action="store_true", help="feature map in channels-last layout")
+    ap.add_argument("--slope", type=float, default=1.0, help="fused LeakyReLU slope of the feature map (1 = none)")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--time", action="store_true", help="print CUDA-event time per step and per kernel")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
@@ -34,7 +36,7 @@ def main():
     flows = [torch.randn(B, 2, H, W, device=dev, generator=g) * 8 for _ in range(2)]
     resids = [(torch.randn(B, 2 * K, H, W, device=dev, generator=g) * 5).requires_grad_(True) for _ in range(2)]
     thetas = [torch.randn(B, 2, K, device=dev, generator=g).requires_grad_(True) for _ in range(2)]
-    spec = pkg.LossSpec(K=K, H=H, W=W, D=a.D, Cf=a.Cf, clamp_t=20.0, robust=a.robust)
+    spec = pkg.LossSpec(K=K, H=H, W=W, D=a.D, Cf=a.Cf, clamp_t=20.0, robust=a.robust, feat_lrelu_slope=a.slope)
     gl = torch.ones(2, device=dev)
     lib = pkg.load_library()
     for kv in filter(None, a.opt.split(",")):
@@ -42,7 +44,10 @@ def main():
         assert lib.rcf_debug_set_option(int(o), int(v)) == 0
     Cf = a.Cf
     if Cf > 0:
-        feat = torch.randn(2, B, Cf, H, W, device=dev, generator=g).requires_grad_(True)
+        feat = torch.randn(2 * B, Cf, H, W, device=dev, generator=g)
+        if a.nhwc:
+            feat = feat.contiguous(memory_format=torch.channels_last)
+        feat = feat.view(2, B, Cf, H, W).requires_grad_(True)
         mlp = [(torch.randn(Cf, Cf, 1, device=dev, generator=g) / Cf ** 0.5).requires_grad_(True),
                torch.zeros(Cf, device=dev).requires_grad_(True),
                (torch.randn(2, Cf, 1, device=dev, generator=g) / Cf ** 0.5).requires_grad_(True),
