@@ -38,8 +38,8 @@ RCF_HD constexpr int rcf_cb(int D) { return 3 + 3 * D + D * (D + 1) / 2; }
 RCF_HD constexpr int rcf_segd(int D) { return 3 + 5 * D + 2 * D * D; }
 RCF_HD constexpr int rcf_sym_idx(int D, int d, int e) { return d * D - d * (d - 1) / 2 + (e - d); }
 
-#define RCF_POOL_CHUNK_NHWC 512
-RCF_HD int rcf_pool_chunk(int K, int nhwc) { return nhwc ? RCF_POOL_CHUNK_NHWC : (K <= 4 ? 2048 : 1024); }
+RCF_HD constexpr int rcf_pool_chunk_nhwc(int) { return 512; }   // pixels per CTA, channels-last pooling
+RCF_HD int rcf_pool_chunk(int K, int nhwc) { return nhwc ? rcf_pool_chunk_nhwc(K) : (K <= 4 ? 2048 : 1024); }
 
 // ---- memory plan ------------------------------------------------------------------------------
 struct RcfLayout {

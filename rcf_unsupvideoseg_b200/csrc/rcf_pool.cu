@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
 // Forward: per-thread accumulators acc[4 channels][K], no shuffles; the groups are combined through shared memory.
 template <int K>
 __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
-    constexpr int CHUNK = RCF_POOL_CHUNK_NHWC;
+    constexpr int CHUNK = rcf_pool_chunk_nhwc(K);
     extern __shared__ float sm[];
     float* msT = sm;                         // [CHUNK][K]   mask tile, pixel-major
     float* redn = sm + CHUNK * K;            // [groups][Cf*K]
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
 template <int K>
 static cudaError_t launch_pool_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
     const int groups = RCF_BLOCK / (a.Cf / 4);
-    const size_t smem = ((size_t)RCF_POOL_CHUNK_NHWC * K + (size_t)groups * a.Cf * K) * sizeof(float);
+    const size_t smem = ((size_t)rcf_pool_chunk_nhwc(K) * K + (size_t)groups * a.Cf * K) * sizeof(float);
     dim3 grid(a.nchunkp, a.nfd), block(RCF_BLOCK);
     k_pool_nhwc<K><<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
