@@ -14,15 +14,27 @@ __device__ inline void reduce_partials(const float* __restrict__ part, int nstat
     const int tid = threadIdx.x;
     const int sub = tid & (lps - 1);
     const int per_pass = blockDim.x / lps;
-    for (int s0 = 0; s0 < nstat; s0 += per_pass) {     // uniform trip count: shuffles stay convergent
-        const int s = s0 + tid / lps;
-        double v = 0.0;
-        if (s < nstat) {
-            const float* p = part + (size_t)s * nchunk;
-            for (int c = sub; c < nchunk; c += lps) v += (double)__ldcg(p + c);
+    constexpr int U = 4;                               // statistics in flight per thread (independent load chains)
+    for (int s0 = 0; s0 < nstat; s0 += U * per_pass) { // uniform trip count: shuffles stay convergent
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = s0 + u * per_pass + tid / lps;
+            v[u] = 0.0;
+            if (s < nstat) {
+                const float* p = part + (size_t)s * nchunk;
+                for (int c = sub; c < nchunk; c += lps) v[u] += (double)__ldcg(p + c);
+            }
         }
-        for (int o = lps >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (sub == 0 && s < nstat) out[s] = v;
+        for (int o = lps >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] += __shfl_xor_sync(0xffffffffu, v[u], o);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = s0 + u * per_pass + tid / lps;
+            if (sub == 0 && s < nstat) out[s] = v[u];
+        }
     }
 }
 
