@@ -104,6 +104,9 @@ typedef struct RcfInputs {
     const float* b1;           /* flow_feat_after_agg.0.bias   [Cf]                             */
     const float* w2;           /* flow_feat_after_agg.2.weight [2,Cf]                 (ref :99) */
     const float* b2;           /* flow_feat_after_agg.2.bias   [2]                              */
+    const float* feat_bias;    /* optional [Cf] (channels-last feat only): bias of the last conv of flow_feat_before_agg
+                                  (ref :89-91) added on load, so the conv runs bias-free and its separate bias-add and
+                                  bias-gradient reduction kernels disappear; NULL = feat already contains the bias */
 } RcfInputs;
 
 /* Optional per-pixel outputs of the forward pass; any pointer may be NULL. */
@@ -125,6 +128,7 @@ typedef struct RcfGrads {
     float* db1;        /* [Cf] */
     float* dw2;        /* [2,Cf] */
     float* db2;        /* [2] */
+    float* dfeat_bias; /* [Cf] gradient of RcfInputs.feat_bias (sum over pixels of dfeat), or NULL */
 } RcfGrads;
 
 /* ABI version of the loaded library (== RCF_ABI_VERSION of the header it was built from). */

@@ -38,7 +38,7 @@ class RcfDesc(C.Structure):
 class RcfInputs(C.Structure):
     _fields_ = [
         ("mask", _ptr2), ("flow", _ptr2), ("resid", _ptr2), ("feat", _ptr2), ("theta", _ptr2),
-        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("feat_bias", C.c_void_p),
     ]
 
 
@@ -50,7 +50,7 @@ class RcfVisOut(C.Structure):
 class RcfGrads(C.Structure):
     _fields_ = [
         ("dmask", _ptr2), ("dresid", _ptr2), ("dfeat", _ptr2), ("dtheta", _ptr2),
-        ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
+        ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p), ("dfeat_bias", C.c_void_p),
     ]
 
 

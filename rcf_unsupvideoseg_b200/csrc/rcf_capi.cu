@@ -55,6 +55,7 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
         a.resid_bs[i] = d.resid_bstride[i]; a.feat_bs[i] = d.feat_bstride[i];
     }
     a.w1 = in.w1; a.b1 = in.b1; a.w2 = in.w2; a.b2 = in.b2;
+    a.feat_bias = d.feat_nhwc ? in.feat_bias : nullptr;
     char* c = static_cast<char*>(ctx);
     a.segd = reinterpret_cast<double*>(c + L.c_segd);
     a.coef = reinterpret_cast<float*>(c + L.c_coef);
@@ -70,6 +71,9 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.dh = reinterpret_cast<double*>(w + L.w_dh);
     a.thbar = reinterpret_cast<double*>(w + L.w_thbar);
     a.sync = reinterpret_cast<int*>(w + L.w_sync);
+    a.dbpart = reinterpret_cast<float*>(w + L.w_dbpart);
+    a.dbfd = reinterpret_cast<double*>(w + L.w_dbfd);
+    a.nblkpb = L.nblkpb;
     a.lag = g_fused_lag;
     a.l2_hints = g_l2_hints;   // pass 2 streams flow/residual evict-first so the masks of pass 1 survive in L2
     a.nchunk1 = L.nchunk1; a.nchunk2 = L.nchunk2; a.nchunkb = L.nchunkb; a.nchunkp = L.nchunkp;
@@ -83,6 +87,7 @@ int validate_inputs(const RcfDesc& d, const RcfInputs& in) {
         else if (!in.theta[i]) return RCF_ERR_NULL;
     }
     if (d.theta_mode == 1 && (!in.w1 || !in.b1 || !in.w2 || !in.b2)) return RCF_ERR_NULL;
+    if (in.feat_bias && !d.feat_nhwc) return RCF_ERR_MODE;
     return RCF_OK;
 }
 
@@ -221,12 +226,13 @@ extern "C" int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const floa
         if (a.dfeat[i]) any_dfeat = true;
     }
     a.dw1 = grads->dw1; a.db1 = grads->db1; a.dw2 = grads->dw2; a.db2 = grads->db2;
+    a.dfeat_bias = (desc->feat_nhwc && in->feat_bias) ? grads->dfeat_bias : nullptr;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     RCF_CUDA(rcf_launch_segment_bwd(a, s));
     { ScopedTime t(RCF_TIME_BWD, s); RCF_CUDA(rcf_launch_bwd(a, vec, s)); }
     bool any_dmask = false;
     for (int i = 0; i < desc->ndir; ++i) any_dmask |= (a.dmask[i] != nullptr);
-    if (desc->theta_mode == 1 && (any_dmask || any_dfeat)) {
+    if (desc->theta_mode == 1 && (any_dmask || any_dfeat || a.dfeat_bias)) {
         // adds the pooled-feature term onto dmask (read-modify-write) and writes dfeat
         ScopedTime t(RCF_TIME_POOL_BWD, s);
         RCF_CUDA(rcf_launch_pool_bwd(a, vec_pool, s));

@@ -48,7 +48,8 @@ struct RcfLayout {
     // ctx (bytes offsets)
     size_t c_segd, c_coef, c_mlp, c_gm, c_bytes;
     // ws
-    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_sync, w_bytes;
+    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_sync, w_dbpart, w_dbfd, w_bytes;
+    int nblkpb;   // CTAs per frame-direction of the channels-last pooling backward (256 pixels each)
 };
 
 static inline size_t rcf_align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -84,6 +85,9 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.w_dh = o;      o = rcf_align256(o + nseg * d.Cf * sizeof(double));
     L.w_thbar = o;   o = rcf_align256(o + nseg * 2 * sizeof(double));
     L.w_sync = o;    o = rcf_align256(o + (size_t)(1 + 2 * L.nfd) * sizeof(int));   // ticket, pass-1 counters, ready flags
+    L.nblkpb = (L.P + 255) / 256;
+    L.w_dbpart = o;  o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * L.nblkpb * d.Cf * sizeof(float) : 0));   // per-CTA bias-gradient partials
+    L.w_dbfd = o;    o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * d.Cf * sizeof(double) : 0));
     L.w_bytes = o ? o : 256;
     return L;
 }
@@ -108,6 +112,7 @@ struct RcfK {
     const float* theta[2];
     long long mask_bs[2], flow_bs[2], resid_bs[2], feat_bs[2];
     const float *w1, *b1, *w2, *b2;
+    const float* feat_bias;   // [Cf] or null (channels-last only)
     // ctx
     double* segd;
     float* coef;
@@ -137,6 +142,10 @@ struct RcfK {
     float* dmask[2]; float* dresid[2]; float* dfeat[2]; float* dtheta[2];
     long long dmask_bs[2], dresid_bs[2], dfeat_bs[2];
     float *dw1, *db1, *dw2, *db2;
+    float* dfeat_bias;        // [Cf] or null
+    float* dbpart;            // ws: [nfd][nblkpb][Cf]
+    double* dbfd;             // ws: [nfd][Cf]
+    int nblkpb;
 };
 
 #ifdef __CUDACC__

@@ -173,6 +173,11 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
     const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
     const float* __restrict__ feat = a.feat[dir] + (long long)b * a.feat_bs[dir];
     const float slope = a.feat_slope;
+    float bias[4] = {0.0f, 0.0f, 0.0f, 0.0f};       // bias of the last conv, added on load (conv runs bias-free)
+    if (a.feat_bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bias[j] = __ldg(a.feat_bias + c4 * 4 + j);
+    }
 
     for (int i = tid; i < CHUNK * K; i += RCF_BLOCK) {
         const int k = i / CHUNK, p = i - k * CHUNK;                  // coalesced along pixels per plane
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
 #pragma unroll 8
     for (int p = grp; p < pend; p += groups) {
         const float4 g = __ldg(gp + (long long)p * nf4s);
-        float gv[4] = {g.x, g.y, g.z, g.w};
+        float gv[4] = {g.x + bias[0], g.y + bias[1], g.z + bias[2], g.w + bias[3]};
 #pragma unroll
         for (int j = 0; j < 4; ++j) gv[j] = gv[j] >= 0.0f ? gv[j] : slope * gv[j];
 #pragma unroll
@@ -247,6 +252,11 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int k = 0; k < K; ++k) c[j][k] = a.poolbar[(size_t)fd * Cf * K + (c4 * 4 + j) * K + k];
+    float bias[4] = {0.0f, 0.0f, 0.0f, 0.0f}, dbias[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (a.feat_bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bias[j] = __ldg(a.feat_bias + c4 * 4 + j);
+    }
     __syncthreads();
 
     const int pend = min(TP, P - p0);
@@ -273,7 +283,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
 #pragma unroll
         for (int k = 0; k < K; ++k) part[k] = 0.0f;
         if (live) {
-            float gv[4] = {g.x, g.y, g.z, g.w}, dact[4], dg[4];
+            float gv[4] = {g.x + bias[0], g.y + bias[1], g.z + bias[2], g.w + bias[3]}, dact[4], dg[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 dact[j] = gv[j] >= 0.0f ? 1.0f : slope;
@@ -289,7 +299,12 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
                     dg[j] = fmaf(c[j][k], m, dg[j]);
                 }
             }
-            if (dgp) dgp[(long long)p * nf4] = make_float4(dg[0] * dact[0], dg[1] * dact[1], dg[2] * dact[2], dg[3] * dact[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                dg[j] *= dact[j];
+                dbias[j] += dg[j];
+            }
+            if (dgp) dgp[(long long)p * nf4] = make_float4(dg[0], dg[1], dg[2], dg[3]);
         }
         if (fast) {
             if constexpr (K == 4) {
@@ -320,6 +335,51 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
             if (p0 + p < P) dmask[(long long)k * P + p0 + p] = dms[p * K + k];
         }
     }
+    if (a.dfeat_bias) {
+        // per-CTA partial of the bias gradient: combine the pixel groups in fixed order (tiles are free to reuse now)
+        __syncthreads();
+        float* red = sm;                       // [groups][Cf] = 1024 floats (the launch sizes shared memory for it)
+        for (int j = 0; j < 4; ++j) red[grp * Cf + c4 * 4 + j] = dbias[j];
+        __syncthreads();
+        for (int f = tid; f < Cf; f += RCF_BLOCK) {
+            float v = 0.0f;
+            for (int g2 = 0; g2 < groups; ++g2) v += red[g2 * Cf + f];
+            a.dbpart[((size_t)fd * a.nblkpb + blockIdx.x) * Cf + f] = v;
+        }
+    }
+}
+
+// bias gradient of the last conv: two fixed-order levels over the per-CTA partials of k_pool_bwd_nhwc
+__global__ void __launch_bounds__(256) k_bias_grad_fd(const RcfK a) {
+    const int fd = blockIdx.x, Cf = a.Cf, nb = a.nblkpb;
+    __shared__ double part[256];
+    const int lanes = Cf < 256 ? Cf : 256;                 // threads per slice
+    const int slices = 256 / lanes;
+    const int sl = threadIdx.x / lanes, t0 = threadIdx.x - sl * lanes;
+    for (int f0 = 0; f0 < Cf; f0 += lanes) {
+        const int f = f0 + t0;
+        double v = 0.0;
+        if (sl < slices && f < Cf) {
+            const int lo = (int)((long long)nb * sl / slices), hi = (int)((long long)nb * (sl + 1) / slices);
+#pragma unroll 8
+            for (int i = lo; i < hi; ++i) v += (double)__ldcg(a.dbpart + ((size_t)fd * nb + i) * Cf + f);
+        }
+        part[threadIdx.x] = v;
+        __syncthreads();
+        if (sl == 0 && f < Cf) {
+            double tot = 0.0;
+            for (int s2 = 0; s2 < slices; ++s2) tot += part[s2 * lanes + t0];
+            a.dbfd[(size_t)fd * Cf + f] = tot;
+        }
+        __syncthreads();
+    }
+}
+__global__ void k_bias_grad_final(const RcfK a) {
+    for (int f = threadIdx.x; f < a.Cf; f += blockDim.x) {
+        double v = 0.0;
+        for (int fd = 0; fd < a.nfd; ++fd) v += a.dbfd[(size_t)fd * a.Cf + f];
+        a.dfeat_bias[f] = (float)v;
+    }
 }
 
 template <int K>
@@ -334,7 +394,14 @@ static cudaError_t launch_pool_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
 template <int K>
 static cudaError_t launch_pool_bwd_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
     dim3 grid((a.P + 255) / 256, a.nfd), block(RCF_BLOCK);
-    k_pool_bwd_nhwc<K><<<grid, block, (size_t)2 * 256 * K * sizeof(float), s>>>(a);
+    const size_t tile = (size_t)2 * 256 * K, red = 1024;     // mask + dM tiles; [groups][Cf] = 1024 floats for the bias partial
+    k_pool_bwd_nhwc<K><<<grid, block, (tile > red ? tile : red) * sizeof(float), s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !a.dfeat_bias) return e;
+    k_bias_grad_fd<<<a.nfd, 256, 0, s>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_bias_grad_final<<<1, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

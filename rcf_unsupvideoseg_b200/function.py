@@ -115,7 +115,7 @@ class RcfMotionLossFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, spec: LossSpec, masks, feat, w1, b1, w2, b2, *per_dir):
+    def forward(ctx, spec: LossSpec, masks, feat, feat_bias, w1, b1, w2, b2, *per_dir):
         lib = _lib.load_library()
         ndir = masks.shape[1]
         assert len(per_dir) == 3 * ndir
@@ -137,6 +137,12 @@ class RcfMotionLossFn(torch.autograd.Function):
             assert feat is not None and tuple(feat.shape) == (ndir, B, spec.Cf, H, W), \
                 f"feature map shape {None if feat is None else tuple(feat.shape)}"
             feat_v, nhwc = _feat_layout(feat, spec.Cf, H, W)
+        fb = None
+        if feat_bias is not None:
+            if not nhwc:
+                raise RuntimeError("feat_bias needs a channels-last feature map (fuse the bias into the conv otherwise)")
+            fb = feat_bias.detach().float().contiguous()
+            assert fb.numel() == spec.Cf
         thetas_v = [t.float().contiguous() if t is not None else None for t in thetas]
         for f in flows_v:
             assert f.shape == (B, 2, H, W), f"flow shape {tuple(f.shape)}"
@@ -164,6 +170,8 @@ class RcfMotionLossFn(torch.autograd.Function):
                 inp.theta[i] = thetas_v[i].data_ptr()
         if spec.Cf > 0:
             inp.w1, inp.b1, inp.w2, inp.b2 = (t.data_ptr() for t in (w1c, b1c, w2c, b2c))
+            if fb is not None:
+                inp.feat_bias = fb.data_ptr()
 
         ctx_bytes, ws_bytes = _sizes(lib, desc, spec, B, ndir)
         ctx_buf = torch.empty(ctx_bytes, dtype=torch.uint8, device=dev)
@@ -188,10 +196,11 @@ class RcfMotionLossFn(torch.autograd.Function):
                                        C.byref(vis_struct) if vis_struct is not None else None, stream), "rcf_forward")
 
         ctx.spec, ctx.ndir, ctx.B, ctx.nhwc = spec, ndir, B, nhwc
+        ctx.has_fb = fb is not None
         ctx.masks_shape = tuple(masks.shape)
         ctx.save_for_backward(masks_v, ctx_buf, *flows_v, *resids_v,
                               *([feat_v] if feat_v is not None else []), *[t for t in thetas_v if t is not None],
-                              *([w1c, b1c, w2c, b2c] if spec.Cf > 0 else []))
+                              *([w1c, b1c, w2c, b2c] if spec.Cf > 0 else []), *([fb] if fb is not None else []))
         ctx.mark_non_differentiable(*vis_tensors)
         return (loss, *vis_tensors)
 
@@ -207,13 +216,14 @@ class RcfMotionLossFn(torch.autograd.Function):
         resids_v = saved[2 + ndir:2 + 2 * ndir]
         rest = saved[2 + 2 * ndir:]
         dev = masks_v.device
-        # needs_input_grad: (spec, masks, feat, w1, b1, w2, b2, *flows, *resids, *thetas)
+        # needs_input_grad: (spec, masks, feat, feat_bias, w1, b1, w2, b2, *flows, *resids, *thetas)
         need = ctx.needs_input_grad
         need_masks = need[1]
         need_feat = need[2]
-        need_w = any(need[3:7])
-        need_resid = [need[7 + ndir + i] for i in range(ndir)]
-        need_theta = [need[7 + 2 * ndir + i] for i in range(ndir)]
+        need_fb = need[3] and ctx.has_fb
+        need_w = any(need[4:8])
+        need_resid = [need[8 + ndir + i] for i in range(ndir)]
+        need_theta = [need[8 + 2 * ndir + i] for i in range(ndir)]
 
         desc = _make_desc(spec, B, ndir)
         desc.feat_nhwc = int(ctx.nhwc)
@@ -224,6 +234,8 @@ class RcfMotionLossFn(torch.autograd.Function):
             feat_v = rest[0]
             w1c, b1c, w2c, b2c = rest[1:5]
             inp.w1, inp.b1, inp.w2, inp.b2 = (t.data_ptr() for t in (w1c, b1c, w2c, b2c))
+            if ctx.has_fb:
+                inp.feat_bias = rest[5].data_ptr()
             if need_feat:
                 if ctx.nhwc:    # gradient in the layout of the feature map (cuDNN's backward then needs no transposes either)
                     d_feat = torch.empty((ndir * B, Cf, H, W), dtype=torch.float32, device=dev,
@@ -255,6 +267,10 @@ class RcfMotionLossFn(torch.autograd.Function):
                 if need_theta[i]:
                     d_thetas[i] = torch.empty(B, 2, K, dtype=torch.float32, device=dev)
                     grads.dtheta[i] = d_thetas[i].data_ptr()
+        d_fb = None
+        if Cf > 0 and need_fb:
+            d_fb = torch.empty(Cf, dtype=torch.float32, device=dev)
+            grads.dfeat_bias = d_fb.data_ptr()
         dw = [None, None, None, None]
         if Cf > 0 and need_w:
             dw = [torch.empty(Cf, Cf, 1, dtype=torch.float32, device=dev), torch.empty(Cf, dtype=torch.float32, device=dev),
@@ -268,18 +284,20 @@ class RcfMotionLossFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.rcf_backward(C.byref(desc), C.byref(inp), gl.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
                                         C.byref(grads), stream), "rcf_backward")
-        return (None, d_masks, d_feat, *dw, *([None] * ndir), *d_resids, *d_thetas)
+        return (None, d_masks, d_feat, d_fb, *dw, *([None] * ndir), *d_resids, *d_thetas)
 
 
 def rcf_motion_loss(spec: LossSpec, masks: torch.Tensor, flows: Sequence[torch.Tensor],
                     resids: Sequence[torch.Tensor], *, feats: Optional[Sequence[torch.Tensor]] = None,
-                    mlp: Optional[Sequence[torch.Tensor]] = None, thetas: Optional[Sequence[torch.Tensor]] = None):
+                    mlp: Optional[Sequence[torch.Tensor]] = None, thetas: Optional[Sequence[torch.Tensor]] = None,
+                    feat_bias: Optional[torch.Tensor] = None):
     """Functional entry point.  masks [B,ndir,K,H,W]; flows/resids (and feats or thetas) per direction.
 
     Returns (loss [ndir], vis tuple).  Exactly one of (feats + mlp weights) or thetas must be given,
     consistently with spec.Cf.  `feats` is either the direction-major 5-D tensor [ndir,B,Cf,H,W] (preferred:
     one conv call over the concatenated directions, no copies) or a sequence of per-direction [B,Cf,H,W] tensors
-    (stacked here, which costs a copy).
+    (stacked here, which costs a copy).  `feat_bias` [Cf] (channels-last feats only) is the bias of the conv that produced
+    `feats`, applied inside the kernels so that the conv itself can run bias-free.
     """
     ndir = masks.shape[1]
     feat = None
@@ -292,5 +310,5 @@ def rcf_motion_loss(spec: LossSpec, masks: torch.Tensor, flows: Sequence[torch.T
         assert thetas is not None
         w1 = b1 = w2 = b2 = None
         per_dir = (*flows, *resids, *thetas)
-    out = RcfMotionLossFn.apply(spec, masks, feat, w1, b1, w2, b2, *per_dir)
+    out = RcfMotionLossFn.apply(spec, masks, feat, feat_bias if feat is not None else None, w1, b1, w2, b2, *per_dir)
     return out[0], tuple(out[1:])

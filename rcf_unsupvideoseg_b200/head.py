@@ -170,12 +170,24 @@ class FlowAggregationHeadWithResidual(nn.Module):
         inside the pooling kernels (and its derivative inside the pooling backward), which saves one full read+write
         of the [B,Cf,H,W] map in forward and one read + one read+write in backward."""
         seq = self.flow_feat_before_agg
-        Cf = self.num_flow_feat_channels
-        if self.channels_last_features and Cf % 4 == 0 and Cf <= 128 and 256 % (Cf // 4) == 0:
+        if self._use_channels_last():
             # cuDNN's tensor-core convolutions are channels-last natively: feeding them channels-last tensors removes
-            # their NCHW<->NHWC transposes (27 of ~70 launches per step at 96x96); the pooling kernels read that layout
+            # their NCHW<->NHWC transposes (27 of ~70 launches per step at 96x96); the pooling kernels read that layout.
+            # The last conv runs WITHOUT its bias: the pooling kernels add it on load and return its gradient, which
+            # removes ATen's separate bias-add and bias-gradient reduction kernels over the [B,Cf,H,W] map.
             flow = flow.contiguous(memory_format=torch.channels_last)
-        return seq[2](seq[1](seq[0](flow)))
+            c2 = seq[2]
+            feat = F.conv2d(seq[1](seq[0](flow)), c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
+            if c2.bias is None:
+                return feat, None
+            if feat.is_contiguous(memory_format=torch.channels_last):
+                return feat, c2.bias
+            return feat + c2.bias.view(1, -1, 1, 1), None       # cuDNN answered in NCHW: plain bias add
+        return seq[2](seq[1](seq[0](flow))), None
+
+    def _use_channels_last(self) -> bool:
+        Cf = self.num_flow_feat_channels
+        return bool(self.channels_last_features) and Cf % 4 == 0 and Cf <= 128 and 256 % (Cf // 4) == 0
 
     def _spec(self, K, H, W, *, want_vis, vis_norm, inv_n=0.0, clamp_fused=True) -> LossSpec:
         unbounded = bool(self.free_residual and self.residual_adjustment_scale == -1.)
@@ -220,12 +232,12 @@ class FlowAggregationHeadWithResidual(nn.Module):
                 assert r.shape[-2:] == (H, W), f"residual spatial size {tuple(r.shape[-2:])} != mask size {(H, W)}"
                 k_flows.append(kf.detach()); c_flows.append(cf_); rs.append(r)
             # one pass of the conv branch over both directions (batch-concatenated), then a free 5-D view
-            feat = self._features_preact(torch.cat(c_flows, 0) if ndir > 1 else c_flows[0])
+            feat, feat_bias = self._features_preact(torch.cat(c_flows, 0) if ndir > 1 else c_flows[0])
             assert feat.shape[2:] == masks5.shape[3:], \
                 f"{feat.shape[2:]} != {masks5.shape[3:]} (should match on spatial dimension)"   # :247-248
             feat = feat.view(ndir, B, *feat.shape[1:])
             spec = self._spec(K, H, W, want_vis=want_vis, vis_norm=vis_norm, inv_n=inv_n, clamp_fused=fused)
-            loss, vis = rcf_motion_loss(spec, masks5, k_flows, rs, feats=feat, mlp=self._mlp_params())
+            loss, vis = rcf_motion_loss(spec, masks5, k_flows, rs, feats=feat, mlp=self._mlp_params(), feat_bias=feat_bias)
         return loss, vis
 
     # ------------------------------------------------------------------------------------------
@@ -251,11 +263,11 @@ class FlowAggregationHeadWithResidual(nn.Module):
         if self.allow_residual_resize and tuple(resid.shape[-2:]) != self.mask_size:
             resid = F.interpolate(resid, self.mask_size, mode='bilinear')
         with torch.no_grad(), torch.autocast(device_type="cuda", enabled=False):
-            feat = self._features_preact(flow)
+            feat, feat_bias = self._features_preact(flow)
             assert feat.shape[2:] == mask.shape[2:], f"{feat.shape[2:]} != {mask.shape[2:]} (should match on spatial dimension)"
             spec = self._spec(K, H, W, want_vis=True, vis_norm=False, clamp_fused=False)
             _, vis = rcf_motion_loss(spec, mask.float().unsqueeze(1), [flow], [resid], feats=feat.unsqueeze(0),
-                                     mlp=self._mlp_params())
+                                     mlp=self._mlp_params(), feat_bias=feat_bias)
         return vis[1], vis[2], vis[3], (vis[4] if len(vis) > 4 else None)
 
     def forward(self, imgs, masks, gt_fw_flows, gt_bw_flows, all_pred_residual_fw, all_pred_residual_bw):
