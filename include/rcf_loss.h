@@ -168,6 +168,19 @@ RCF_API int rcf_flow_warp_backward(const float* x, const float* flow, const floa
  * (absolute x,y positions) into out [B,1,H,W]; scratch_u64 = B*H*W 64-bit words (order-independent fixed-point sums). */
 RCF_API int rcf_corresponding_map(const float* coords, float* out, void* scratch_u64, int B, int H, int W, void* stream);
 
+/* ---- first layer of flow_feat_before_agg (reference :84-88): act = LeakyReLU(conv_ks(clamp(flow)) + bias) ----------
+ * flow[dir]: [B,2,H,W] planes with batch stride flow_bstride[dir] (elements); w [Cf,2,ks,ks]; b [Cf];
+ * act / dact: channels-last [ndir*B, H, W, Cf] dense (what the second, tensor-core convolution consumes natively).
+ * ks in {1,3,5}; Cf % 4 == 0, Cf <= 128, 256 % (Cf/4) == 0, else RCF_ERR_UNSUPPORTED (use the framework's conv).
+ * clamp_t < 0: no clamp.  No gradient w.r.t. the flow is produced (the RAFT flow carries none). */
+RCF_API int rcf_stem_forward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W, int Cf,
+                             int ks, const float* w, const float* b, float clamp_t, float slope, float* act, void* stream);
+RCF_API int rcf_stem_workspace_bytes(int ndir, int B, int H, int W, int Cf, int ks, size_t* bytes);
+/* dw [Cf,2,ks,ks], db [Cf] from dact (gradient w.r.t. act) and the forward output act; ws from rcf_stem_workspace_bytes. */
+RCF_API int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W, int Cf,
+                              int ks, float clamp_t, float slope, const float* act, const float* dact, float* dw, float* db,
+                              void* ws, void* stream);
+
 /* Measurement hook (bench.py): record the two caller-owned cudaEvent_t handles immediately before and
  * after the launch of streaming kernel `which` in the following rcf_forward / rcf_backward calls of this
  * process (on the stream those calls are given).  which: 0 off, 1 k_moments, 2 k_loss, 3 k_bwd,

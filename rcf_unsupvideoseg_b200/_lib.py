@@ -56,7 +56,7 @@ class RcfGrads(C.Structure):
 
 EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "rcf_forward", "rcf_backward",
                     "rcf_debug_time_kernel", "rcf_flow_warp_forward", "rcf_flow_warp_backward", "rcf_corresponding_map",
-                    "rcf_debug_set_option")
+                    "rcf_debug_set_option", "rcf_stem_forward", "rcf_stem_workspace_bytes", "rcf_stem_backward")
 
 _lib = None
 _lock = threading.Lock()
@@ -108,6 +108,15 @@ def load_library(build_if_missing: bool = True):
                                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.rcf_corresponding_map.restype = C.c_int
         lib.rcf_corresponding_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.rcf_stem_forward.restype = C.c_int
+        lib.rcf_stem_forward.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        lib.rcf_stem_workspace_bytes.restype = C.c_int
+        lib.rcf_stem_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        lib.rcf_stem_backward.restype = C.c_int
+        lib.rcf_stem_backward.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rcf_debug_set_option.restype = C.c_int
         lib.rcf_debug_set_option.argtypes = [C.c_int, C.c_int]
         if lib.rcf_abi_version() != RCF_ABI_VERSION:

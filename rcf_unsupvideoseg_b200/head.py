@@ -30,6 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .function import LossSpec, rcf_motion_loss
+from .stem import flow_stem, stem_supported
 
 logger = logging.getLogger("main")
 
@@ -138,6 +139,8 @@ class FlowAggregationHeadWithResidual(nn.Module):
         self.return_flows = True
         self.loss_inv_n = 0.0
         self.channels_last_features = True
+        #   handwritten_stem=False sends the first conv + LeakyReLU through cuDNN/ATen instead of csrc/rcf_stem.cu.
+        self.handwritten_stem = True
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -165,11 +168,28 @@ class FlowAggregationHeadWithResidual(nn.Module):
             # the reference reaches `return ..., residual_adjustment, ...` with the name unbound (:305-310)
             raise UnboundLocalError("local variable 'residual_adjustment' referenced before assignment")
 
-    def _features_preact(self, flow):
+    def _features_preact(self, flow, stem_flows=None, stem_clamp=None):
         """conv -> LeakyReLU -> conv of flow_feat_before_agg (reference :84-91); the trailing LeakyReLU (:92) is applied
         inside the pooling kernels (and its derivative inside the pooling backward), which saves one full read+write
-        of the [B,Cf,H,W] map in forward and one read + one read+write in backward."""
+        of the [B,Cf,H,W] map in forward and one read + one read+write in backward.
+
+        `flow` is the (prepared) conv input [N,2,H,W]; when `stem_flows` is given (per-direction raw flows whose only
+        preparation is the clamp `stem_clamp`) and the shape is supported, the first conv + LeakyReLU run as the
+        hand-written stem kernel instead and `flow` may be None."""
         seq = self.flow_feat_before_agg
+        if self._use_channels_last() and stem_flows is not None and self.handwritten_stem \
+                and stem_supported(self.num_flow_feat_channels, seq[0].kernel_size[0]) and seq[0].bias is not None:
+            c2 = seq[2]
+            act1 = flow_stem(stem_flows, seq[0].weight, seq[0].bias, stem_clamp, seq[1].negative_slope)
+            feat = F.conv2d(act1, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
+            if c2.bias is None:
+                return feat, None
+            if feat.is_contiguous(memory_format=torch.channels_last):
+                return feat, c2.bias
+            return feat + c2.bias.view(1, -1, 1, 1), None
+        if flow is None:
+            flow = torch.cat([self._clamped(f, stem_clamp) for f in stem_flows], 0) if len(stem_flows) > 1 \
+                else self._clamped(stem_flows[0], stem_clamp)
         if self._use_channels_last():
             # cuDNN's tensor-core convolutions are channels-last natively: feeding them channels-last tensors removes
             # their NCHW<->NHWC transposes (27 of ~70 launches per step at 96x96); the pooling kernels read that layout.
@@ -184,6 +204,10 @@ class FlowAggregationHeadWithResidual(nn.Module):
                 return feat, c2.bias
             return feat + c2.bias.view(1, -1, 1, 1), None       # cuDNN answered in NCHW: plain bias add
         return seq[2](seq[1](seq[0](flow))), None
+
+    @staticmethod
+    def _clamped(f, t):
+        return f if t is None else f.clamp(min=-t, max=t)
 
     def _use_channels_last(self) -> bool:
         Cf = self.num_flow_feat_channels
@@ -202,8 +226,7 @@ class FlowAggregationHeadWithResidual(nn.Module):
     def _prepare(self, flow, resid, H, W):
         """Returns (flow for the kernels, flow for the conv branch, clamp_fused, residual at mask_size)."""
         if self._fused_clamp():
-            k_flow = flow
-            c_flow = flow.clamp(min=-self.clamp_flow_t, max=self.clamp_flow_t) if self.clamp_flow_t is not None else flow
+            k_flow, c_flow = flow, None        # the clamp is applied inside the kernels (loss passes and conv stem)
             fused = True
         else:
             k_flow = c_flow = self.norm_and_clamp_flow(flow)
@@ -232,7 +255,10 @@ class FlowAggregationHeadWithResidual(nn.Module):
                 assert r.shape[-2:] == (H, W), f"residual spatial size {tuple(r.shape[-2:])} != mask size {(H, W)}"
                 k_flows.append(kf.detach()); c_flows.append(cf_); rs.append(r)
             # one pass of the conv branch over both directions (batch-concatenated), then a free 5-D view
-            feat, feat_bias = self._features_preact(torch.cat(c_flows, 0) if ndir > 1 else c_flows[0])
+            if fused:   # only the clamp stands between the raw flow and the conv: the stem kernel applies it itself
+                feat, feat_bias = self._features_preact(None, stem_flows=k_flows, stem_clamp=self.clamp_flow_t)
+            else:
+                feat, feat_bias = self._features_preact(torch.cat(c_flows, 0) if ndir > 1 else c_flows[0])
             assert feat.shape[2:] == masks5.shape[3:], \
                 f"{feat.shape[2:]} != {masks5.shape[3:]} (should match on spatial dimension)"   # :247-248
             feat = feat.view(ndir, B, *feat.shape[1:])
@@ -263,7 +289,7 @@ class FlowAggregationHeadWithResidual(nn.Module):
         if self.allow_residual_resize and tuple(resid.shape[-2:]) != self.mask_size:
             resid = F.interpolate(resid, self.mask_size, mode='bilinear')
         with torch.no_grad(), torch.autocast(device_type="cuda", enabled=False):
-            feat, feat_bias = self._features_preact(flow)
+            feat, feat_bias = self._features_preact(None, stem_flows=[flow], stem_clamp=None)
             assert feat.shape[2:] == mask.shape[2:], f"{feat.shape[2:]} != {mask.shape[2:]} (should match on spatial dimension)"
             spec = self._spec(K, H, W, want_vis=True, vis_norm=False, clamp_fused=False)
             _, vis = rcf_motion_loss(spec, mask.float().unsqueeze(1), [flow], [resid], feats=feat.unsqueeze(0),

@@ -423,3 +423,41 @@ def test_channels_last_feature_path_matches_nchw(rcf, name):
     assert rel_l2(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) < 2e-5
     for a_, b_ in zip(res[0][3], res[1][3]):
         assert rel_l2(a_.cpu().numpy(), b_.cpu().numpy()) < 2e-4
+
+
+@pytest.mark.parametrize("ks,Cf,H,W", [(3, 64, 19, 23), (1, 16, 8, 12), (5, 8, 14, 9), (3, 128, 6, 6)])
+def test_handwritten_conv_stem_vs_torch(rcf, ks, Cf, H, W):
+    """csrc/rcf_stem.cu (clamp + conv + bias + LeakyReLU, and its weight/bias gradients) against ATen in fp64."""
+    from rcf_unsupvideoseg_b200.stem import flow_stem
+    torch.manual_seed(3)
+    B = 3
+    flows = [torch.randn(B, 2, H, W, device="cuda") * 15 for _ in range(2)]
+    conv = torch.nn.Conv2d(2, Cf, ks, padding=(ks - 1) // 2).cuda()
+    act = flow_stem(flows, conv.weight, conv.bias, 20.0, 0.1)
+    gout = torch.randn_like(act)
+    gw, gb = torch.autograd.grad(act, [conv.weight, conv.bias], gout)
+    conv64 = torch.nn.Conv2d(2, Cf, ks, padding=(ks - 1) // 2).cuda().double()
+    conv64.load_state_dict({k: v.double() for k, v in conv.state_dict().items()})
+    x64 = torch.cat(flows, 0).double().clamp(-20, 20)
+    ref = torch.nn.functional.leaky_relu(conv64(x64), 0.1)
+    rw, rb = torch.autograd.grad(ref, [conv64.weight, conv64.bias], gout.double())
+    assert act.shape == (2 * B, Cf, H, W) and act.is_contiguous(memory_format=torch.channels_last)
+    assert rel_l2(act.cpu().numpy(), ref.cpu().numpy()) < 1e-6
+    assert rel_l2(gw.cpu().numpy(), rw.cpu().numpy()) < 1e-5
+    assert rel_l2(gb.cpu().numpy(), rb.cpu().numpy()) < 1e-5
+    gw2, gb2 = torch.autograd.grad(flow_stem(flows, conv.weight, conv.bias, 20.0, 0.1), [conv.weight, conv.bias], gout)
+    assert torch.equal(gw, gw2) and torch.equal(gb, gb2)        # deterministic reduction
+
+
+def test_head_paths_agree_stem_on_off(rcf):
+    g = Golden("affine_l1")
+    res = []
+    for stem in (True, False):
+        head = build_head(rcf, g)
+        head.handwritten_stem = stem
+        flows, loss, grads = run_head(head, g.inputs, g.gbar)
+        res.append((float(loss["seg"]), grads["d_masks"], [p.grad.clone() for p in head.parameters()]))
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[1][0])
+    assert rel_l2(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) < 2e-5
+    for a_, b_ in zip(res[0][2], res[1][2]):
+        assert rel_l2(a_.cpu().numpy(), b_.cpu().numpy()) < 2e-4
