@@ -48,7 +48,7 @@ struct RcfLayout {
     // ctx (bytes offsets)
     size_t c_segd, c_coef, c_mlp, c_gm, c_bytes;
     // ws
-    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_sync, w_dbpart, w_dbfd, w_bytes;
+    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_sync, w_dbpart, w_dbfd, w_poolsum, w_bytes;
     int nblkpb;   // CTAs per frame-direction of the channels-last pooling backward (256 pixels each)
 };
 
@@ -88,6 +88,7 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.nblkpb = (L.P + 255) / 256;
     L.w_dbpart = o;  o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * L.nblkpb * d.Cf * sizeof(float) : 0));   // per-CTA bias-gradient partials
     L.w_dbfd = o;    o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * d.Cf * sizeof(double) : 0));
+    L.w_poolsum = o; o = rcf_align256(o + nseg * d.Cf * sizeof(double));
     L.w_bytes = o ? o : 256;
     return L;
 }
@@ -145,6 +146,7 @@ struct RcfK {
     float* dfeat_bias;        // [Cf] or null
     float* dbpart;            // ws: [nfd][nblkpb][Cf]
     double* dbfd;             // ws: [nfd][Cf]
+    double* poolsum;          // ws: [nfd][Cf*K] pooled sums (un-normalised), reduced over chunks by k_pool_reduce
     int nblkpb;
 };
 
@@ -249,6 +251,21 @@ __device__ __forceinline__ void warp_reduce_store(const float (&acc)[N], int lan
         if ((lane & ((1 << SH) - 1)) == 0 && BASE + idx < N) dst[BASE + idx] = tot;
         warp_reduce_store<N, BASE + 32>(acc, lane, dst);
     }
+}
+
+// One warp sums n floats at base[i*stride] in fp64: lanes stride over i with four independent chains (loads in flight),
+// then a butterfly.  The order depends on n only => bit-reproducible.  Loads bypass L1 (written by other SMs / kernels).
+__device__ __forceinline__ double warp_sum_strided(const float* __restrict__ base, int n, long long stride, int lane) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int i = lane;
+    for (; i + 96 < n; i += 128) {
+        a0 += (double)__ldcg(base + (long long)i * stride);
+        a1 += (double)__ldcg(base + (long long)(i + 32) * stride);
+        a2 += (double)__ldcg(base + (long long)(i + 64) * stride);
+        a3 += (double)__ldcg(base + (long long)(i + 96) * stride);
+    }
+    for (; i < n; i += 32) a0 += (double)__ldcg(base + (long long)i * stride);
+    return warp_sum_d((a0 + a1) + (a2 + a3));
 }
 
 __device__ __forceinline__ float fast_ex2(float x) {

@@ -349,30 +349,24 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
     }
 }
 
-// bias gradient of the last conv: two fixed-order levels over the per-CTA partials of k_pool_bwd_nhwc
+// Chunk partials of the pooling -> pooled sums, one warp per (frame-direction, channel, segment): thousands of warps
+// instead of one CTA per frame-direction walking hundreds of chunks serially inside k_segment_fwd.
+__global__ void __launch_bounds__(256) k_pool_reduce(const RcfK a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nout = a.nfd * a.Cf * a.K;
+    if (warp >= nout) return;
+    const double v = warp_sum_strided(a.partp + (size_t)warp * a.nchunkp, a.nchunkp, 1, lane);
+    if (lane == 0) a.poolsum[warp] = v;
+}
+
+// bias gradient of the last conv: two fixed-order levels over the per-CTA partials of k_pool_bwd_nhwc;
+// level 1 = one warp per (frame-direction, channel)
 __global__ void __launch_bounds__(256) k_bias_grad_fd(const RcfK a) {
-    const int fd = blockIdx.x, Cf = a.Cf, nb = a.nblkpb;
-    __shared__ double part[256];
-    const int lanes = Cf < 256 ? Cf : 256;                 // threads per slice
-    const int slices = 256 / lanes;
-    const int sl = threadIdx.x / lanes, t0 = threadIdx.x - sl * lanes;
-    for (int f0 = 0; f0 < Cf; f0 += lanes) {
-        const int f = f0 + t0;
-        double v = 0.0;
-        if (sl < slices && f < Cf) {
-            const int lo = (int)((long long)nb * sl / slices), hi = (int)((long long)nb * (sl + 1) / slices);
-#pragma unroll 8
-            for (int i = lo; i < hi; ++i) v += (double)__ldcg(a.dbpart + ((size_t)fd * nb + i) * Cf + f);
-        }
-        part[threadIdx.x] = v;
-        __syncthreads();
-        if (sl == 0 && f < Cf) {
-            double tot = 0.0;
-            for (int s2 = 0; s2 < slices; ++s2) tot += part[s2 * lanes + t0];
-            a.dbfd[(size_t)fd * Cf + f] = tot;
-        }
-        __syncthreads();
-    }
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.nfd * a.Cf) return;
+    const int fd = warp / a.Cf, f = warp - fd * a.Cf;
+    const double v = warp_sum_strided(a.dbpart + (size_t)fd * a.nblkpb * a.Cf + f, a.nblkpb, a.Cf, lane);
+    if (lane == 0) a.dbfd[warp] = v;
 }
 __global__ void k_bias_grad_final(const RcfK a) {
     for (int f = threadIdx.x; f < a.Cf; f += blockDim.x) {
@@ -398,7 +392,7 @@ static cudaError_t launch_pool_bwd_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
     k_pool_bwd_nhwc<K><<<grid, block, (tile > red ? tile : red) * sizeof(float), s>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !a.dfeat_bias) return e;
-    k_bias_grad_fd<<<a.nfd, 256, 0, s>>>(a);
+    k_bias_grad_fd<<<(a.nfd * a.Cf * 32 + 255) / 256, 256, 0, s>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_bias_grad_final<<<1, 256, 0, s>>>(a);
@@ -444,9 +438,16 @@ static cudaError_t launch_pool_bwd_k(const RcfK& a, bool vec, cudaStream_t s) {
     }                                                      \
     return cudaErrorInvalidValue;
 
-cudaError_t rcf_launch_pool(const RcfK& a, bool vec, cudaStream_t s) {
+static cudaError_t launch_pool_dispatch(const RcfK& a, bool vec, cudaStream_t s) {
     if (a.feat_nhwc) { RCF_K_SWITCH(launch_pool_nhwc_k) }
     RCF_K_SWITCH(launch_pool_k)
+}
+cudaError_t rcf_launch_pool(const RcfK& a, bool vec, cudaStream_t s) {
+    const cudaError_t e = launch_pool_dispatch(a, vec, s);
+    if (e != cudaSuccess) return e;
+    const int nout = a.nfd * a.Cf * a.K;
+    k_pool_reduce<<<(nout * 32 + 255) / 256, 256, 0, s>>>(a);
+    return cudaGetLastError();
 }
 cudaError_t rcf_launch_pool_bwd(const RcfK& a, bool vec, cudaStream_t s) {
     if (a.feat_nhwc) { RCF_K_SWITCH(launch_pool_bwd_nhwc_k) }

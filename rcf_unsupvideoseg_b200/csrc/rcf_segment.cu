@@ -34,9 +34,8 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_fwd(const RcfK a) {
     if (a.theta_mode == 1) {
         double* pool = dyn;              // [f*K + k]
         double* hpre = dyn + Cf * K;     // [i*K + k]
-        reduce_partials(a.partp + (size_t)fd * Cf * K * a.nchunkp, Cf * K, a.nchunkp, pool);
-        __syncthreads();
-        for (int i = tid; i < Cf * K; i += blockDim.x) pool[i] /= stat[(i % K) * NS];
+        for (int i = tid; i < Cf * K; i += blockDim.x)          // chunk partials were summed by k_pool_reduce
+            pool[i] = __ldcg(a.poolsum + (size_t)fd * Cf * K + i) / stat[(i % K) * NS];
         __syncthreads();
         double* mlp = a.mlp + (size_t)fd * K * 2 * Cf;   // [k][0: pool | 1: hpre][Cf]
         for (int t = tid; t < Cf * K; t += blockDim.x) {

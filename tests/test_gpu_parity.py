@@ -442,7 +442,7 @@ def test_handwritten_conv_stem_vs_torch(rcf, ks, Cf, H, W):
     ref = torch.nn.functional.leaky_relu(conv64(x64), 0.1)
     rw, rb = torch.autograd.grad(ref, [conv64.weight, conv64.bias], gout.double())
     assert act.shape == (2 * B, Cf, H, W) and act.is_contiguous(memory_format=torch.channels_last)
-    assert rel_l2(act.cpu().numpy(), ref.cpu().numpy()) < 1e-6
+    assert rel_l2(act.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
     assert rel_l2(gw.cpu().numpy(), rw.cpu().numpy()) < 1e-5
     assert rel_l2(gb.cpu().numpy(), rb.cpu().numpy()) < 1e-5
     gw2, gb2 = torch.autograd.grad(flow_stem(flows, conv.weight, conv.bias, 20.0, 0.1), [conv.weight, conv.bias], gout)
