@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_stem_fwd(const StemK a) {
     }
     __syncthreads();
     float4* __restrict__ out = reinterpret_cast<float4*>(a.act + (long long)n * a.P * Cf) + c4;
+#pragma unroll 2
     for (int p = grp; p < STEM_TW * STEM_TH; p += groups) {
         const int ly = p / STEM_TW, lx = p - ly * STEM_TW;
         const int y = y0 + ly, x = x0 + lx;
