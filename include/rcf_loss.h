@@ -44,7 +44,7 @@ extern "C" {
 #define RCF_API
 #endif
 
-#define RCF_ABI_VERSION 1
+#define RCF_ABI_VERSION 2
 #define RCF_MAX_K 8          /* mask_layer supported by the compiled kernels */
 #define RCF_MAX_CF 256       /* num_flow_feat_channels supported by the segment kernels */
 
@@ -92,6 +92,10 @@ typedef struct RcfDesc {
        cuDNN's tensor-core convolutions produce natively; avoids its NCHW<->NHWC transposes).  Requires Cf % 4 == 0,
        Cf <= 128 and 256 % (Cf/4) == 0. */
     int32_t feat_nhwc;
+    /* rcf_backward: 0 = grad_loss holds ndir floats (one upstream gradient per direction); 1 = grad_loss holds ONE float,
+       the gradient of the total loss[ndir] = flow_loss['seg'] (reference :397), applied to every direction.  The
+       reference's caller only ever differentiates 'seg' (rcf_model.py:464-470). */
+    int32_t grad_loss_total;
 } RcfDesc;
 
 typedef struct RcfInputs {
@@ -143,12 +147,13 @@ RCF_API int rcf_query_sizes(const RcfDesc* desc, size_t* ctx_bytes, size_t* ws_b
 
 /* Forward: replaces norm_and_clamp_flow's clamp (:155-156), aggregate_flow_with_residual (:235-310,
  * incl. get_demean_affine_flow :164-233) and the loss terms (:359-368) for ndir directions.
- * loss[dir] (device, fp32) receives flow_loss['seg_fw'] / ['seg_bw'].  `vis` may be NULL. */
+ * loss (device, fp32, ndir + 1 floats): loss[dir] receives flow_loss['seg_fw'] / ['seg_bw'] and loss[ndir] their
+ * sum flow_loss['seg'] (:397).  `vis` may be NULL. */
 RCF_API int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss, void* ctx, void* ws,
                 const RcfVisOut* vis, void* stream);
 
-/* Backward of sum_dir grad_loss[dir] * loss[dir] (grad_loss: device, fp32, [ndir]); replaces the
- * autograd replay of every op of :242-368.  `ctx` must come from rcf_forward on the same inputs. */
+/* Backward of sum_dir grad_loss[dir] * loss[dir] (grad_loss: device, fp32, [ndir]; or one float, the gradient of
+ * loss[ndir], when desc->grad_loss_total); replaces the autograd replay of every op of :242-368.  `ctx` must come from rcf_forward on the same inputs. */
 RCF_API int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const float* grad_loss, const void* ctx,
                  void* ws, const RcfGrads* grads, void* stream);
 
@@ -180,6 +185,16 @@ RCF_API int rcf_stem_workspace_bytes(int ndir, int B, int H, int W, int Cf, int 
 RCF_API int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W, int Cf,
                               int ks, float clamp_t, float slope, const float* act, const float* dact, float* dw, float* db,
                               void* ws, void* stream);
+
+/* ---- input staging: bilinear resize of dense NCHW fp32 planes ------------------------------------
+ * Replaces F.interpolate(all_pred_residual, mask_size, mode='bilinear') of the head (reference :271-273, :294-296;
+ * align_corners = 0) and mmseg's resize() of the RAFT flows in the caller (models/rcf_model.py:438-442; align_corners
+ * from the config).  nten (1 or 2) tensors of `planes` = B*C planes each are resized [h,w] -> [H,W] in one launch.
+ * The backward is a deterministic gather (no atomics, no zero-fill): grad_in[h,w] from grad_out[H,W]. */
+RCF_API int rcf_resize_bilinear_forward(const float* const* in, float* const* out, int nten, int planes, int h, int w,
+                                        int H, int W, int align_corners, void* stream);
+RCF_API int rcf_resize_bilinear_backward(const float* const* grad_out, float* const* grad_in, int nten, int planes, int h,
+                                         int w, int H, int W, int align_corners, void* stream);
 
 /* Measurement hook (bench.py): record the two caller-owned cudaEvent_t handles immediately before and
  * after the launch of streaming kernel `which` in the following rcf_forward / rcf_backward calls of this

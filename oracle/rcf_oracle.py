@@ -101,10 +101,15 @@ def conv2d_same_backward(x, w, dout, need_dx=True):
     return dx, dw, db
 
 
-def _interp_axis(n_in: int, n_out: int):
-    """Source indices / weights of F.interpolate(mode='bilinear', align_corners=False)."""
-    scale = n_in / n_out
-    src = (np.arange(n_out, dtype=np.float64) + 0.5) * scale - 0.5
+def _interp_axis(n_in: int, n_out: int, align_corners: bool = False):
+    """Source indices / weights of F.interpolate(mode='bilinear') (ATen upsample_bilinear2d: scale = in/out and
+    src = max(scale*(dst+0.5)-0.5, 0), or scale = (in-1)/(out-1) and src = scale*dst with align_corners)."""
+    if align_corners:
+        scale = (n_in - 1) / (n_out - 1) if n_out > 1 else 0.0
+        src = np.arange(n_out, dtype=np.float64) * scale
+    else:
+        scale = n_in / n_out
+        src = (np.arange(n_out, dtype=np.float64) + 0.5) * scale - 0.5
     src = np.maximum(src, 0.0)
     i0 = np.minimum(np.floor(src).astype(np.int64), n_in - 1)
     i1 = np.minimum(i0 + 1, n_in - 1)
@@ -112,21 +117,22 @@ def _interp_axis(n_in: int, n_out: int):
     return i0, i1, lam
 
 
-def bilinear_resize(x, size):
-    """[B,C,h,w] -> [B,C,H,W]; reference :271-273 (F.interpolate defaults)."""
+def bilinear_resize(x, size, align_corners: bool = False):
+    """[B,C,h,w] -> [B,C,H,W]; reference :271-273 (F.interpolate defaults) and, with align_corners, the caller's
+    mmseg resize of the flows (models/rcf_model.py:438-442)."""
     H, W = size
     h, w = x.shape[2:]
-    y0, y1, ly = _interp_axis(h, H)
-    x0, x1, lx = _interp_axis(w, W)
+    y0, y1, ly = _interp_axis(h, H, align_corners)
+    x0, x1, lx = _interp_axis(w, W, align_corners)
     rows = x[:, :, y0, :] * (1 - ly)[None, None, :, None] + x[:, :, y1, :] * ly[None, None, :, None]
     return rows[:, :, :, x0] * (1 - lx) + rows[:, :, :, x1] * lx
 
 
-def bilinear_resize_backward(dout, in_size):
+def bilinear_resize_backward(dout, in_size, align_corners: bool = False):
     h, w = in_size
     B, C, H, W = dout.shape
-    y0, y1, ly = _interp_axis(h, H)
-    x0, x1, lx = _interp_axis(w, W)
+    y0, y1, ly = _interp_axis(h, H, align_corners)
+    x0, x1, lx = _interp_axis(w, W, align_corners)
     drows = np.zeros((B, C, H, w), dtype=dout.dtype)
     np.add.at(drows, (slice(None), slice(None), slice(None), x0), dout * (1 - lx))
     np.add.at(drows, (slice(None), slice(None), slice(None), x1), dout * lx)

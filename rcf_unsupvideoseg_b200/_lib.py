@@ -12,7 +12,7 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "librcf_loss.so")
 
-RCF_ABI_VERSION = 1
+RCF_ABI_VERSION = 2
 RCF_MAX_K = 8
 RCF_MAX_CF = 256
 
@@ -31,7 +31,7 @@ class RcfDesc(C.Structure):
         ("mask_bstride", _i64x2), ("flow_bstride", _i64x2), ("resid_bstride", _i64x2), ("feat_bstride", _i64x2),
         ("dmask_bstride", _i64x2), ("dresid_bstride", _i64x2), ("dfeat_bstride", _i64x2),
         ("vis_bstride", C.c_int64), ("vis_dstride", C.c_int64), ("vis_scale", C.c_float * 2),
-        ("feat_lrelu_slope", C.c_float), ("feat_nhwc", C.c_int32),
+        ("feat_lrelu_slope", C.c_float), ("feat_nhwc", C.c_int32), ("grad_loss_total", C.c_int32),
     ]
 
 
@@ -56,7 +56,8 @@ class RcfGrads(C.Structure):
 
 EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "rcf_forward", "rcf_backward",
                     "rcf_debug_time_kernel", "rcf_flow_warp_forward", "rcf_flow_warp_backward", "rcf_corresponding_map",
-                    "rcf_debug_set_option", "rcf_stem_forward", "rcf_stem_workspace_bytes", "rcf_stem_backward")
+                    "rcf_debug_set_option", "rcf_stem_forward", "rcf_stem_workspace_bytes", "rcf_stem_backward",
+                    "rcf_resize_bilinear_forward", "rcf_resize_bilinear_backward")
 
 _lib = None
 _lock = threading.Lock()
@@ -117,6 +118,10 @@ def load_library(build_if_missing: bool = True):
         lib.rcf_stem_backward.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p]
+        for fn in (lib.rcf_resize_bilinear_forward, lib.rcf_resize_bilinear_backward):
+            fn.restype = C.c_int
+            fn.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                           C.c_int, C.c_int, C.c_void_p]
         lib.rcf_debug_set_option.restype = C.c_int
         lib.rcf_debug_set_option.argtypes = [C.c_int, C.c_int]
         if lib.rcf_abi_version() != RCF_ABI_VERSION:

@@ -210,6 +210,7 @@ extern "C" int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const floa
     RcfK a;
     fill_common(a, *desc, *in, L, const_cast<void*>(ctx), ws);
     a.grad_loss = grad_loss;
+    a.grad_total = desc->grad_loss_total ? 1 : 0;
     bool vec = vec_ok_inputs(*desc, *in, false);
     bool vec_pool = vec_ok_inputs(*desc, *in, true);
     bool any_dfeat = false;

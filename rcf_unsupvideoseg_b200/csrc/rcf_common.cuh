@@ -140,6 +140,7 @@ struct RcfK {
     float vis_scale[2];
     // backward
     const float* grad_loss;
+    int grad_total;           // grad_loss is one float (gradient of the total), not one per direction
     float* dmask[2]; float* dresid[2]; float* dfeat[2]; float* dtheta[2];
     long long dmask_bs[2], dresid_bs[2], dfeat_bs[2];
     float *dw1, *db1, *dw2, *db2;

@@ -1,0 +1,157 @@
+// rcf_resize.cu -- bilinear resize of NCHW fp32 planes, forward and (deterministic) backward.
+//
+// Reference call sites (input staging):
+//   models/flow_aggregation_head_with_residual.py:271-273, :294-296
+//       all_pred_residual = F.interpolate(all_pred_residual, self.mask_size, mode='bilinear')   (align_corners=False)
+//   models/rcf_model.py:438-442   mmseg `resize(gt_*_flows, size=mask_size, mode='bilinear', align_corners=...)`
+// Both end in ATen's upsample_bilinear2d: per output pixel
+//   src = align ? scale*dst : max(scale*(dst+0.5)-0.5, 0),  i0 = (int)src,  i1 = i0 + (i0 < in-1),  l1 = src-i0,  l0 = 1-l1
+//   out = l0y*(l0x*v00 + l1x*v01) + l1y*(l0x*v10 + l1x*v11),      scale = align ? (in-1)/(out-1) : in/out   (fp32)
+// ATen's forward launches 9 CTAs for the DAVIS training shape (8x8x48x48 -> 96x96: 36 us on a B200) and its backward is a
+// zero-fill plus float atomics (order-dependent).  Here: one launch covers both directions' tensors, 128-bit stores, and
+// the backward is a GATHER (each input pixel sums the output pixels whose footprint contains it, in a fixed order), so
+// gradients are bit-reproducible and need no zero-fill.
+#include "rcf_common.cuh"
+
+namespace {
+
+struct ResizeK {
+    const float* src[2];
+    float* dst[2];
+    int h, w, H, W;          // input (h,w) -> output (H,W) of the FORWARD op
+    float sy, sx;            // source-index scales
+    int align;
+};
+
+__device__ __forceinline__ float src_index(float scale, int dst, int align) {
+    if (align) return scale * (float)dst;
+    const float s = scale * ((float)dst + 0.5f) - 0.5f;
+    return s < 0.0f ? 0.0f : s;
+}
+
+struct Tap1 { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Tap1 make_tap1(float scale, int dst, int n_in, int align) {
+    Tap1 t;
+    const float s = src_index(scale, dst, align);
+    t.i0 = min((int)s, n_in - 1);
+    t.i1 = t.i0 + (t.i0 < n_in - 1 ? 1 : 0);
+    t.l1 = s - (float)t.i0;
+    t.l0 = 1.0f - t.l1;
+    return t;
+}
+
+// PX consecutive output pixels (flat index within the plane) per thread.
+template <int PX>
+__global__ void __launch_bounds__(256) k_resize_fwd(const ResizeK a) {
+    const int P = a.H * a.W;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
+    if (p >= P) return;
+    const size_t plane = blockIdx.y;
+    const float* __restrict__ in = a.src[blockIdx.z] + plane * (size_t)a.h * a.w;
+    float* __restrict__ out = a.dst[blockIdx.z] + plane * (size_t)P;
+    int y = p / a.W, x = p - y * a.W;
+    Tap1 ty = make_tap1(a.sy, y, a.h, a.align);
+    float v[PX];
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+        const Tap1 tx = make_tap1(a.sx, x, a.w, a.align);
+        const float* r0 = in + (size_t)ty.i0 * a.w;
+        const float* r1 = in + (size_t)ty.i1 * a.w;
+        v[j] = ty.l0 * (tx.l0 * __ldg(r0 + tx.i0) + tx.l1 * __ldg(r0 + tx.i1))
+             + ty.l1 * (tx.l0 * __ldg(r1 + tx.i0) + tx.l1 * __ldg(r1 + tx.i1));
+        if (++x == a.W) { x = 0; ++y; if (j + 1 < PX && y < a.H) ty = make_tap1(a.sy, y, a.h, a.align); }
+    }
+    Pack<PX>::st(out + p, v);
+}
+
+// Conservative range of output indices whose taps can touch input index j (every candidate is then tested exactly).
+__device__ __forceinline__ void cand_range(float scale, int j, int n_out, int align, int& lo, int& hi) {
+    if (!(scale > 1e-12f)) { lo = 0; hi = n_out - 1; return; }
+    const float inv = 1.0f / scale;
+    float a, b;
+    if (align) { a = ((float)j - 1.0f) * inv; b = ((float)j + 1.0f) * inv; }
+    else { a = ((float)j - 0.5f) * inv - 0.5f; b = ((float)j + 1.5f) * inv - 0.5f; }
+    a = fminf(fmaxf(a - 2.0f, 0.0f), (float)(n_out - 1));
+    b = fminf(fmaxf(b + 2.0f, 0.0f), (float)(n_out - 1));
+    lo = (int)a; hi = (int)b;
+}
+
+__device__ __forceinline__ float tap_weight(const Tap1& t, int j) {
+    return (t.i0 == j ? t.l0 : 0.0f) + (t.i1 == j ? t.l1 : 0.0f);
+}
+
+// One thread per INPUT pixel (of the forward op): dst = grad_in [h,w], src = grad_out [H,W].
+__global__ void __launch_bounds__(256) k_resize_bwd(const ResizeK a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.h * a.w) return;
+    const size_t plane = blockIdx.y;
+    const float* __restrict__ g = a.src[blockIdx.z] + plane * (size_t)a.H * a.W;
+    float* __restrict__ gi = a.dst[blockIdx.z] + plane * (size_t)a.h * a.w;
+    const int j = p / a.w, i = p - j * a.w;
+    int ylo, yhi, xlo, xhi;
+    cand_range(a.sy, j, a.H, a.align, ylo, yhi);
+    cand_range(a.sx, i, a.W, a.align, xlo, xhi);
+    // shrink the column range to the taps that really touch column i (weights are re-evaluated per row otherwise)
+    while (xlo <= xhi && tap_weight(make_tap1(a.sx, xlo, a.w, a.align), i) == 0.0f) ++xlo;
+    while (xhi >= xlo && tap_weight(make_tap1(a.sx, xhi, a.w, a.align), i) == 0.0f) --xhi;
+    float acc = 0.0f;
+    for (int y = ylo; y <= yhi; ++y) {
+        const float wy = tap_weight(make_tap1(a.sy, y, a.h, a.align), j);
+        if (wy == 0.0f) continue;
+        const float* row = g + (size_t)y * a.W;
+        float racc = 0.0f;
+        for (int x = xlo; x <= xhi; ++x)
+            racc = fmaf(tap_weight(make_tap1(a.sx, x, a.w, a.align), i), __ldg(row + x), racc);
+        acc = fmaf(wy, racc, acc);
+    }
+    gi[p] = acc;
+}
+
+float host_scale(int n_in, int n_out, int align) {
+    if (align) return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f;
+    return (float)n_in / (float)n_out;
+}
+
+int check(const void* const* a, const void* const* b, int nten, long long planes, int h, int w, int H, int W) {
+    if (!a || !b) return RCF_ERR_NULL;
+    if (nten < 1 || nten > 2 || planes < 1 || planes > 65535 || h < 1 || w < 1 || H < 1 || W < 1) return RCF_ERR_SHAPE;
+    if ((long long)h * w > 0x7fffffffLL / 4 || (long long)H * W > 0x7fffffffLL / 4) return RCF_ERR_SHAPE;
+    for (int t = 0; t < nten; ++t) {
+        if (!a[t] || !b[t]) return RCF_ERR_NULL;
+        if ((reinterpret_cast<uintptr_t>(a[t]) & 3u) || (reinterpret_cast<uintptr_t>(b[t]) & 3u)) return RCF_ERR_ALIGN;
+    }
+    return RCF_OK;
+}
+
+}  // namespace
+
+extern "C" int rcf_resize_bilinear_forward(const float* const* in, float* const* out, int nten, int planes, int h, int w,
+                                           int H, int W, int align_corners, void* stream) {
+    const int v = check(reinterpret_cast<const void* const*>(in), reinterpret_cast<const void* const*>(out), nten, planes, h, w, H, W);
+    if (v != RCF_OK) return v;
+    ResizeK a{};
+    bool vec = ((long long)H * W) % 4 == 0;
+    for (int t = 0; t < nten; ++t) {
+        a.src[t] = in[t]; a.dst[t] = out[t];
+        if (reinterpret_cast<uintptr_t>(out[t]) & 15u) vec = false;
+    }
+    a.h = h; a.w = w; a.H = H; a.W = W; a.align = align_corners ? 1 : 0;
+    a.sy = host_scale(h, H, a.align); a.sx = host_scale(w, W, a.align);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int P = H * W;
+    if (vec) k_resize_fwd<4><<<dim3((P / 4 + 255) / 256, planes, nten), 256, 0, s>>>(a);
+    else k_resize_fwd<1><<<dim3((P + 255) / 256, planes, nten), 256, 0, s>>>(a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int rcf_resize_bilinear_backward(const float* const* grad_out, float* const* grad_in, int nten, int planes, int h,
+                                            int w, int H, int W, int align_corners, void* stream) {
+    const int v = check(reinterpret_cast<const void* const*>(grad_out), reinterpret_cast<const void* const*>(grad_in), nten, planes, h, w, H, W);
+    if (v != RCF_OK) return v;
+    ResizeK a{};
+    for (int t = 0; t < nten; ++t) { a.src[t] = grad_out[t]; a.dst[t] = grad_in[t]; }
+    a.h = h; a.w = w; a.H = H; a.W = W; a.align = align_corners ? 1 : 0;
+    a.sy = host_scale(h, H, a.align); a.sx = host_scale(w, W, a.align);
+    k_resize_bwd<<<dim3((h * w + 255) / 256, planes, nten), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return (int)cudaGetLastError();
+}

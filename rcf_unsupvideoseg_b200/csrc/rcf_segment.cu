@@ -90,13 +90,17 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_finalize(const RcfK a, int GM) {
 }
 
 __global__ void k_loss_sum(const RcfK a, int GM) {
-    // one warp per direction; lanes stride over the batch, fp64 butterfly
+    // one warp per direction; lanes stride over the batch, fp64 butterfly; loss[ndir] = fp32 sum of the directions (:397)
     const int dir = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (dir >= a.ndir) return;
-    double v = 0.0;
-    for (int b = lane; b < a.B; b += 32) v += a.gm[(size_t)(dir * a.B + b) * GM];
-    v = warp_sum_d(v);
-    if (lane == 0) a.loss[dir] = (float)(v * (double)a.inv_n);
+    __shared__ float ldir[2];
+    if (dir < a.ndir) {
+        double v = 0.0;
+        for (int b = lane; b < a.B; b += 32) v += a.gm[(size_t)(dir * a.B + b) * GM];
+        v = warp_sum_d(v);
+        if (lane == 0) { ldir[dir] = (float)(v * (double)a.inv_n); a.loss[dir] = ldir[dir]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) a.loss[a.ndir] = a.ndir == 2 ? ldir[0] + ldir[1] : ldir[0];
 }
 
 template <int D>
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
     const int fd = blockIdx.x, K = a.K, Cf = a.Cf, tid = threadIdx.x;
     const int dir = fd / a.B, b = fd - dir * a.B;
     const int GM = rcf_gm(K, D);
-    const double gs = -(double)a.grad_loss[dir] * (double)a.inv_n;
+    const double gs = -(double)a.grad_loss[a.grad_total ? 0 : dir] * (double)a.inv_n;
     const double* gm = a.gm + (size_t)fd * GM;
     const double* sd = a.segd + (size_t)fd * K * SEGD;
     if (tid == 0) a.gscale[fd] = (float)gs;

@@ -110,8 +110,11 @@ class RcfMotionLossFn(torch.autograd.Function):
       flows  tuple of ndir  [B, 2, H, W]  (no grad; the clamp is applied inside the kernels)
       resids tuple of ndir  [B, 2K, H, W] (grad)
       thetas tuple of ndir  [B, 2, K]     (grad)                            when spec.Cf == 0
-    Returns loss [ndir] and, when spec.want_vis, the un-differentiable tensors
-    (gt, pred, agg, res[, aff]) each [B, 2*ndir, H, W].
+    Returns loss [ndir], total (0-dim, = sum of the directions, reference :397) and, when spec.want_vis, the
+    un-differentiable tensors (gt, pred, agg, res[, aff]) each [B, 2*ndir, H, W].  `loss` and `total` are two views of
+    one (ndir+1)-float buffer the library fills: differentiating `total` (what the reference's caller does,
+    rcf_model.py:464-470) hands its 0-dim gradient straight to the library, with no select/add/fill kernels of
+    autograd in between.
     """
 
     @staticmethod
@@ -176,7 +179,7 @@ class RcfMotionLossFn(torch.autograd.Function):
         ctx_bytes, ws_bytes = _sizes(lib, desc, spec, B, ndir)
         ctx_buf = torch.empty(ctx_bytes, dtype=torch.uint8, device=dev)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        loss = torch.empty(ndir, dtype=torch.float32, device=dev)
+        loss_buf = torch.empty(ndir + 1, dtype=torch.float32, device=dev)
 
         vis_tensors: Tuple[torch.Tensor, ...] = ()
         vis_struct = None
@@ -192,7 +195,7 @@ class RcfMotionLossFn(torch.autograd.Function):
 
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
-            _lib.check(lib.rcf_forward(C.byref(desc), C.byref(inp), loss.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
+            _lib.check(lib.rcf_forward(C.byref(desc), C.byref(inp), loss_buf.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
                                        C.byref(vis_struct) if vis_struct is not None else None, stream), "rcf_forward")
 
         ctx.spec, ctx.ndir, ctx.B, ctx.nhwc = spec, ndir, B, nhwc
@@ -202,13 +205,17 @@ class RcfMotionLossFn(torch.autograd.Function):
                               *([feat_v] if feat_v is not None else []), *[t for t in thetas_v if t is not None],
                               *([w1c, b1c, w2c, b2c] if spec.Cf > 0 else []), *([fb] if fb is not None else []))
         ctx.mark_non_differentiable(*vis_tensors)
-        return (loss, *vis_tensors)
+        ctx.set_materialize_grads(False)     # no zero-filled gradients for the visualisation outputs / unused loss views
+        return (loss_buf[:ndir], loss_buf[ndir], *vis_tensors)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, grad_loss, *grad_vis):
+    def backward(ctx, grad_loss, grad_total, *grad_vis):
         lib = _lib.load_library()
         spec, ndir, B = ctx.spec, ctx.ndir, ctx.B
+        n_in = 8 + 3 * ndir
+        if grad_loss is None and grad_total is None:
+            return (None,) * n_in
         K, H, W, Cf = spec.K, spec.H, spec.W, spec.Cf
         saved = list(ctx.saved_tensors)
         masks_v, ctx_buf = saved[0], saved[1]
@@ -279,7 +286,14 @@ class RcfMotionLossFn(torch.autograd.Function):
 
         _, ws_bytes = _sizes(lib, desc, spec, B, ndir)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        gl = grad_loss.detach().to(torch.float32).contiguous()
+        if grad_loss is None:            # only the total was differentiated: its 0-dim gradient serves every direction
+            gl = grad_total.detach().to(torch.float32).contiguous()
+            desc.grad_loss_total = 1
+        else:
+            gl = grad_loss.detach().to(torch.float32)
+            if grad_total is not None:
+                gl = gl + grad_total.detach().to(torch.float32)
+            gl = gl.contiguous()
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             _lib.check(lib.rcf_backward(C.byref(desc), C.byref(inp), gl.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
@@ -290,10 +304,10 @@ class RcfMotionLossFn(torch.autograd.Function):
 def rcf_motion_loss(spec: LossSpec, masks: torch.Tensor, flows: Sequence[torch.Tensor],
                     resids: Sequence[torch.Tensor], *, feats: Optional[Sequence[torch.Tensor]] = None,
                     mlp: Optional[Sequence[torch.Tensor]] = None, thetas: Optional[Sequence[torch.Tensor]] = None,
-                    feat_bias: Optional[torch.Tensor] = None):
+                    feat_bias: Optional[torch.Tensor] = None, with_total: bool = False):
     """Functional entry point.  masks [B,ndir,K,H,W]; flows/resids (and feats or thetas) per direction.
 
-    Returns (loss [ndir], vis tuple).  Exactly one of (feats + mlp weights) or thetas must be given,
+    Returns (loss [ndir], vis tuple); with `with_total=True`, (loss [ndir], total 0-dim, vis tuple).  Exactly one of (feats + mlp weights) or thetas must be given,
     consistently with spec.Cf.  `feats` is either the direction-major 5-D tensor [ndir,B,Cf,H,W] (preferred:
     one conv call over the concatenated directions, no copies) or a sequence of per-direction [B,Cf,H,W] tensors
     (stacked here, which costs a copy).  `feat_bias` [Cf] (channels-last feats only) is the bias of the conv that produced
@@ -311,4 +325,6 @@ def rcf_motion_loss(spec: LossSpec, masks: torch.Tensor, flows: Sequence[torch.T
         w1 = b1 = w2 = b2 = None
         per_dir = (*flows, *resids, *thetas)
     out = RcfMotionLossFn.apply(spec, masks, feat, feat_bias if feat is not None else None, w1, b1, w2, b2, *per_dir)
-    return out[0], tuple(out[1:])
+    if with_total:
+        return out[0], out[1], tuple(out[2:])
+    return out[0], tuple(out[2:])

@@ -29,7 +29,7 @@ class _LossOnly(nn.Module):
             _, fl = self.head(self._imgs, masks, gt_fw, gt_bw, res_fw, res_bw)
         finally:
             self.head.return_flows = prev
-        return torch.stack([fl["seg_fw"], fl["seg_bw"]])
+        return fl["seg_fw"], fl["seg_bw"], fl["seg"]
 
 
 def make_graphed_head(head, sample_inputs, num_warmup_iters: int = 3):
@@ -41,7 +41,7 @@ def make_graphed_head(head, sample_inputs, num_warmup_iters: int = 3):
     graphed = torch.cuda.make_graphed_callables(mod, samples, num_warmup_iters=num_warmup_iters)
 
     def call(masks, gt_fw, gt_bw, res_fw, res_bw):
-        l2 = graphed(masks, gt_fw, gt_bw, res_fw, res_bw)
-        return {"seg_fw": l2[0], "seg_bw": l2[1], "seg": l2[0] + l2[1]}
+        seg_fw, seg_bw, seg = graphed(masks, gt_fw, gt_bw, res_fw, res_bw)
+        return {"seg_fw": seg_fw, "seg_bw": seg_bw, "seg": seg}
 
     return call

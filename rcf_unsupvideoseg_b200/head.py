@@ -30,6 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .function import LossSpec, rcf_motion_loss
+from .resize import resize_bilinear_multi
 from .stem import flow_stem, stem_supported
 
 logger = logging.getLogger("main")
@@ -231,9 +232,20 @@ class FlowAggregationHeadWithResidual(nn.Module):
         else:
             k_flow = c_flow = self.norm_and_clamp_flow(flow)
             fused = False
-        if self.allow_residual_resize and tuple(resid.shape[-2:]) != self.mask_size:   # :271-273, :294-296
-            resid = F.interpolate(resid, self.mask_size, mode='bilinear')
         return k_flow, c_flow, fused, resid
+
+    def _resize_residuals(self, resids):
+        """:271-273, :294-296 -- F.interpolate(resid, mask_size, mode='bilinear'); both directions in one launch."""
+        if not self.allow_residual_resize:
+            return list(resids)
+        todo = [i for i, r in enumerate(resids) if tuple(r.shape[-2:]) != self.mask_size]
+        out = list(resids)
+        if len(todo) == 2 and resids[0].shape == resids[1].shape:
+            out[todo[0]], out[todo[1]] = resize_bilinear_multi([resids[0], resids[1]], self.mask_size)
+        else:
+            for i in todo:
+                out[i] = resize_bilinear_multi([resids[i]], self.mask_size)[0]
+        return out
 
     def _mlp_params(self):
         l0, l2 = self.flow_feat_after_agg[0], self.flow_feat_after_agg[2]
@@ -249,6 +261,7 @@ class FlowAggregationHeadWithResidual(nn.Module):
             masks5 = masks5.float()
             k_flows, c_flows, rs = [], [], []
             fused = True
+            resids = self._resize_residuals([r.float() for r in resids])
             for flow, resid in zip(flows, resids):
                 kf, cf_, fused_i, r = self._prepare(flow.float(), resid.float(), H, W)
                 fused = fused and fused_i
@@ -263,8 +276,9 @@ class FlowAggregationHeadWithResidual(nn.Module):
                 f"{feat.shape[2:]} != {masks5.shape[3:]} (should match on spatial dimension)"   # :247-248
             feat = feat.view(ndir, B, *feat.shape[1:])
             spec = self._spec(K, H, W, want_vis=want_vis, vis_norm=vis_norm, inv_n=inv_n, clamp_fused=fused)
-            loss, vis = rcf_motion_loss(spec, masks5, k_flows, rs, feats=feat, mlp=self._mlp_params(), feat_bias=feat_bias)
-        return loss, vis
+            loss, total, vis = rcf_motion_loss(spec, masks5, k_flows, rs, feats=feat, mlp=self._mlp_params(),
+                                               feat_bias=feat_bias, with_total=True)
+        return loss, total, vis
 
     # ------------------------------------------------------------------------------------------
     def get_demean_affine_flow(self, mask, flow):
@@ -285,9 +299,7 @@ class FlowAggregationHeadWithResidual(nn.Module):
         self._check_residual_mode()
         B, K, H, W = mask.shape
         flow = flow.float()
-        resid = all_pred_residual.float()
-        if self.allow_residual_resize and tuple(resid.shape[-2:]) != self.mask_size:
-            resid = F.interpolate(resid, self.mask_size, mode='bilinear')
+        resid = self._resize_residuals([all_pred_residual.float()])[0]
         with torch.no_grad(), torch.autocast(device_type="cuda", enabled=False):
             feat, feat_bias = self._features_preact(None, stem_flows=[flow], stem_clamp=None)
             assert feat.shape[2:] == mask.shape[2:], f"{feat.shape[2:]} != {mask.shape[2:]} (should match on spatial dimension)"
@@ -306,8 +318,8 @@ class FlowAggregationHeadWithResidual(nn.Module):
 
         gt_fw_flow = gt_fw_flows[:, 0, ...]
         gt_bw_flow = gt_bw_flows[:, 0, ...]
-        loss, vis = self._run(masks, [gt_fw_flow, gt_bw_flow], [all_pred_residual_fw, all_pred_residual_bw],
-                              want_vis=self.return_flows, vis_norm=True, inv_n=float(self.loss_inv_n))
+        loss, total, vis = self._run(masks, [gt_fw_flow, gt_bw_flow], [all_pred_residual_fw, all_pred_residual_bw],
+                                     want_vis=self.return_flows, vis_norm=True, inv_n=float(self.loss_inv_n))
         flow_loss['seg_fw'] = loss[0]
         flow_loss['seg_bw'] = loss[1]
         if self.return_flows:
@@ -317,5 +329,5 @@ class FlowAggregationHeadWithResidual(nn.Module):
             flows['residual_adj'].append(vis[3])
             if len(vis) > 4:
                 flows['affine_flow'].append(vis[4])
-        flow_loss['seg'] = flow_loss['seg_fw'] + flow_loss['seg_bw']
+        flow_loss['seg'] = total      # = seg_fw + seg_bw (:397), summed in fp32 by the library
         return flows, flow_loss
