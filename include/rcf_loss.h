@@ -179,12 +179,17 @@ RCF_API int rcf_corresponding_map(const float* coords, float* out, void* scratch
  * ks in {1,3,5}; Cf % 4 == 0, Cf <= 128, 256 % (Cf/4) == 0, else RCF_ERR_UNSUPPORTED (use the framework's conv).
  * clamp_t < 0: no clamp.  No gradient w.r.t. the flow is produced (the RAFT flow carries none). */
 RCF_API int rcf_stem_forward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W, int Cf,
-                             int ks, const float* w, const float* b, float clamp_t, float slope, float* act, void* stream);
+                             int ks, const float* w, const float* b, float clamp_t, float slope, float* act,
+                             uint32_t* sign, void* stream);
 RCF_API int rcf_stem_workspace_bytes(int ndir, int B, int H, int W, int Cf, int ks, size_t* bytes);
-/* dw [Cf,2,ks,ks], db [Cf] from dact (gradient w.r.t. act) and the forward output act; ws from rcf_stem_workspace_bytes. */
+/* dw [Cf,2,ks,ks], db [Cf] from dact (gradient w.r.t. act) and EITHER the forward output act OR the sign bits the forward
+ * wrote; ws from rcf_stem_workspace_bytes.
+ * sign (optional, Cf == 64 only): [ndir*B, H, W, Cf/32] 32-bit words, bit f%32 of word f/32 set <=> the pre-activation of
+ * channel f is <= 0.  With Cf == 64 both passes run on tensor cores (mma.sync TF32, 3xTF32 split = fp32-grade accuracy)
+ * and the backward reads these 8 B/px instead of the 256 B/px activation map. */
 RCF_API int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W, int Cf,
-                              int ks, float clamp_t, float slope, const float* act, const float* dact, float* dw, float* db,
-                              void* ws, void* stream);
+                              int ks, float clamp_t, float slope, const float* act, const uint32_t* sign, const float* dact,
+                              float* dw, float* db, void* ws, void* stream);
 
 /* ---- input staging: bilinear resize of dense NCHW fp32 planes ------------------------------------
  * Replaces F.interpolate(all_pred_residual, mask_size, mode='bilinear') of the head (reference :271-273, :294-296;

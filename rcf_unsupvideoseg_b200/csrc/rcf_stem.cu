@@ -21,7 +21,9 @@ struct StemK {
     const float* w;      // [Cf][2][KS][KS]
     const float* b;      // [Cf]
     float* act;          // [N][P][Cf]
-    const float* act_in; // backward: forward output (sign of the pre-activation)
+    const float* act_in; // backward: forward output (sign of the pre-activation) -- CUDA-core path
+    uint32_t* sign_out;  // tensor-core path: [N][P][Cf/32] bit f%32 of word f/32 set <=> pre-activation of channel f is <= 0
+    const uint32_t* sign_in;
     const float* dact;   // [N][P][Cf]
     float* part;         // [gridDim.x][Cf*(NT+1)]
     int ntiles;          // N * tiles per image
@@ -170,6 +172,294 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_stem_bwd(const StemK a) {
     }
 }
 
+
+// ================================================================================================================
+// Tensor-core path for Cf == 64 (the reference default, configs/*/rcf_stage*.yaml never change it).
+// The CUDA-core kernels above are issue-bound: 72 FFMA + 18 LDS per thread per pixel (measured 225 us forward / 340 us
+// backward at 2x2x480x854 against HBM floors of 65 / 130 us).  Both passes are small GEMMs over the pixel axis,
+//     forward   act[p, f]  = sum_t tap[p, t] * w[t, f]          [P x 19] . [19 x 64]   (tap 18 == 1: the bias)
+//     backward  dw [f, t]  = sum_p dpre[p, f] * tap[p, t]       [64 x P] . [P x 19]    (tap 18 == 1: the bias gradient)
+// so they run on mma.sync.m16n8k8 TF32 with the 3xTF32 split (hi*hi + hi*lo + lo*hi, fp32 accumulate: ~2^-21 relative,
+// i.e. fp32-grade -- plain TF32 would break the 1e-4 parity bar).  That is 36 MMA per 16 pixels x 32 channels instead of
+// 576 FFMA.  This is NOT a tcgen05 shape: K is 19 and the kernels are HBM-bound once the issue pressure is gone.
+// Rows / columns of the MMA tiles are PERMUTED channel indices so that every lane owns 8 consecutive channels of a
+// pixel: 128-bit global loads / stores in the native channels-last layout, no shuffles, no shared-memory transpose.
+// The forward also emits one bit per (pixel, channel) -- the sign of the pre-activation -- and the backward reads those
+// 8 B/px instead of re-reading the 256 B/px activation map.
+// ================================================================================================================
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// d += a * b with a, b given as (hi, lo) TF32 pairs; small terms first
+__device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+    mma_tf32(d, al, bh[0], bh[1]);
+    mma_tf32(d, ah, bl[0], bl[1]);
+    mma_tf32(d, ah, bh[0], bh[1]);
+}
+
+// cheap split for values produced in registers: hi = truncation (1 LOP3), lo = x - hi (exact), lo rounded to TF32 by
+// adding half an ulp to its bit pattern (the MMA ignores the low 13 bits).  |x - hi - lo'| <= 2^-21 |x|.
+__device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) + 0x1000u;
+}
+
+// Shared-memory word of tap `ti` relative to a pixel's tile position: (offset, multiplier of the pixel offset).
+// ti < NT: the conv tap; ti == NT: a constant 1 (bias column); above: a constant 0 (padding of the K / N dimension).
+template <int KS>
+__device__ __forceinline__ void tap_addr(int ti, int& off, int& mul) {
+    constexpr int NT = 2 * KS * KS, SW = STEM_TW + KS - 1, SH = STEM_TH + KS - 1;
+    if (ti < NT) {
+        const int c = ti / (KS * KS), r = ti - c * KS * KS, dy = r / KS, dx = r - dy * KS;
+        off = (c * SH + dy) * SW + dx; mul = 1;
+    } else {
+        off = 2 * SH * SW + (ti == NT ? 0 : 1); mul = 0;
+    }
+}
+
+constexpr int STEM_MMA_CF = 64;
+
+// The clamped flow tile (+halo, zero outside the frame) is kept in shared memory already split into TF32 (hi, lo)
+// words, so the MMA operands that come from it cost two LDS and no ALU work.  The loads of the NEXT tile are issued
+// before the current tile is computed and committed to shared memory afterwards (software pipeline: the HBM latency of
+// this read-once input is hidden behind the MMAs instead of being paid at a barrier).
+template <int KS>
+struct StemTile {
+    static constexpr int SW = STEM_TW + KS - 1, SH = STEM_TH + KS - 1, TSZ = 2 * SH * SW, R = (KS - 1) / 2;
+    static constexpr int NE = (TSZ + RCF_BLOCK - 1) / RCF_BLOCK;
+    float pre[NE];
+    __device__ __forceinline__ void fetch(const StemK& a, int tl, int tx, int ty) {
+        const int n = tl / (tx * ty), r = tl - n * tx * ty;
+        const int y0 = (r / tx) * STEM_TH, x0 = (r - (r / tx) * tx) * STEM_TW;
+        const int dir = n / a.B, b = n - dir * a.B;
+        const float* __restrict__ fl = (dir ? a.flow[1] : a.flow[0]) + (long long)b * (dir ? a.flow_bs[1] : a.flow_bs[0]);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int i = threadIdx.x + e * RCF_BLOCK;
+            const int c = i / (SH * SW), q = i - c * SH * SW;
+            const int ly = q / SW, lx = q - ly * SW;
+            const int y = y0 + ly - R, x = x0 + lx - R;
+            float v = 0.0f;
+            if (i < TSZ && y >= 0 && y < a.H && x >= 0 && x < a.W) v = __ldg(fl + (long long)c * a.P + (long long)y * a.W + x);
+            pre[e] = v;
+        }
+    }
+    __device__ __forceinline__ void commit(const StemK& a, uint32_t* Thi, uint32_t* Tlo) const {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int i = threadIdx.x + e * RCF_BLOCK;
+            if (i < TSZ) split_tf32(clamp_flow(pre[e], a.clamp_t), Thi[i], Tlo[i]);
+        }
+    }
+};
+
+// Forward.  CTA = 8 warps on a 32x8 tile = 16 M-tiles of 16 pixels (half a tile row); warp w computes channels
+// [32*(w&1), +32) of M-tiles (w>>1) + 4i.  Column c of N-tile j is channel 32*half + 16*(j>>1) + 4*(c>>1) + 2*(j&1) + (c&1):
+// lane (g = lane/4, t = lane%4) ends up with channels 4t..4t+3 (N-tiles 0,1) and 16+4t..16+4t+3 (N-tiles 2,3) of the
+// pixels g and g+8, so each 128-bit store instruction of the warp writes 64 contiguous bytes per pixel (full sectors).
+template <int KS>
+__global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(const StemK a) {
+    using TL = StemTile<KS>;
+    constexpr int NT = 2 * KS * KS, NKS = (NT + 1 + 7) / 8, SW = TL::SW, TSZ = TL::TSZ;
+    constexpr int Cf = STEM_MMA_CF;
+    __shared__ uint32_t Thi[TSZ + 2], Tlo[TSZ + 2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int half = warp & 1, mset = warp >> 1;
+    const int tx = (a.W + STEM_TW - 1) / STEM_TW, ty = (a.H + STEM_TH - 1) / STEM_TH;
+
+    uint32_t bh[4][NKS][2], bl[4][NKS][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = half * 32 + (j >> 1) * 16 + (g >> 1) * 4 + 2 * (j & 1) + (g & 1);
+#pragma unroll
+        for (int s = 0; s < NKS; ++s)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 8 * s + t + 4 * e;
+                const float wv = k < NT ? __ldg(a.w + (size_t)ch * NT + k) : (k == NT ? __ldg(a.b + ch) : 0.0f);
+                split_tf32(wv, bh[j][s][e], bl[j][s][e]);
+            }
+    }
+    int offA[NKS][2], mulA[NKS][2];
+#pragma unroll
+    for (int s = 0; s < NKS; ++s)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) tap_addr<KS>(8 * s + t + 4 * e, offA[s][e], mulA[s][e]);
+    if (tid == 0) { Thi[TSZ] = __float_as_uint(1.0f); Tlo[TSZ] = 0u; Thi[TSZ + 1] = 0u; Tlo[TSZ + 1] = 0u; }
+
+    TL st;
+    int tl = blockIdx.x;
+    if (tl < a.ntiles) st.fetch(a, tl, tx, ty);
+    for (; tl < a.ntiles; tl += gridDim.x) {
+        const int n = tl / (tx * ty), r = tl - n * tx * ty;
+        const int y0 = (r / tx) * STEM_TH, x0 = (r - (r / tx) * tx) * STEM_TW;
+        __syncthreads();                               // previous tile fully consumed
+        st.commit(a, Thi, Tlo);
+        __syncthreads();
+        if (tl + (int)gridDim.x < a.ntiles) st.fetch(a, tl + gridDim.x, tx, ty);     // in flight while this tile is computed
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            const int mt = mset + 4 * i, ly = mt >> 1, lx0 = (mt & 1) * 16;
+            const int y = y0 + ly;
+            if (y >= a.H || x0 + lx0 >= a.W) continue;          // warp-uniform
+            const int pix0 = ly * SW + lx0 + g, pix1 = pix0 + 8;
+            float c[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) c[j][q] = 0.0f;
+#pragma unroll
+            for (int s = 0; s < NKS; ++s) {
+                const int i0 = offA[s][0] + pix0 * mulA[s][0], i1 = offA[s][0] + pix1 * mulA[s][0];
+                const int i2 = offA[s][1] + pix0 * mulA[s][1], i3 = offA[s][1] + pix1 * mulA[s][1];
+                const uint32_t ah[4] = {Thi[i0], Thi[i1], Thi[i2], Thi[i3]};
+                const uint32_t al[4] = {Tlo[i0], Tlo[i1], Tlo[i2], Tlo[i3]};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_3xtf32(c[j], ah, al, bh[j][s], bl[j][s]);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                        // row g (h = 0) and row g + 8 (h = 1) of the M-tile
+                const int x = x0 + lx0 + g + 8 * h;
+                float o[8];
+                uint32_t bits = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float v = c[j][2 * h + e];
+                        const bool pos = v > 0.0f;
+                        o[2 * j + e] = pos ? v : a.slope * v;        // o[0..3]: channels 4t..4t+3, o[4..7]: 16+4t..16+4t+3
+                        bits |= (pos ? 0u : 1u) << (2 * j + e);
+                    }
+                uint32_t word = ((bits & 15u) << (4 * t)) | ((bits >> 4) << (16 + 4 * t));
+                word |= __shfl_xor_sync(0xffffffffu, word, 1);
+                word |= __shfl_xor_sync(0xffffffffu, word, 2);
+                if (x < a.W) {
+                    const long long px = (long long)n * a.P + (long long)y * a.W + x;
+                    float* dst = a.act + px * Cf + half * 32 + 4 * t;
+                    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(dst + 16) = make_float4(o[4], o[5], o[6], o[7]);
+                    if (t == 0 && a.sign_out) a.sign_out[px * 2 + half] = word;
+                }
+            }
+        }
+    }
+}
+
+// Backward.  M = channels, N = taps (+ the ones column that yields the bias gradient), K = pixels.  A tile has 32
+// groups of 8 consecutive pixels; warp w accumulates channels [32*(w&1), +32) over the groups (w>>1) + 4i.  Row
+// r = g + 8h of M-tile m is channel 32*half + 4g + 2m + h: a lane needs channels 4g..4g+3 of the pixels t and t+4 of the
+// group = one 128-bit load each, and the 8 lanes of a pixel read 128 contiguous bytes.
+template <int KS>
+__global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_bwd_mma(const StemK a) {
+    using TL = StemTile<KS>;
+    constexpr int NT = 2 * KS * KS, NO = NT + 1, NJ = (NO + 7) / 8, NOP = NJ * 8, SW = TL::SW, TSZ = TL::TSZ;
+    constexpr int Cf = STEM_MMA_CF;
+    __shared__ uint32_t Thi[TSZ + 2], Tlo[TSZ + 2];
+    extern __shared__ float red[];                   // [RCF_WARPS][32 * NOP]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int half = warp & 1, gset = warp >> 1;
+    const int tx = (a.W + STEM_TW - 1) / STEM_TW, ty = (a.H + STEM_TH - 1) / STEM_TH;
+
+    float acc[2][NJ][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.0f;
+    int offB[NJ], mulB[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) tap_addr<KS>(8 * j + g, offB[j], mulB[j]);
+    if (tid == 0) { Thi[TSZ] = __float_as_uint(1.0f); Tlo[TSZ] = 0u; Thi[TSZ + 1] = 0u; Tlo[TSZ + 1] = 0u; }
+
+    TL st;
+    int tl = blockIdx.x;
+    if (tl < a.ntiles) st.fetch(a, tl, tx, ty);
+    for (; tl < a.ntiles; tl += gridDim.x) {      // fixed tile -> CTA assignment (reproducible)
+        const int n = tl / (tx * ty), r = tl - n * tx * ty;
+        const int y0 = (r / tx) * STEM_TH, x0 = (r - (r / tx) * tx) * STEM_TW;
+        __syncthreads();
+        st.commit(a, Thi, Tlo);
+        __syncthreads();
+        if (tl + (int)gridDim.x < a.ntiles) st.fetch(a, tl + gridDim.x, tx, ty);
+#pragma unroll 4
+        for (int i = 0; i < 8; ++i) {
+            const int q = gset + 4 * i, ly = q >> 2, lx0 = (q & 3) * 8;
+            const int y = y0 + ly;
+            if (y >= a.H || x0 + lx0 >= a.W) continue;          // warp-uniform
+            const int xA = x0 + lx0 + t;
+            const long long pxA = (long long)n * a.P + (long long)y * a.W + xA;
+            float v[2][4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const bool in = xA + 4 * e < a.W;
+                float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t sg = 0u;
+                if (in) {
+                    d4 = __ldg(reinterpret_cast<const float4*>(a.dact + (pxA + 4 * e) * Cf + half * 32 + 4 * g));
+                    sg = __ldg(a.sign_in + (pxA + 4 * e) * 2 + half) >> (4 * g);
+                }
+                v[e][0] = (sg & 1u) ? d4.x * a.slope : d4.x;
+                v[e][1] = (sg & 2u) ? d4.y * a.slope : d4.y;
+                v[e][2] = (sg & 4u) ? d4.z * a.slope : d4.z;
+                v[e][3] = (sg & 8u) ? d4.w * a.slope : d4.w;
+            }
+            const int pA = ly * SW + lx0 + t;
+            uint32_t bh[NJ][2], bl[NJ][2];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int i0 = offB[j] + pA * mulB[j], i1 = offB[j] + (pA + 4) * mulB[j];
+                bh[j][0] = Thi[i0]; bl[j][0] = Tlo[i0];
+                bh[j][1] = Thi[i1]; bl[j][1] = Tlo[i1];
+            }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                uint32_t ah[4], al[4];
+                split_tf32_fast(v[0][2 * m], ah[0], al[0]);
+                split_tf32_fast(v[0][2 * m + 1], ah[1], al[1]);
+                split_tf32_fast(v[1][2 * m], ah[2], al[2]);
+                split_tf32_fast(v[1][2 * m + 1], ah[3], al[3]);
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) mma_3xtf32(acc[m][j], ah, al, bh[j], bl[j]);
+            }
+        }
+    }
+    // combine the warps of each channel half in warp order through shared memory; part[cta][f * NO + tap]
+    float* mine = red + (size_t)warp * 32 * NOP;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int fl = 4 * g + 2 * m + h;                 // channel within the half
+                mine[fl * NOP + 8 * j + 2 * t] = acc[m][j][2 * h];
+                mine[fl * NOP + 8 * j + 2 * t + 1] = acc[m][j][2 * h + 1];
+            }
+    __syncthreads();
+    for (int o = tid; o < Cf * NO; o += RCF_BLOCK) {
+        const int f = o / NO, tp = o - f * NO;
+        const int hf = f >> 5, fl = f & 31;
+        float s = 0.0f;
+#pragma unroll
+        for (int wi = 0; wi < RCF_WARPS / 2; ++wi) s += red[(size_t)(2 * wi + hf) * 32 * NOP + fl * NOP + tp];
+        a.part[(size_t)blockIdx.x * Cf * NO + o] = s;
+    }
+}
+
 __global__ void __launch_bounds__(256) k_stem_bwd_final(const float* __restrict__ part, int nparts, int Cf, int NT,
                                                         float* __restrict__ dw, float* __restrict__ db) {
     const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;   // warp per output f*(NT+1)+t
@@ -217,16 +507,27 @@ extern "C" int rcf_stem_workspace_bytes(int ndir, int B, int H, int W, int Cf, i
 
 extern "C" int rcf_stem_forward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W,
                                 int Cf, int ks, const float* w, const float* b, float clamp_t, float slope, float* act,
-                                void* stream) {
+                                uint32_t* sign, void* stream) {
     const int v = stem_check(ndir, B, H, W, Cf, ks);
     if (v != RCF_OK) return v;
     if (!flow || !flow_bstride || !flow[0] || (ndir > 1 && !flow[1]) || !w || !b || !act) return RCF_ERR_NULL;
     if (reinterpret_cast<uintptr_t>(act) & 15u) return RCF_ERR_ALIGN;
+    if (sign && Cf != STEM_MMA_CF) return RCF_ERR_UNSUPPORTED;
     StemK a{};
     fill(a, flow, flow_bstride, ndir, B, H, W, Cf, clamp_t, slope);
-    a.w = w; a.b = b; a.act = act;
-    dim3 grid((W + STEM_TW - 1) / STEM_TW, (H + STEM_TH - 1) / STEM_TH, ndir * B);
+    a.w = w; a.b = b; a.act = act; a.sign_out = sign;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (Cf == STEM_MMA_CF) {            // tensor-core path, persistent CTAs (weights split once per CTA)
+        const int g = stem_grid_bwd(a.ntiles);
+        switch (ks) {
+            case 1: k_stem_fwd_mma<1><<<g, RCF_BLOCK, 0, s>>>(a); break;
+            case 3: k_stem_fwd_mma<3><<<g, RCF_BLOCK, 0, s>>>(a); break;
+            case 5: k_stem_fwd_mma<5><<<g, RCF_BLOCK, 0, s>>>(a); break;
+        }
+        RCF_CUDA(cudaGetLastError());
+        return RCF_OK;
+    }
+    dim3 grid((W + STEM_TW - 1) / STEM_TW, (H + STEM_TH - 1) / STEM_TH, ndir * B);
     switch (ks) {
         case 1: k_stem_fwd<1><<<grid, RCF_BLOCK, 0, s>>>(a); break;
         case 3: k_stem_fwd<3><<<grid, RCF_BLOCK, 0, s>>>(a); break;
@@ -236,37 +537,58 @@ extern "C" int rcf_stem_forward(const float* const* flow, const int64_t* flow_bs
     return RCF_OK;
 }
 
+template <int KS>
+static int launch_stem_bwd_mma(const StemK& a, int g, cudaStream_t s) {
+    constexpr int NJ = (2 * KS * KS + 1 + 7) / 8;
+    const size_t smem = (size_t)RCF_WARPS * 32 * NJ * 8 * sizeof(float);
+    RCF_CUDA(cudaFuncSetAttribute(k_stem_bwd_mma<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_stem_bwd_mma<KS><<<g, RCF_BLOCK, smem, s>>>(a);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W,
-                                 int Cf, int ks, float clamp_t, float slope, const float* act, const float* dact,
-                                 float* dw, float* db, void* ws, void* stream) {
+                                 int Cf, int ks, float clamp_t, float slope, const float* act, const uint32_t* sign,
+                                 const float* dact, float* dw, float* db, void* ws, void* stream) {
     const int v = stem_check(ndir, B, H, W, Cf, ks);
     if (v != RCF_OK) return v;
-    if (!flow || !flow_bstride || !flow[0] || (ndir > 1 && !flow[1]) || !act || !dact || !dw || !db || !ws) return RCF_ERR_NULL;
+    if (!flow || !flow_bstride || !flow[0] || (ndir > 1 && !flow[1]) || (!act && !sign) || !dact || !dw || !db || !ws)
+        return RCF_ERR_NULL;
     if ((reinterpret_cast<uintptr_t>(act) | reinterpret_cast<uintptr_t>(dact)) & 15u) return RCF_ERR_ALIGN;
+    if (sign && Cf != STEM_MMA_CF) return RCF_ERR_UNSUPPORTED;
     StemK a{};
     fill(a, flow, flow_bstride, ndir, B, H, W, Cf, clamp_t, slope);
-    a.act_in = act; a.dact = dact; a.part = static_cast<float*>(ws);
+    a.act_in = act; a.sign_in = sign; a.dact = dact; a.part = static_cast<float*>(ws);
     const int g = stem_grid_bwd(a.ntiles);
     const int NT = 2 * ks * ks;
-    const size_t smem = (size_t)RCF_WARPS * Cf * (NT + 1) * sizeof(float);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (smem > 220 * 1024) return RCF_ERR_UNSUPPORTED;
-    const bool big = smem > 40 * 1024;       // (plus the static tile) needs the opt-in shared-memory limit
-    switch (ks) {
-        case 1:
-            if (big) RCF_CUDA(cudaFuncSetAttribute(k_stem_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_stem_bwd<1><<<g, RCF_BLOCK, smem, s>>>(a);
-            break;
-        case 3:
-            if (big) RCF_CUDA(cudaFuncSetAttribute(k_stem_bwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_stem_bwd<3><<<g, RCF_BLOCK, smem, s>>>(a);
-            break;
-        case 5:
-            if (big) RCF_CUDA(cudaFuncSetAttribute(k_stem_bwd<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_stem_bwd<5><<<g, RCF_BLOCK, smem, s>>>(a);
-            break;
+    if (sign) {                         // tensor-core path (sign bits written by rcf_stem_forward)
+        int e = RCF_OK;
+        switch (ks) {
+            case 1: e = launch_stem_bwd_mma<1>(a, g, s); break;
+            case 3: e = launch_stem_bwd_mma<3>(a, g, s); break;
+            case 5: e = launch_stem_bwd_mma<5>(a, g, s); break;
+        }
+        if (e != RCF_OK) return e;
+    } else {
+        const size_t smem = (size_t)RCF_WARPS * Cf * (NT + 1) * sizeof(float);
+        if (smem > 220 * 1024) return RCF_ERR_UNSUPPORTED;
+        const bool big = smem > 40 * 1024;       // (plus the static tile) needs the opt-in shared-memory limit
+        switch (ks) {
+            case 1:
+                if (big) RCF_CUDA(cudaFuncSetAttribute(k_stem_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_stem_bwd<1><<<g, RCF_BLOCK, smem, s>>>(a);
+                break;
+            case 3:
+                if (big) RCF_CUDA(cudaFuncSetAttribute(k_stem_bwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_stem_bwd<3><<<g, RCF_BLOCK, smem, s>>>(a);
+                break;
+            case 5:
+                if (big) RCF_CUDA(cudaFuncSetAttribute(k_stem_bwd<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_stem_bwd<5><<<g, RCF_BLOCK, smem, s>>>(a);
+                break;
+        }
+        RCF_CUDA(cudaGetLastError());
     }
-    RCF_CUDA(cudaGetLastError());
     const int nout = Cf * (NT + 1);
     k_stem_bwd_final<<<(nout * 32 + 255) / 256, 256, 0, s>>>(a.part, g, Cf, NT, dw, db);
     RCF_CUDA(cudaGetLastError());

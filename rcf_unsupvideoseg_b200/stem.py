@@ -44,13 +44,17 @@ class _StemFn(torch.autograd.Function):
         w = weight.detach().float().contiguous()
         b = bias.detach().float().contiguous()
         act = torch.empty((ndir * B, Cf, H, W), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        # Cf == 64: tensor-core kernels; the forward leaves one sign bit per (pixel, channel) for the backward (8 B/px)
+        sign = torch.empty(ndir * B * H * W * 2, dtype=torch.int32, device=dev) if Cf == 64 else None
         ptrs = (C.c_void_p * 2)(*[f.data_ptr() for f in fl], *([None] * (2 - ndir)))
         strides = (C.c_int64 * 2)(*[f.stride(0) for f in fl], *([0] * (2 - ndir)))
         with torch.cuda.device(dev):
             _lib.check(lib.rcf_stem_forward(ptrs, strides, ndir, B, H, W, Cf, ks, w.data_ptr(), b.data_ptr(),
                                             float(clamp_t), float(slope), act.data_ptr(),
+                                            sign.data_ptr() if sign is not None else None,
                                             torch.cuda.current_stream(dev).cuda_stream), "rcf_stem_forward")
-        ctx.save_for_backward(act, w, *fl)
+        ctx.has_sign = sign is not None
+        ctx.save_for_backward(sign if sign is not None else act, w, *fl)
         ctx.meta = (ndir, B, H, W, Cf, ks, float(clamp_t), float(slope))
         return act
 
@@ -59,8 +63,8 @@ class _StemFn(torch.autograd.Function):
     def backward(ctx, dact):
         lib = _lib.load_library()
         ndir, B, H, W, Cf, ks, clamp_t, slope = ctx.meta
-        act, w, *fl = ctx.saved_tensors
-        dev = act.device
+        kept, w, *fl = ctx.saved_tensors          # sign bits (Cf == 64) or the activation map
+        dev = kept.device
         g = dact.float().contiguous(memory_format=torch.channels_last)
         nbytes = C.c_size_t()
         _lib.check(lib.rcf_stem_workspace_bytes(ndir, B, H, W, Cf, ks, C.byref(nbytes)), "rcf_stem_workspace_bytes")
@@ -70,8 +74,9 @@ class _StemFn(torch.autograd.Function):
         ptrs = (C.c_void_p * 2)(*[f.data_ptr() for f in fl], *([None] * (2 - ndir)))
         strides = (C.c_int64 * 2)(*[f.stride(0) for f in fl], *([0] * (2 - ndir)))
         with torch.cuda.device(dev):
-            _lib.check(lib.rcf_stem_backward(ptrs, strides, ndir, B, H, W, Cf, ks, clamp_t, slope, act.data_ptr(),
-                                             g.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
+            _lib.check(lib.rcf_stem_backward(ptrs, strides, ndir, B, H, W, Cf, ks, clamp_t, slope,
+                                             None if ctx.has_sign else kept.data_ptr(),
+                                             kept.data_ptr() if ctx.has_sign else None, g.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
                                              torch.cuda.current_stream(dev).cuda_stream), "rcf_stem_backward")
         return (dw, db, None, None, *([None] * ndir))
 

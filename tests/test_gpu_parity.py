@@ -425,7 +425,8 @@ def test_channels_last_feature_path_matches_nchw(rcf, name):
         assert rel_l2(a_.cpu().numpy(), b_.cpu().numpy()) < 2e-4
 
 
-@pytest.mark.parametrize("ks,Cf,H,W", [(3, 64, 19, 23), (1, 16, 8, 12), (5, 8, 14, 9), (3, 128, 6, 6)])
+@pytest.mark.parametrize("ks,Cf,H,W", [(3, 64, 19, 23), (1, 16, 8, 12), (5, 8, 14, 9), (3, 128, 6, 6),
+                                       (3, 64, 70, 101), (1, 64, 9, 40), (5, 64, 33, 47), (3, 64, 96, 96)])
 def test_handwritten_conv_stem_vs_torch(rcf, ks, Cf, H, W):
     """csrc/rcf_stem.cu (clamp + conv + bias + LeakyReLU, and its weight/bias gradients) against ATen in fp64."""
     from rcf_unsupvideoseg_b200.stem import flow_stem
