@@ -201,6 +201,18 @@ RCF_API int rcf_resize_bilinear_forward(const float* const* in, float* const* ou
 RCF_API int rcf_resize_bilinear_backward(const float* const* grad_out, float* const* grad_in, int nten, int planes, int h,
                                          int w, int H, int W, int align_corners, void* stream);
 
+/* ---- caller-side mask preparation (reference models/rcf_model.py:433-434, :376-378) ----------------
+ * logits / masks / grad_masks / dlogits: dense [nframes, K, P] fp32 (the reference's [B, I, K, H, W] with nframes = B*I,
+ * P = H*W).  Forward: masks = softmax over K (:433) and entropy[0] = -(masks * log_softmax(masks)).sum(K).mean() --
+ * including the reference's log-softmax OF the probabilities (:434) -- in one pass; ws from
+ * rcf_mask_prep_workspace_floats.  Backward: dlogits = softmax-backward of (grad_masks + grad_entropy * dEntropy/dmasks)
+ * in one pass; grad_masks (the motion loss's mask gradient) and grad_entropy (device scalar) may each be NULL. */
+RCF_API int rcf_mask_prep_workspace_floats(int nframes, int P, size_t* nfloats);
+RCF_API int rcf_mask_prep_forward(const float* logits, float* masks, float* entropy, float* ws, int nframes, int K, int P,
+                                  void* stream);
+RCF_API int rcf_mask_prep_backward(const float* masks, const float* grad_masks, const float* grad_entropy, float* dlogits,
+                                   int nframes, int K, int P, void* stream);
+
 /* Measurement hook (bench.py): record the two caller-owned cudaEvent_t handles immediately before and
  * after the launch of streaming kernel `which` in the following rcf_forward / rcf_backward calls of this
  * process (on the stream those calls are given).  which: 0 off, 1 k_moments, 2 k_loss, 3 k_bwd,

@@ -444,3 +444,30 @@ def synthetic_inputs(B, K, H, W, seed=0, resid_hw=None, mask_sharpness=1.0, dtyp
     rfw = rng.normal(0.0, 5.0, size=(B, 2 * K, rh, rw))
     rbw = rng.normal(0.0, 5.0, size=(B, 2 * K, rh, rw))
     return tuple(a.astype(dtype) for a in (masks, fw, bw, rfw, rbw))
+
+
+# ----------------------------------------------------------------------------------------------
+# caller-side mask preparation (models/rcf_model.py:433-434, :376-378) -- SURVEY 8f rank 2
+# ----------------------------------------------------------------------------------------------
+def mask_prep_forward(logits):
+    """logits [B,I,K,H,W] -> (masks, entropy): softmax over K (:433), log_softmax OF the masks (:434, as written) and
+    -(masks * log_masks).sum(2).mean() (:376-378)."""
+    x = logits - logits.max(axis=2, keepdims=True)
+    e = np.exp(x)
+    m = e / e.sum(axis=2, keepdims=True)
+    lse = np.log(np.exp(m).sum(axis=2, keepdims=True))
+    ls = m - lse
+    return m, float(-(m * ls).sum(axis=2).mean())
+
+
+def mask_prep_backward(masks, g_masks, g_entropy):
+    """d(loss)/d(logits) given d/d(masks) (or None) and the scalar d/d(entropy) (or None)."""
+    m = masks
+    npix = m.size / m.shape[2]
+    g = np.zeros_like(m) if g_masks is None else g_masks.astype(m.dtype).copy()
+    if g_entropy is not None:
+        lse = np.log(np.exp(m).sum(axis=2, keepdims=True))
+        ls = m - lse
+        q = np.exp(ls)
+        g = g - g_entropy / npix * (ls + m - q * m.sum(axis=2, keepdims=True))
+    return m * (g - (m * g).sum(axis=2, keepdims=True))

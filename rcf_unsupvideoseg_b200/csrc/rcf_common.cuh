@@ -132,6 +132,7 @@ struct RcfK {
     int* sync;     // fused forward: [0] ticket, [1..nfd] pass-1 arrival counters, [1+nfd..] ready flags
     int lag;       // fused forward: pass 2 of frame-direction t is scheduled LAG slots after its pass 1
     int l2_hints;  // pass 2 streams flow/residual with an L2 evict-first policy (keeps the masks resident)
+    int mlp_smem;     // segment kernels stage the MLP weights in shared memory (Cf % 4 == 0 and Cf <= 128)
     int single_pass;  // theta supplied and D == 0: no pass 1; S_k comes out of pass 2 (k_finalize stores it)
     // forward outputs
     float* loss;

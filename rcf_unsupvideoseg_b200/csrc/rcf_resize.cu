@@ -107,6 +107,44 @@ __global__ void __launch_bounds__(256) k_resize_bwd(const ResizeK a) {
     gi[p] = acc;
 }
 
+// Exact 2x upsampling without align_corners (the DAVIS configs: residual 48x48 -> mask_size 96x96): the transpose of the
+// interpolation is a fixed 4x4 stencil -- input index j receives the outputs 2j-1, 2j, 2j+1, 2j+2 with weights
+// 1/4, 3/4, 3/4, 1/4; at the borders the clamped source index folds the missing neighbour's 1/4 into the 3/4 tap.
+// No searches, no float->int conversions, 16 independent loads per thread.
+__device__ __forceinline__ void taps_2x(int j, int n_in, int (&idx)[4], float (&wt)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { idx[q] = 2 * j - 1 + q; wt[q] = (q == 0 || q == 3) ? 0.25f : 0.75f; }
+    if (j == 0) { idx[0] = 0; wt[0] = 0.0f; wt[1] = 1.0f; }
+    if (j == n_in - 1) { idx[3] = 2 * j + 1; wt[3] = 0.0f; wt[2] = 1.0f; }
+}
+
+__global__ void __launch_bounds__(256) k_resize_bwd_2x(const ResizeK a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.h * a.w) return;
+    const size_t plane = blockIdx.y;
+    const float* __restrict__ g = a.src[blockIdx.z] + plane * (size_t)a.H * a.W;
+    float* __restrict__ gi = a.dst[blockIdx.z] + plane * (size_t)a.h * a.w;
+    const int j = p / a.w, i = p - j * a.w;
+    int yi[4], xi[4];
+    float wy[4], wx[4];
+    taps_2x(j, a.h, yi, wy);
+    taps_2x(i, a.w, xi, wx);
+    float v[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[r][c] = __ldg(g + (size_t)yi[r] * a.W + xi[c]);
+    float acc = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float racc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) racc = fmaf(wx[c], v[r][c], racc);
+        acc = fmaf(wy[r], racc, acc);
+    }
+    gi[p] = acc;
+}
+
 float host_scale(int n_in, int n_out, int align) {
     if (align) return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f;
     return (float)n_in / (float)n_out;
@@ -152,6 +190,10 @@ extern "C" int rcf_resize_bilinear_backward(const float* const* grad_out, float*
     for (int t = 0; t < nten; ++t) { a.src[t] = grad_out[t]; a.dst[t] = grad_in[t]; }
     a.h = h; a.w = w; a.H = H; a.W = W; a.align = align_corners ? 1 : 0;
     a.sy = host_scale(h, H, a.align); a.sx = host_scale(w, W, a.align);
-    k_resize_bwd<<<dim3((h * w + 255) / 256, planes, nten), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    const dim3 grid((h * w + 255) / 256, planes, nten);
+    if (!a.align && H == 2 * h && W == 2 * w && h >= 2 && w >= 2)
+        k_resize_bwd_2x<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    else
+        k_resize_bwd<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return (int)cudaGetLastError();
 }

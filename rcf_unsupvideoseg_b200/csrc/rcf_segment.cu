@@ -34,6 +34,30 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_fwd(const RcfK a) {
     if (a.theta_mode == 1) {
         double* pool = dyn;              // [f*K + k]
         double* hpre = dyn + Cf * K;     // [i*K + k]
+        // The MLP weights are staged in shared memory with coalesced 128-bit loads issued BEFORE the partial sums are
+        // reduced (one global round trip in total instead of one per 8 multiply-adds); rows padded to Cf+1 words.
+        float* w1s = reinterpret_cast<float*>(dyn + 2 * Cf * K);          // [Cf][Cf+1]   (only when a.mlp_smem)
+        float* w2s = w1s + Cf * (Cf + 1);                                   // [2][Cf]
+        if (a.mlp_smem) {
+            for (int q0 = tid; q0 < Cf * Cf / 4; q0 += 4 * blockDim.x) {      // 4 loads in flight per thread
+                float4 w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + u * blockDim.x;
+                    if (q < Cf * Cf / 4) w[u] = __ldg(reinterpret_cast<const float4*>(a.w1) + q);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + u * blockDim.x;
+                    if (q < Cf * Cf / 4) {
+                        const int i = (q * 4) / Cf, j = q * 4 - i * Cf;
+                        float* d = w1s + i * (Cf + 1) + j;
+                        d[0] = w[u].x; d[1] = w[u].y; d[2] = w[u].z; d[3] = w[u].w;
+                    }
+                }
+            }
+            for (int q = tid; q < 2 * Cf; q += blockDim.x) w2s[q] = __ldg(a.w2 + q);
+        }
         for (int i = tid; i < Cf * K; i += blockDim.x)          // chunk partials were summed by k_pool_reduce
             pool[i] = __ldcg(a.poolsum + (size_t)fd * Cf * K + i) / stat[(i % K) * NS];
         __syncthreads();
@@ -41,24 +65,31 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_fwd(const RcfK a) {
         for (int t = tid; t < Cf * K; t += blockDim.x) {
             const int i = t / K, k = t - i * K;
             double v = (double)a.b1[i];
-            const float* __restrict__ w = a.w1 + (size_t)i * Cf;
+            if (a.mlp_smem) {
+                const float* __restrict__ w = w1s + i * (Cf + 1);
 #pragma unroll 8
-            for (int j = 0; j < Cf; ++j) v += (double)__ldg(w + j) * pool[j * K + k];
+                for (int j = 0; j < Cf; ++j) v += (double)w[j] * pool[j * K + k];
+            } else {
+                const float* __restrict__ w = a.w1 + (size_t)i * Cf;
+#pragma unroll 8
+                for (int j = 0; j < Cf; ++j) v += (double)__ldg(w + j) * pool[j * K + k];
+            }
             hpre[t] = v;
             mlp[(size_t)k * 2 * Cf + Cf + i] = v;
             mlp[(size_t)k * 2 * Cf + i] = pool[t];
         }
         __syncthreads();
-        if (tid < 2 * K) {
-            const int c = tid / K, k = tid - c * K;
-            double v = (double)a.b2[c];
-            const float* __restrict__ w = a.w2 + (size_t)c * Cf;
-#pragma unroll 8
-            for (int i = 0; i < Cf; ++i) {
+        // theta[c][k]: one warp per output, lanes stride over the hidden units, fp64 butterfly (fixed order)
+        for (int o = tid >> 5; o < 2 * K; o += blockDim.x >> 5) {
+            const int c = o / K, k = o - c * K, lane = tid & 31;
+            double v = 0.0;
+            for (int i = lane; i < Cf; i += 32) {
                 const double h = hpre[i * K + k];
-                v += (double)__ldg(w + i) * (h >= 0.0 ? h : 0.1 * h);
+                const float w = a.mlp_smem ? w2s[c * Cf + i] : __ldg(a.w2 + (size_t)c * Cf + i);
+                v += (double)w * (h >= 0.0 ? h : 0.1 * h);
             }
-            theta_s[c * K + k] = v;
+            v = warp_sum_d(v);
+            if (lane == 0) theta_s[c * K + k] = v + (double)a.b2[c];
         }
     } else {
         if (tid < 2 * K) theta_s[tid] = (double)a.theta[dir][(size_t)b * 2 * K + tid];   // [B,2,K]
@@ -187,6 +218,17 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
     if (a.theta_mode == 1) {
         double* dh = dyn;             // [i*K + k]
         double* pbar = dyn + Cf * K;  // [j*K + k]
+        float* w1s = reinterpret_cast<float*>(dyn + 2 * Cf * K);          // [Cf][Cf]   (only when a.mlp_smem)
+        if (a.mlp_smem)
+            for (int q0 = tid; q0 < Cf * Cf / 4; q0 += 4 * blockDim.x) {      // 4 loads in flight per thread
+                float4 w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (q0 + u * blockDim.x < Cf * Cf / 4) w[u] = __ldg(reinterpret_cast<const float4*>(a.w1) + q0 + u * blockDim.x);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (q0 + u * blockDim.x < Cf * Cf / 4) reinterpret_cast<float4*>(w1s)[q0 + u * blockDim.x] = w[u];
+            }
         const double* mlp = a.mlp + (size_t)fd * K * 2 * Cf;
         for (int t = tid; t < Cf * K; t += blockDim.x) {
             const int i = t / K, k = t - i * K;
@@ -197,18 +239,25 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
         }
         __syncthreads();
         for (int t = tid; t < Cf * K; t += blockDim.x) {
-            const int k = t / Cf, j = t - k * Cf;       // consecutive threads -> consecutive j (coalesced w1 reads)
+            const int k = t / Cf, j = t - k * Cf;       // consecutive threads -> consecutive j (coalesced / conflict-free w1 reads)
             double v = 0.0;
+            if (a.mlp_smem) {
 #pragma unroll 8
-            for (int i = 0; i < Cf; ++i) v += (double)__ldg(a.w1 + (size_t)i * Cf + j) * dh[i * K + k];
+                for (int i = 0; i < Cf; ++i) v += (double)w1s[i * Cf + j] * dh[i * K + k];
+            } else {
+#pragma unroll 8
+                for (int i = 0; i < Cf; ++i) v += (double)__ldg(a.w1 + (size_t)i * Cf + j) * dh[i * K + k];
+            }
             pbar[j * K + k] = v;
             a.poolbar[((size_t)fd * Cf + j) * K + k] = (float)(v / sd[k * SEGD]);
         }
         __syncthreads();
-        if (tid < K) {
+        for (int k = tid >> 5; k < K; k += blockDim.x >> 5) {      // one warp per segment, fp64 butterfly
+            const int lane = tid & 31;
             double v = 0.0;
-            for (int j = 0; j < Cf; ++j) v += pbar[j * K + tid] * mlp[(size_t)tid * 2 * Cf + j];
-            poolterm[tid] = v;
+            for (int j = lane; j < Cf; j += 32) v += pbar[j * K + k] * mlp[(size_t)k * 2 * Cf + j];
+            v = warp_sum_d(v);
+            if (lane == 0) poolterm[k] = v;
         }
         __syncthreads();
     }
@@ -218,67 +267,105 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
     }
 }
 
-// grid = Cf + 1 blocks of 256 threads.  Block i < Cf: row i of dW1 and db1[i].  Block Cf: dW2, db2.
-// The segment sum is split over G = 256/64 thread groups (fixed partition) and combined through shared memory
-// in group order: deterministic, and 4x shorter dependent chains than one thread per output.
+// Parameter gradients of the segment MLP: tiny fp64 GEMMs over the segment axis s = fd*K + k (nseg = nfd*K terms),
+//   dW1[i][j] = sum_s dh[s][i] * pool[s][j],  db1[i] = sum_s dh[s][i]                      (blocks 0 .. Cf/RB-1: RB rows each)
+//   dW2[c][j] = sum_s thbar[s][c] * lrelu(hpre[s][j]),  db2[c] = sum_s thbar[s][c]         (last block)
+// The operands are staged through shared memory in chunks of SC segments with coalesced loads (one global round trip
+// per chunk instead of one per term) and every output is accumulated by ONE thread in segment order: deterministic.
+constexpr int MPG_RB = 4, MPG_SC = 32;
 __global__ void __launch_bounds__(256) k_mlp_param_grad(const RcfK a) {
-    const int Cf = a.Cf, K = a.K, nseg = a.nfd * K;
-    const int i = blockIdx.x;
-    const double* __restrict__ dh = a.dh;
-    const double* __restrict__ mlp = a.mlp;
-    const double* __restrict__ thbar = a.thbar;
-    __shared__ double part[256];
-    const int nout = (i < Cf) ? Cf + 1 : 2 * Cf + 2;        // outputs of this block (weights + bias)
-    int groups = 256 / ((nout + 31) / 32 * 32);
-    if (groups < 1) groups = 1;
-    const int lanes = 256 / groups;                          // threads per group (>= nout when groups > 1)
-    const int grp = threadIdx.x / lanes, t0 = threadIdx.x - grp * lanes;
-    const int s_lo = (int)((long long)nseg * grp / groups), s_hi = (int)((long long)nseg * (grp + 1) / groups);
-    for (int o0 = 0; o0 < nout; o0 += lanes) {
-        const int o = o0 + t0;
-        double v = 0.0;
-        if (o < nout && grp < groups) {
-            if (i < Cf) {
-                if (o < Cf) {
-#pragma unroll 8
-                    for (int s = s_lo; s < s_hi; ++s) v += __ldg(dh + (size_t)s * Cf + i) * __ldg(mlp + (size_t)s * 2 * Cf + o);
+    const int Cf = a.Cf, nseg = a.nfd * a.K, tid = threadIdx.x;
+    const bool w2blk = blockIdx.x == gridDim.x - 1;
+    extern __shared__ double sm[];                 // right[SC][Cf] | left[SC][RB]
+    double* right = sm;
+    double* left = sm + MPG_SC * Cf;
+    const int i0 = blockIdx.x * MPG_RB;
+    const int nrow = w2blk ? 2 : min(MPG_RB, Cf - i0);
+    constexpr int MAXO = (MPG_RB * (RCF_MAX_CF + 1) + 255) / 256;     // outputs per thread (weights + bias column)
+    double acc[MAXO];
+#pragma unroll
+    for (int u = 0; u < MAXO; ++u) acc[u] = 0.0;
+    const int nout = nrow * (Cf + 1);
+    for (int s0 = 0; s0 < nseg; s0 += MPG_SC) {
+        const int ns = min(MPG_SC, nseg - s0);
+        __syncthreads();
+        double lv = 0.0;                                  // ns * nrow <= 128: one element per thread
+        if (tid < ns * nrow) {
+            const int s = tid / nrow, r = tid - s * nrow;
+            lv = w2blk ? __ldcg(a.thbar + (size_t)(s0 + s) * 2 + r) : __ldcg(a.dh + (size_t)(s0 + s) * Cf + i0 + r);
+        }
+        for (int q0 = tid; q0 < ns * Cf; q0 += 8 * 256) {  // 8 loads in flight per thread
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int q = q0 + u * 256;
+                if (q < ns * Cf) {
+                    const int s = q / Cf, j = q - s * Cf;
+                    v[u] = __ldcg(a.mlp + (size_t)(s0 + s) * 2 * Cf + (w2blk ? Cf : 0) + j);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int q = q0 + u * 256;
+                if (q < ns * Cf) right[q] = (w2blk && v[u] < 0.0) ? 0.1 * v[u] : v[u];
+            }
+        }
+        if (tid < ns * nrow) left[(tid / nrow) * MPG_RB + (tid - (tid / nrow) * nrow)] = lv;
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < MAXO; ++u) {
+            const int o = tid + u * 256;
+            if (o < nout) {
+                const int r = o / (Cf + 1), j = o - r * (Cf + 1);
+                double v = acc[u];
+                if (j < Cf) {
+#pragma unroll 4
+                    for (int s = 0; s < ns; ++s) v += left[s * MPG_RB + r] * right[s * Cf + j];
                 } else {
-#pragma unroll 8
-                    for (int s = s_lo; s < s_hi; ++s) v += __ldg(dh + (size_t)s * Cf + i);
+#pragma unroll 4
+                    for (int s = 0; s < ns; ++s) v += left[s * MPG_RB + r];
                 }
-            } else if (o < 2 * Cf) {
-                const int c = o / Cf, j = o - c * Cf;
-#pragma unroll 8
-                for (int s = s_lo; s < s_hi; ++s) {
-                    const double hp = __ldg(mlp + (size_t)s * 2 * Cf + Cf + j);
-                    v += __ldg(thbar + (size_t)s * 2 + c) * (hp >= 0.0 ? hp : 0.1 * hp);
-                }
-            } else {
-                const int c = o - 2 * Cf;
-#pragma unroll 8
-                for (int s = s_lo; s < s_hi; ++s) v += __ldg(thbar + (size_t)s * 2 + c);
+                acc[u] = v;
             }
         }
-        part[threadIdx.x] = v;
-        __syncthreads();
-        if (grp == 0 && o < nout) {
-            double tot = 0.0;
-            for (int g = 0; g < groups; ++g) tot += part[g * lanes + t0];
-            if (i < Cf) {
-                if (o < Cf) a.dw1[(size_t)i * Cf + o] = (float)tot;
-                else a.db1[i] = (float)tot;
-            } else if (o < 2 * Cf) {
-                a.dw2[o] = (float)tot;
+    }
+#pragma unroll
+    for (int u = 0; u < MAXO; ++u) {
+        const int o = tid + u * 256;
+        if (o < nout) {
+            const int r = o / (Cf + 1), j = o - r * (Cf + 1);
+            if (w2blk) {
+                if (j < Cf) a.dw2[(size_t)r * Cf + j] = (float)acc[u]; else a.db2[r] = (float)acc[u];
             } else {
-                a.db2[o - 2 * Cf] = (float)tot;
+                if (j < Cf) a.dw1[(size_t)(i0 + r) * Cf + j] = (float)acc[u]; else a.db1[i0 + r] = (float)acc[u];
             }
         }
-        __syncthreads();
     }
 }
 
+// dynamic shared memory of the segment kernels: pool/hpre (or dh/pbar) in fp64 + the staged MLP weights
+static size_t seg_dyn_bytes(const RcfK& a) {
+    if (a.theta_mode != 1) return 0;
+    size_t b = (size_t)2 * a.Cf * a.K * sizeof(double);
+    if (a.mlp_smem) b += ((size_t)a.Cf * (a.Cf + 1) + 2 * a.Cf) * sizeof(float);
+    return b;
+}
+
+template <typename Kern>
+static cudaError_t seg_allow_smem(Kern kern, size_t dyn) {
+    if (dyn <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+}
+
 cudaError_t rcf_launch_segment_fwd(const RcfK& a, cudaStream_t s) {
-    const size_t dyn = a.theta_mode == 1 ? (size_t)2 * a.Cf * a.K * sizeof(double) : 0;
+    const size_t dyn = seg_dyn_bytes(a);
+    cudaError_t e0 = cudaSuccess;
+    switch (a.D) {
+        case 0: e0 = seg_allow_smem(k_segment_fwd<0>, dyn); break;
+        case 2: e0 = seg_allow_smem(k_segment_fwd<2>, dyn); break;
+        case 5: e0 = seg_allow_smem(k_segment_fwd<5>, dyn); break;
+    }
+    if (e0 != cudaSuccess) return e0;
     switch (a.D) {
         case 0: k_segment_fwd<0><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
         case 2: k_segment_fwd<2><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
@@ -298,7 +385,14 @@ cudaError_t rcf_launch_finalize(const RcfK& a, cudaStream_t s) {
 }
 
 cudaError_t rcf_launch_segment_bwd(const RcfK& a, cudaStream_t s) {
-    const size_t dyn = a.theta_mode == 1 ? (size_t)2 * a.Cf * a.K * sizeof(double) : 0;
+    const size_t dyn = seg_dyn_bytes(a);
+    cudaError_t e0 = cudaSuccess;
+    switch (a.D) {
+        case 0: e0 = seg_allow_smem(k_segment_bwd<0>, dyn); break;
+        case 2: e0 = seg_allow_smem(k_segment_bwd<2>, dyn); break;
+        case 5: e0 = seg_allow_smem(k_segment_bwd<5>, dyn); break;
+    }
+    if (e0 != cudaSuccess) return e0;
     switch (a.D) {
         case 0: k_segment_bwd<0><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
         case 2: k_segment_bwd<2><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
@@ -308,7 +402,10 @@ cudaError_t rcf_launch_segment_bwd(const RcfK& a, cudaStream_t s) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (a.theta_mode == 1 && a.dw1 && a.db1 && a.dw2 && a.db2) {
-        k_mlp_param_grad<<<a.Cf + 1, 256, 0, s>>>(a);
+        const size_t sm = (size_t)MPG_SC * (a.Cf + MPG_RB) * sizeof(double);
+        e = seg_allow_smem(k_mlp_param_grad, sm);
+        if (e != cudaSuccess) return e;
+        k_mlp_param_grad<<<(a.Cf + MPG_RB - 1) / MPG_RB + 1, 256, sm, s>>>(a);
         e = cudaGetLastError();
     }
     return e;

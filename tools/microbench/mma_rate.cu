@@ -4,7 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-constexpr int ITERS = 4096, CHAINS = 8;
+constexpr int ITERS = 2048, CHAINS = 8;
 
 template <int MODE>
 __global__ void __launch_bounds__(256) k(float* out, long long* clk) {
@@ -27,7 +27,11 @@ __global__ void __launch_bounds__(256) k(float* out, long long* clk) {
             else if (MODE == 3)
                 asm volatile("mma.sync.aligned.m16n8k4.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                              : "+f"(d[c][0]), "+f"(d[c][1]), "+f"(d[c][2]), "+f"(d[c][3]) : "r"(a0), "r"(a1), "r"(b0));
-            else {
+            else if (MODE == 5) {       // fp64 FMA: 2 per chain slot (d[c][0..1] and d[c][2..3] viewed as doubles)
+                double* dd = reinterpret_cast<double*>(d[c]);
+                dd[0] = fma(dd[0], 1.0001, 0.5);
+                dd[1] = fma(dd[1], 1.0001, 0.5);
+            } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) d[c][q] = fmaf(d[c][q], 1.0001f, 0.5f);
             }
@@ -66,6 +70,7 @@ int main() {
         run<1>("mma.m16n8k16 bf16", 16 * 8 * 16, c);
         run<2>("mma.m16n8k16 f16", 16 * 8 * 16, c);
         run<4>("ffma x4 (per lane)", 32 * 4, c);
+        run<5>("dfma x2 (per lane)", 32 * 2, c);
     }
     return 0;
 }
