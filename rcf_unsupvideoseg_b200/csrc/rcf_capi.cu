@@ -74,7 +74,7 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.dbpart = reinterpret_cast<float*>(w + L.w_dbpart);
     a.dbfd = reinterpret_cast<double*>(w + L.w_dbfd);
     a.poolsum = reinterpret_cast<double*>(w + L.w_poolsum);
-    a.nblkpb = L.nblkpb;
+    a.nblkpb = L.nblkpb; a.poolchunk = L.poolchunk; a.pooltp = L.pooltp;
     a.mlp_smem = (d.theta_mode == 1 && d.Cf % 4 == 0 && d.Cf <= 128 && aligned16(in.w1)) ? 1 : 0;
     a.lag = g_fused_lag;
     a.l2_hints = g_l2_hints;   // pass 2 streams flow/residual evict-first so the masks of pass 1 survive in L2

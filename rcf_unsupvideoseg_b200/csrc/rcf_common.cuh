@@ -38,8 +38,17 @@ RCF_HD constexpr int rcf_cb(int D) { return 3 + 3 * D + D * (D + 1) / 2; }
 RCF_HD constexpr int rcf_segd(int D) { return 3 + 5 * D + 2 * D * D; }
 RCF_HD constexpr int rcf_sym_idx(int D, int d, int e) { return d * D - d * (d - 1) / 2 + (e - d); }
 
-RCF_HD constexpr int rcf_pool_chunk_nhwc(int) { return 512; }   // pixels per CTA, channels-last pooling
-RCF_HD int rcf_pool_chunk(int K, int nhwc) { return nhwc ? rcf_pool_chunk_nhwc(K) : (K <= 4 ? 2048 : 1024); }
+// Pixels per CTA of the channels-last pooling forward: 512 for large frames; halved while the grid would not give every
+// SM ~4 CTAs (the 96x96 / 48x48 training shapes: 12.1 -> 6.0 us at 8x2x48x48, 14.6 -> 13.5 us at 96x96).
+RCF_HD int rcf_pool_chunk_nhwc(int P, int nfd) {
+    int c = 512;
+    while (c > 128 && (long long)((P + c - 1) / c) * nfd < 4 * 148) c >>= 1;
+    return c;
+}
+// (measured: the backward does NOT benefit -- 22.4 -> 24.5 us at 8x2x96x96 with 64-pixel CTAs: its per-CTA prologue, the
+// coefficient pack and two tiles, outweighs the shorter pixel loop -- so it keeps 256 pixels per CTA)
+RCF_HD int rcf_pool_tp_nhwc(int, int) { return 256; }
+RCF_HD int rcf_pool_chunk(int K, int nhwc, int P, int nfd) { return nhwc ? rcf_pool_chunk_nhwc(P, nfd) : (K <= 4 ? 2048 : 1024); }
 
 // ---- memory plan ------------------------------------------------------------------------------
 struct RcfLayout {
@@ -49,7 +58,8 @@ struct RcfLayout {
     size_t c_segd, c_coef, c_mlp, c_gm, c_bytes;
     // ws
     size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_sync, w_dbpart, w_dbfd, w_poolsum, w_bytes;
-    int nblkpb;   // CTAs per frame-direction of the channels-last pooling backward (256 pixels each)
+    int nblkpb;   // CTAs per frame-direction of the channels-last pooling backward (pooltp pixels each)
+    int poolchunk, pooltp;
 };
 
 static inline size_t rcf_align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -66,7 +76,7 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.nchunk1 = (L.P + RCF_CHUNK_MOM - 1) / RCF_CHUNK_MOM;
     L.nchunk2 = (L.P + RCF_CHUNK_LOSS - 1) / RCF_CHUNK_LOSS;
     L.nchunkb = (L.P + RCF_CHUNK_BWD - 1) / RCF_CHUNK_BWD;
-    const int pc = rcf_pool_chunk(d.K, d.feat_nhwc);
+    const int pc = rcf_pool_chunk(d.K, d.feat_nhwc, L.P, L.nfd);
     L.nchunkp = (L.P + pc - 1) / pc;
     const size_t nseg = (size_t)L.nfd * d.K;
     size_t o = 0;
@@ -85,7 +95,9 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.w_dh = o;      o = rcf_align256(o + nseg * d.Cf * sizeof(double));
     L.w_thbar = o;   o = rcf_align256(o + nseg * 2 * sizeof(double));
     L.w_sync = o;    o = rcf_align256(o + (size_t)(1 + 2 * L.nfd) * sizeof(int));   // ticket, pass-1 counters, ready flags
-    L.nblkpb = (L.P + 255) / 256;
+    L.pooltp = rcf_pool_tp_nhwc(L.P, L.nfd);
+    L.poolchunk = pc;
+    L.nblkpb = (L.P + L.pooltp - 1) / L.pooltp;
     L.w_dbpart = o;  o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * L.nblkpb * d.Cf * sizeof(float) : 0));   // per-CTA bias-gradient partials
     L.w_dbfd = o;    o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * d.Cf * sizeof(double) : 0));
     L.w_poolsum = o; o = rcf_align256(o + nseg * d.Cf * sizeof(double));
@@ -150,6 +162,7 @@ struct RcfK {
     double* dbfd;             // ws: [nfd][Cf]
     double* poolsum;          // ws: [nfd][Cf*K] pooled sums (un-normalised), reduced over chunks by k_pool_reduce
     int nblkpb;
+    int poolchunk, pooltp;    // pixels per CTA of k_pool_nhwc / k_pool_bwd_nhwc
 };
 
 #ifdef __CUDACC__

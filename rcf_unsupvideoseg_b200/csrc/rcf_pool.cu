@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
 // Forward: per-thread accumulators acc[4 channels][K], no shuffles; the groups are combined through shared memory.
 template <int K>
 __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
-    constexpr int CHUNK = rcf_pool_chunk_nhwc(K);
+    const int CHUNK = a.poolchunk;
     extern __shared__ float sm[];
     float* msT = sm;                         // [CHUNK][K]   mask tile, pixel-major
     float* redn = sm + CHUNK * K;            // [groups][Cf*K]
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
 // back to the NCHW gradient planes with coalesced stores.
 template <int K>
 __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
-    constexpr int TP = 256;                  // pixels per CTA
+    const int TP = a.pooltp;                 // pixels per CTA
     extern __shared__ float sm[];
     float* msT = sm;                         // [TP][K]
     float* dms = sm + TP * K;                // [TP][K]
@@ -379,7 +379,7 @@ __global__ void k_bias_grad_final(const RcfK a) {
 template <int K>
 static cudaError_t launch_pool_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
     const int groups = RCF_BLOCK / (a.Cf / 4);
-    const size_t smem = ((size_t)rcf_pool_chunk_nhwc(K) * K + (size_t)groups * a.Cf * K) * sizeof(float);
+    const size_t smem = ((size_t)a.poolchunk * K + (size_t)groups * a.Cf * K) * sizeof(float);
     dim3 grid(a.nchunkp, a.nfd), block(RCF_BLOCK);
     k_pool_nhwc<K><<<grid, block, smem, s>>>(a);
     return cudaGetLastError();
@@ -387,8 +387,8 @@ static cudaError_t launch_pool_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
 
 template <int K>
 static cudaError_t launch_pool_bwd_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
-    dim3 grid((a.P + 255) / 256, a.nfd), block(RCF_BLOCK);
-    const size_t tile = (size_t)2 * 256 * K, red = 1024;     // mask + dM tiles; [groups][Cf] = 1024 floats for the bias partial
+    dim3 grid(a.nblkpb, a.nfd), block(RCF_BLOCK);
+    const size_t tile = (size_t)2 * a.pooltp * K, red = 1024;     // mask + dM tiles; [groups][Cf] = 1024 floats for the bias partial
     k_pool_bwd_nhwc<K><<<grid, block, (tile > red ? tile : red) * sizeof(float), s>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !a.dfeat_bias) return e;
