@@ -38,16 +38,18 @@ RCF_HD constexpr int rcf_cb(int D) { return 3 + 3 * D + D * (D + 1) / 2; }
 RCF_HD constexpr int rcf_segd(int D) { return 3 + 5 * D + 2 * D * D; }
 RCF_HD constexpr int rcf_sym_idx(int D, int d, int e) { return d * D - d * (d - 1) / 2 + (e - d); }
 
-// Pixels per CTA of the channels-last pooling forward: 512 for large frames; halved while the grid would not give every
-// SM ~4 CTAs (the 96x96 / 48x48 training shapes: 12.1 -> 6.0 us at 8x2x48x48, 14.6 -> 13.5 us at 96x96).
+// Pixels per CTA of the channels-last pooling kernels.  A CTA's time is a chain of dependent global round trips (mask
+// tile, batches of feature loads, partial store), so large frames take long chunks (the prologue/epilogue amortise over
+// more batches: 1024 px forward / 512 px backward) and the 96x96 / 48x48 training shapes take short ones in the forward
+// (halved while the grid would not give every SM ~4 CTAs: 12.1 -> 6.0 us at 8x2x48x48).  The backward does not benefit
+// from going below 256 (22.4 -> 24.5 us at 8x2x96x96 with 64-pixel CTAs: its prologue -- coefficient pack and two tiles --
+// outweighs the shorter pixel loop).
 RCF_HD int rcf_pool_chunk_nhwc(int P, int nfd) {
-    int c = 512;
+    int c = 1024;
     while (c > 128 && (long long)((P + c - 1) / c) * nfd < 4 * 148) c >>= 1;
     return c;
 }
-// (measured: the backward does NOT benefit -- 22.4 -> 24.5 us at 8x2x96x96 with 64-pixel CTAs: its per-CTA prologue, the
-// coefficient pack and two tiles, outweighs the shorter pixel loop -- so it keeps 256 pixels per CTA)
-RCF_HD int rcf_pool_tp_nhwc(int, int) { return 256; }
+RCF_HD int rcf_pool_tp_nhwc(int P, int nfd) { return ((long long)((P + 511) / 512) * nfd >= 4 * 148) ? 512 : 256; }
 RCF_HD int rcf_pool_chunk(int K, int nhwc, int P, int nfd) { return nhwc ? rcf_pool_chunk_nhwc(P, nfd) : (K <= 4 ? 2048 : 1024); }
 
 // ---- memory plan ------------------------------------------------------------------------------

@@ -193,17 +193,30 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
     const int pend = min(CHUNK, P - p0);
     const float4* __restrict__ gp = reinterpret_cast<const float4*>(feat + (long long)p0 * Cf) + c4;
     const int nf4s = nf4;    // float4 stride between consecutive pixels
-#pragma unroll 8
-    for (int p = grp; p < pend; p += groups) {
-        const float4 g = __ldg(gp + (long long)p * nf4s);
-        float gv[4] = {g.x + bias[0], g.y + bias[1], g.z + bias[2], g.w + bias[3]};
+    // Explicit batches: the 8 feature loads of a batch are issued before the first one is consumed (nvcc does not
+    // hoist them out of a predicated, runtime-bounded loop on its own: one load in flight per thread = 3.3 TB/s).
+    constexpr int UB = 8;
+    for (int pb = grp; pb < pend; pb += groups * UB) {
+        float4 gq[UB];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gv[j] = gv[j] >= 0.0f ? gv[j] : slope * gv[j];
+        for (int u = 0; u < UB; ++u) {
+            const int p = pb + u * groups;
+            gq[u] = (p < pend) ? __ldg(gp + (long long)p * nf4s) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float m = msT[p * K + k];
+        for (int u = 0; u < UB; ++u) {
+            const int p = pb + u * groups;
+            if (p < pend) {
+                float gv[4] = {gq[u].x + bias[0], gq[u].y + bias[1], gq[u].z + bias[2], gq[u].w + bias[3]};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j][k] = fmaf(gv[j], m, acc[j][k]);
+                for (int j = 0; j < 4; ++j) gv[j] = gv[j] >= 0.0f ? gv[j] : slope * gv[j];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float m = msT[p * K + k];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j][k] = fmaf(gv[j], m, acc[j][k]);
+                }
+            }
         }
     }
 #pragma unroll
@@ -267,8 +280,64 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
     // (2 + 1 shuffles) then two butterflies, instead of 4 x 4 butterflies
     const bool fast = (K == 4) && (nf4 == 16);
     const int kown = ((c4 >> 3) & 1) * 2 + ((c4 >> 2) & 1);
-    // software pipeline: the loads of the next two pixels are in flight while the current one is processed
     const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    bool done = false;
+    if constexpr (K == 4) {
+        if (fast && TP % groups == 0 && (iters & 7) == 0) {
+            // Reference default (Cf = 64, K = 4): batches of 8 pixels per thread, all eight feature loads in flight before
+            // the first is consumed; the mask quadruple is one LDS.128; no per-iteration slow-path branches.
+            done = true;
+            const bool up8 = (c4 & 8) != 0, up4 = (c4 & 4) != 0, writer = (c4 & 3) == 0;
+            for (int it0 = 0; it0 < iters; it0 += 8) {
+                float4 gq[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int p = grp + (it0 + u) * groups;
+                    gq[u] = (p < pend) ? __ldg(gp + (long long)p * nf4) : zero4;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int p = grp + (it0 + u) * groups;          // < TP by construction
+                    const bool live = p < pend;
+                    const float4 m4 = *reinterpret_cast<const float4*>(msT + p * 4);
+                    const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+                    float gv[4] = {gq[u].x + bias[0], gq[u].y + bias[1], gq[u].z + bias[2], gq[u].w + bias[3]}, dg[4], part[4];
+                    float dact[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        dact[j] = gv[j] >= 0.0f ? 1.0f : slope;
+                        gv[j] *= dact[j];
+                        dg[j] = 0.0f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        part[k] = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            part[k] = fmaf(c[j][k], gv[j], part[k]);
+                            dg[j] = fmaf(c[j][k], mv[k], dg[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        dg[j] *= dact[j];
+                        dbias[j] += live ? dg[j] : 0.0f;
+                    }
+                    if (live && dgp) dgp[(long long)p * nf4] = make_float4(dg[0], dg[1], dg[2], dg[3]);
+                    const float s0 = up8 ? part[0] : part[2], s1 = up8 ? part[1] : part[3];
+                    const float k0 = up8 ? part[2] : part[0], k1 = up8 ? part[3] : part[1];
+                    const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
+                    const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
+                    float v = (up4 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up4 ? a0 : a1, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    if (live && writer) dms[p * 4 + kown] += v;        // 4 lanes per pixel, one per k
+                }
+            }
+        }
+    }
+    if (!done) {
+    // software pipeline: the loads of the next two pixels are in flight while the current one is processed
     float4 g0 = (grp < pend) ? __ldg(gp + (long long)grp * nf4) : zero4;
     float4 g1 = (grp + groups < pend) ? __ldg(gp + (long long)(grp + groups) * nf4) : zero4;
 #pragma unroll 2
@@ -306,27 +375,14 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
             }
             if (dgp) dgp[(long long)p * nf4] = make_float4(dg[0], dg[1], dg[2], dg[3]);
         }
-        if (fast) {
-            if constexpr (K == 4) {
-                const bool up8 = (c4 & 8) != 0, up4 = (c4 & 4) != 0;
-                const float s0 = up8 ? part[0] : part[2], s1 = up8 ? part[1] : part[3];
-                const float k0 = up8 ? part[2] : part[0], k1 = up8 ? part[3] : part[1];
-                const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
-                const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
-                float v = (up4 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up4 ? a0 : a1, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                if (live && (c4 & 3) == 0) dms[p * K + kown] += v;        // 4 lanes per pixel, one per k
-            }
-        } else {
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                for (int o = nf4 >> 1; o > 0; o >>= 1) part[k] += __shfl_xor_sync(0xffffffffu, part[k], o);
-            if (live && c4 == 0) {
+        for (int k = 0; k < K; ++k)
+            for (int o = nf4 >> 1; o > 0; o >>= 1) part[k] += __shfl_xor_sync(0xffffffffu, part[k], o);
+        if (live && c4 == 0) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) dms[p * K + k] += part[k];   // one group per pixel: no conflicts
-            }
+            for (int k = 0; k < K; ++k) dms[p * K + k] += part[k];   // one group per pixel: no conflicts
         }
+    }
     }
     __syncthreads();
     if (dmask) {
