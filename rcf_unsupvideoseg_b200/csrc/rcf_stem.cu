@@ -265,38 +265,62 @@ struct StemTile {
     }
 };
 
+__device__ __forceinline__ void mma_tf32_k4(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k4.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+
+// sign bits of four fp32 values ("v <= 0", -0.0 excepted) as a 4-bit field: top bytes of (bits - 1) packed with two
+// byte permutes, masked to the sign positions and gathered with one multiply.
+__device__ __forceinline__ uint32_t nonpos4(float v0, float v1, float v2, float v3) {
+    const uint32_t u0 = __float_as_uint(v0) - 1u, u1 = __float_as_uint(v1) - 1u;
+    const uint32_t u2 = __float_as_uint(v2) - 1u, u3 = __float_as_uint(v3) - 1u;
+    const uint32_t lo = __byte_perm(u0, u1, 0x0073);       // byte0 = top(u0), byte1 = top(u1)
+    const uint32_t hi = __byte_perm(u2, u3, 0x7300);       // byte2 = top(u2), byte3 = top(u3)
+    const uint32_t w = __byte_perm(lo, hi, 0x7610) & 0x80808080u;   // sign of value i at bit 8i+7
+    return (w * 0x00204081u) >> 28;                          // bit i = sign of value i
+}
+
 // Forward.  CTA = 8 warps on a 32x8 tile = 16 M-tiles of 16 pixels (half a tile row); warp w computes channels
 // [32*(w&1), +32) of M-tiles (w>>1) + 4i.  Column c of N-tile j is channel 32*half + 16*(j>>1) + 4*(c>>1) + 2*(j&1) + (c&1):
 // lane (g = lane/4, t = lane%4) ends up with channels 4t..4t+3 (N-tiles 0,1) and 16+4t..16+4t+3 (N-tiles 2,3) of the
 // pixels g and g+8, so each 128-bit store instruction of the warp writes 64 contiguous bytes per pixel (full sectors).
+// K = taps + 1 (bias column): full k8 steps plus one k4 step for a remainder <= 4 (3x3: 19 = 8 + 8 + 3).
+// The scheduler's issue slots are shared by the MMAs and everything else (measured: MMA time + other-instruction time
+// add up), so the epilogue is kept short: LeakyReLU as max(v, slope*v), sign bits by byte permutes, one address per tile.
 template <int KS>
 __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(const StemK a) {
     using TL = StemTile<KS>;
-    constexpr int NT = 2 * KS * KS, NKS = (NT + 1 + 7) / 8, SW = TL::SW, TSZ = TL::TSZ;
+    constexpr int NT = 2 * KS * KS, NK = NT + 1, SW = TL::SW, TSZ = TL::TSZ;
+    constexpr int REM = NK % 8;
+    constexpr bool K4 = REM > 0 && REM <= 4;
+    constexpr int NK8 = K4 ? NK / 8 : (NK + 7) / 8;
+    constexpr int NK8A = NK8 > 0 ? NK8 : 1;
     constexpr int Cf = STEM_MMA_CF;
     __shared__ uint32_t Thi[TSZ + 2], Tlo[TSZ + 2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int half = warp & 1, mset = warp >> 1;
     const int tx = (a.W + STEM_TW - 1) / STEM_TW, ty = (a.H + STEM_TH - 1) / STEM_TH;
 
-    uint32_t bh[4][NKS][2], bl[4][NKS][2];
+    auto wval = [&](int ch, int k) -> float {
+        return k < NT ? __ldg(a.w + (size_t)ch * NT + k) : (k == NT ? __ldg(a.b + ch) : 0.0f);
+    };
+    uint32_t bh[4][NK8A][2], bl[4][NK8A][2], b4h[4], b4l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int ch = half * 32 + (j >> 1) * 16 + (g >> 1) * 4 + 2 * (j & 1) + (g & 1);
 #pragma unroll
-        for (int s = 0; s < NKS; ++s)
+        for (int s = 0; s < NK8; ++s)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int k = 8 * s + t + 4 * e;
-                const float wv = k < NT ? __ldg(a.w + (size_t)ch * NT + k) : (k == NT ? __ldg(a.b + ch) : 0.0f);
-                split_tf32(wv, bh[j][s][e], bl[j][s][e]);
-            }
+            for (int e = 0; e < 2; ++e) split_tf32(wval(ch, 8 * s + t + 4 * e), bh[j][s][e], bl[j][s][e]);
+        if (K4) split_tf32(wval(ch, 8 * NK8 + t), b4h[j], b4l[j]);
     }
-    int offA[NKS][2], mulA[NKS][2];
+    int offA[NK8A][2], mulA[NK8A][2], off4 = 0, mul4 = 0;
 #pragma unroll
-    for (int s = 0; s < NKS; ++s)
+    for (int s = 0; s < NK8; ++s)
 #pragma unroll
         for (int e = 0; e < 2; ++e) tap_addr<KS>(8 * s + t + 4 * e, offA[s][e], mulA[s][e]);
+    if (K4) tap_addr<KS>(8 * NK8 + t, off4, mul4);
     if (tid == 0) { Thi[TSZ] = __float_as_uint(1.0f); Tlo[TSZ] = 0u; Thi[TSZ + 1] = 0u; Tlo[TSZ + 1] = 0u; }
 
     TL st;
@@ -309,6 +333,8 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
         st.commit(a, Thi, Tlo);
         __syncthreads();
         if (tl + (int)gridDim.x < a.ntiles) st.fetch(a, tl + gridDim.x, tx, ty);     // in flight while this tile is computed
+        float* const img = a.act + (long long)n * a.P * Cf + half * 32 + 4 * t;
+        uint32_t* const simg = a.sign_out ? a.sign_out + (long long)n * a.P * 2 + half : nullptr;
 #pragma unroll 1
         for (int i = 0; i < 4; ++i) {
             const int mt = mset + 4 * i, ly = mt >> 1, lx0 = (mt & 1) * 16;
@@ -321,7 +347,7 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
 #pragma unroll
                 for (int q = 0; q < 4; ++q) c[j][q] = 0.0f;
 #pragma unroll
-            for (int s = 0; s < NKS; ++s) {
+            for (int s = 0; s < NK8; ++s) {
                 const int i0 = offA[s][0] + pix0 * mulA[s][0], i1 = offA[s][0] + pix1 * mulA[s][0];
                 const int i2 = offA[s][1] + pix0 * mulA[s][1], i3 = offA[s][1] + pix1 * mulA[s][1];
                 const uint32_t ah[4] = {Thi[i0], Thi[i1], Thi[i2], Thi[i3]};
@@ -329,29 +355,34 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
 #pragma unroll
                 for (int j = 0; j < 4; ++j) mma_3xtf32(c[j], ah, al, bh[j][s], bl[j][s]);
             }
+            if (K4) {
+                const int i0 = off4 + pix0 * mul4, i1 = off4 + pix1 * mul4;
+                const uint32_t ah0 = Thi[i0], ah1 = Thi[i1], al0 = Tlo[i0], al1 = Tlo[i1];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {                        // row g (h = 0) and row g + 8 (h = 1) of the M-tile
-                const int x = x0 + lx0 + g + 8 * h;
-                float o[8];
-                uint32_t bits = 0;
+                for (int j = 0; j < 4; ++j) {
+                    mma_tf32_k4(c[j], al0, al1, b4h[j]);
+                    mma_tf32_k4(c[j], ah0, ah1, b4l[j]);
+                    mma_tf32_k4(c[j], ah0, ah1, b4h[j]);
+                }
+            }
+            const int x = x0 + lx0 + g;
+            const int pofs = y * a.W + x;                        // pixel of row g; row g+8 is 8 pixels further
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const float v = c[j][2 * h + e];
-                        const bool pos = v > 0.0f;
-                        o[2 * j + e] = pos ? v : a.slope * v;        // o[0..3]: channels 4t..4t+3, o[4..7]: 16+4t..16+4t+3
-                        bits |= (pos ? 0u : 1u) << (2 * j + e);
-                    }
-                uint32_t word = ((bits & 15u) << (4 * t)) | ((bits >> 4) << (16 + 4 * t));
+            for (int h = 0; h < 2; ++h) {
+                // o[0..3]: channels 4t..4t+3, o[4..7]: 16+4t..16+4t+3 (of this warp's 32)
+                const float v[8] = {c[0][2 * h], c[0][2 * h + 1], c[1][2 * h], c[1][2 * h + 1],
+                                    c[2][2 * h], c[2][2 * h + 1], c[3][2 * h], c[3][2 * h + 1]};
+                uint32_t word = (nonpos4(v[0], v[1], v[2], v[3]) << (4 * t)) | (nonpos4(v[4], v[5], v[6], v[7]) << (16 + 4 * t));
                 word |= __shfl_xor_sync(0xffffffffu, word, 1);
                 word |= __shfl_xor_sync(0xffffffffu, word, 2);
-                if (x < a.W) {
-                    const long long px = (long long)n * a.P + (long long)y * a.W + x;
-                    float* dst = a.act + px * Cf + half * 32 + 4 * t;
-                    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<float4*>(dst + 16) = make_float4(o[4], o[5], o[6], o[7]);
-                    if (t == 0 && a.sign_out) a.sign_out[px * 2 + half] = word;
+                if (x + 8 * h < a.W) {
+                    float* dst = img + (long long)(pofs + 8 * h) * Cf;
+                    const float sl = a.slope;                    // 0 <= slope <= 1 (checked by the launcher): lrelu = max(v, slope*v)
+                    *reinterpret_cast<float4*>(dst) = make_float4(fmaxf(v[0], sl * v[0]), fmaxf(v[1], sl * v[1]),
+                                                                  fmaxf(v[2], sl * v[2]), fmaxf(v[3], sl * v[3]));
+                    *reinterpret_cast<float4*>(dst + 16) = make_float4(fmaxf(v[4], sl * v[4]), fmaxf(v[5], sl * v[5]),
+                                                                       fmaxf(v[6], sl * v[6]), fmaxf(v[7], sl * v[7]));
+                    if (t == 0 && simg) simg[(long long)(pofs + 8 * h) * 2] = word;
                 }
             }
         }
@@ -361,12 +392,14 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
 // Backward.  M = channels, N = taps (+ the ones column that yields the bias gradient), K = pixels.  A tile has 32
 // groups of 8 consecutive pixels; warp w accumulates channels [32*(w&1), +32) over the groups (w>>1) + 4i.  Row
 // r = g + 8h of M-tile m is channel 32*half + 4g + 2m + h: a lane needs channels 4g..4g+3 of the pixels t and t+4 of the
-// group = one 128-bit load each, and the 8 lanes of a pixel read 128 contiguous bytes.
+// group = one 128-bit load each, and the 8 lanes of a pixel read 128 contiguous bytes.  The loads of four groups
+// (8 x LDG.128 + 8 sign words per lane) are issued before the first group is consumed.
 template <int KS>
 __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_bwd_mma(const StemK a) {
     using TL = StemTile<KS>;
     constexpr int NT = 2 * KS * KS, NO = NT + 1, NJ = (NO + 7) / 8, NOP = NJ * 8, SW = TL::SW, TSZ = TL::TSZ;
     constexpr int Cf = STEM_MMA_CF;
+    constexpr int GB = 4;                              // groups per load batch
     __shared__ uint32_t Thi[TSZ + 2], Tlo[TSZ + 2];
     extern __shared__ float red[];                   // [RCF_WARPS][32 * NOP]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
@@ -395,45 +428,55 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_bwd_mma(c
         st.commit(a, Thi, Tlo);
         __syncthreads();
         if (tl + (int)gridDim.x < a.ntiles) st.fetch(a, tl + gridDim.x, tx, ty);
-#pragma unroll 4
-        for (int i = 0; i < 8; ++i) {
-            const int q = gset + 4 * i, ly = q >> 2, lx0 = (q & 3) * 8;
-            const int y = y0 + ly;
-            if (y >= a.H || x0 + lx0 >= a.W) continue;          // warp-uniform
-            const int xA = x0 + lx0 + t;
-            const long long pxA = (long long)n * a.P + (long long)y * a.W + xA;
-            float v[2][4];
+        const float* const dimg = a.dact + (long long)n * a.P * Cf + half * 32 + 4 * g;
+        const uint32_t* const simg = a.sign_in + (long long)n * a.P * 2 + half;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 8; i0 += GB) {
+            float4 d4[GB][2];
+            uint32_t sg[GB][2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const bool in = xA + 4 * e < a.W;
-                float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                uint32_t sg = 0u;
-                if (in) {
-                    d4 = __ldg(reinterpret_cast<const float4*>(a.dact + (pxA + 4 * e) * Cf + half * 32 + 4 * g));
-                    sg = __ldg(a.sign_in + (pxA + 4 * e) * 2 + half) >> (4 * g);
+            for (int u = 0; u < GB; ++u) {
+                const int q = gset + 4 * (i0 + u), ly = q >> 2, lx0 = (q & 3) * 8;
+                const int y = y0 + ly, xA = x0 + lx0 + t;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const bool in = y < a.H && xA + 4 * e < a.W;
+                    const int pofs = y * a.W + xA + 4 * e;
+                    d4[u][e] = in ? __ldg(reinterpret_cast<const float4*>(dimg + (long long)pofs * Cf)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    sg[u][e] = in ? __ldg(simg + (long long)pofs * 2) : 0u;
                 }
-                v[e][0] = (sg & 1u) ? d4.x * a.slope : d4.x;
-                v[e][1] = (sg & 2u) ? d4.y * a.slope : d4.y;
-                v[e][2] = (sg & 4u) ? d4.z * a.slope : d4.z;
-                v[e][3] = (sg & 8u) ? d4.w * a.slope : d4.w;
-            }
-            const int pA = ly * SW + lx0 + t;
-            uint32_t bh[NJ][2], bl[NJ][2];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int i0 = offB[j] + pA * mulB[j], i1 = offB[j] + (pA + 4) * mulB[j];
-                bh[j][0] = Thi[i0]; bl[j][0] = Tlo[i0];
-                bh[j][1] = Thi[i1]; bl[j][1] = Tlo[i1];
             }
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                uint32_t ah[4], al[4];
-                split_tf32_fast(v[0][2 * m], ah[0], al[0]);
-                split_tf32_fast(v[0][2 * m + 1], ah[1], al[1]);
-                split_tf32_fast(v[1][2 * m], ah[2], al[2]);
-                split_tf32_fast(v[1][2 * m + 1], ah[3], al[3]);
+            for (int u = 0; u < GB; ++u) {
+                const int q = gset + 4 * (i0 + u), ly = q >> 2, lx0 = (q & 3) * 8;
+                if (y0 + ly >= a.H || x0 + lx0 >= a.W) continue;          // warp-uniform
+                float v[2][4];
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) mma_3xtf32(acc[m][j], ah, al, bh[j], bl[j]);
+                for (int e = 0; e < 2; ++e) {
+                    const uint32_t sb = sg[u][e] >> (4 * g);
+                    v[e][0] = (sb & 1u) ? d4[u][e].x * a.slope : d4[u][e].x;
+                    v[e][1] = (sb & 2u) ? d4[u][e].y * a.slope : d4[u][e].y;
+                    v[e][2] = (sb & 4u) ? d4[u][e].z * a.slope : d4[u][e].z;
+                    v[e][3] = (sb & 8u) ? d4[u][e].w * a.slope : d4[u][e].w;
+                }
+                const int pA = ly * SW + lx0 + t;
+                uint32_t bh[NJ][2], bl[NJ][2];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int j0 = offB[j] + pA * mulB[j], j1 = offB[j] + (pA + 4) * mulB[j];
+                    bh[j][0] = Thi[j0]; bl[j][0] = Tlo[j0];
+                    bh[j][1] = Thi[j1]; bl[j][1] = Tlo[j1];
+                }
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    uint32_t ah[4], al[4];
+                    split_tf32_fast(v[0][2 * m], ah[0], al[0]);
+                    split_tf32_fast(v[0][2 * m + 1], ah[1], al[1]);
+                    split_tf32_fast(v[1][2 * m], ah[2], al[2]);
+                    split_tf32_fast(v[1][2 * m + 1], ah[3], al[3]);
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) mma_3xtf32(acc[m][j], ah, al, bh[j], bl[j]);
+                }
             }
         }
     }
@@ -512,12 +555,12 @@ extern "C" int rcf_stem_forward(const float* const* flow, const int64_t* flow_bs
     if (v != RCF_OK) return v;
     if (!flow || !flow_bstride || !flow[0] || (ndir > 1 && !flow[1]) || !w || !b || !act) return RCF_ERR_NULL;
     if (reinterpret_cast<uintptr_t>(act) & 15u) return RCF_ERR_ALIGN;
-    if (sign && Cf != STEM_MMA_CF) return RCF_ERR_UNSUPPORTED;
+    if (sign && (Cf != STEM_MMA_CF || !(slope >= 0.0f && slope <= 1.0f))) return RCF_ERR_UNSUPPORTED;
     StemK a{};
     fill(a, flow, flow_bstride, ndir, B, H, W, Cf, clamp_t, slope);
     a.w = w; a.b = b; a.act = act; a.sign_out = sign;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (Cf == STEM_MMA_CF) {            // tensor-core path, persistent CTAs (weights split once per CTA)
+    if (Cf == STEM_MMA_CF && slope >= 0.0f && slope <= 1.0f) {            // tensor-core path, persistent CTAs (weights split once per CTA)
         const int g = stem_grid_bwd(a.ntiles);
         switch (ks) {
             case 1: k_stem_fwd_mma<1><<<g, RCF_BLOCK, 0, s>>>(a); break;
