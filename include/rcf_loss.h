@@ -233,6 +233,7 @@ RCF_API int rcf_debug_time_kernel(int which, void* start_event, void* stop_event
 #define RCF_OPT_FUSED_LAG 2      /* slots between pass 1 and pass 2 of a frame-direction (1..64) */
 #define RCF_OPT_L2_HINTS 3       /* evict-first streaming loads of flow/residual in pass 2 (default 1) */
 #define RCF_OPT_SINGLE_PASS 4    /* theta_mode 0 with D == 0: skip pass 1, S_k is accumulated inside pass 2 (default 1) */
+#define RCF_OPT_PDL 5            /* programmatic dependent launch between the library's consecutive kernels (default 1) */
 RCF_API int rcf_debug_set_option(int option, int value);
 
 #ifdef __cplusplus

@@ -134,6 +134,8 @@ def load_library(build_if_missing: bool = True):
         lib.rcf_debug_set_option.argtypes = [C.c_int, C.c_int]
         if lib.rcf_abi_version() != RCF_ABI_VERSION:
             raise RcfLibraryError(f"ABI mismatch: library {lib.rcf_abi_version()} vs binding {RCF_ABI_VERSION}")
+        if os.environ.get("RCF_PDL", "1") == "0":      # A/B switch for measurements (results are identical either way)
+            lib.rcf_debug_set_option(5, 0)
         _lib = lib
     return _lib
 

@@ -13,6 +13,7 @@
 
 template <int K, int D, int PX>
 __global__ void __launch_bounds__(RCF_BLOCK, (D <= 2) ? 2 : 1) k_bwd(const RcfK a) {
+    rcf_pdl_prologue();
     constexpr int CF = rcf_cf(D);
     constexpr int CB = rcf_cb(D);
     constexpr int ITER = RCF_CHUNK_BWD / (RCF_BLOCK * PX);
@@ -150,8 +151,8 @@ template <int K, int D>
 static cudaError_t launch_kd(const RcfK& a, bool vec, cudaStream_t s) {
     dim3 grid(a.nchunkb, a.nfd), block(RCF_BLOCK);
     constexpr int VPX = K <= 4 ? 4 : 2;     // pixels per thread on the vector path (register budget)
-    if (vec) k_bwd<K, D, VPX><<<grid, block, 0, s>>>(a);
-    else k_bwd<K, D, 1><<<grid, block, 0, s>>>(a);
+    if (vec) rcf_launch(k_bwd<K, D, VPX>, grid, block, 0, s, a.pdl, a);
+    else rcf_launch(k_bwd<K, D, 1>, grid, block, 0, s, a.pdl, a);
     return cudaGetLastError();
 }
 

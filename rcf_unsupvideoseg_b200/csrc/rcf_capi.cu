@@ -12,6 +12,7 @@ int g_fused_forward = 0;   // rcf_debug_set_option(RCF_OPT_FUSED_FORWARD, 0/1); 
 int g_fused_lag = 4;       // RCF_OPT_FUSED_LAG
 int g_l2_hints = 1;        // RCF_OPT_L2_HINTS
 int g_single_pass = 1;     // RCF_OPT_SINGLE_PASS
+int g_pdl = 1;             // RCF_OPT_PDL
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
@@ -76,6 +77,7 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.poolsum = reinterpret_cast<double*>(w + L.w_poolsum);
     a.nblkpb = L.nblkpb; a.poolchunk = L.poolchunk; a.pooltp = L.pooltp;
     a.mlp_smem = (d.theta_mode == 1 && d.Cf % 4 == 0 && d.Cf <= 128 && aligned16(in.w1)) ? 1 : 0;
+    a.pdl = g_pdl;
     a.lag = g_fused_lag;
     a.l2_hints = g_l2_hints;   // pass 2 streams flow/residual evict-first so the masks of pass 1 survive in L2
     a.nchunk1 = L.nchunk1; a.nchunk2 = L.nchunk2; a.nchunkb = L.nchunkb; a.nchunkp = L.nchunkp;
@@ -117,6 +119,8 @@ struct ScopedTime {
 
 }  // namespace
 
+int rcf_pdl_enabled() { return g_pdl; }
+
 extern "C" int rcf_debug_time_kernel(int which, void* start_event, void* stop_event) {
     if (which < 0 || which > 5) return RCF_ERR_MODE;
     g_hook.which = which;
@@ -130,6 +134,7 @@ extern "C" int rcf_debug_set_option(int option, int value) {
     if (option == RCF_OPT_FUSED_LAG && value >= 1 && value <= 64) { g_fused_lag = value; return RCF_OK; }
     if (option == RCF_OPT_L2_HINTS) { g_l2_hints = value ? 1 : 0; return RCF_OK; }
     if (option == RCF_OPT_SINGLE_PASS) { g_single_pass = value ? 1 : 0; return RCF_OK; }
+    if (option == RCF_OPT_PDL) { g_pdl = value ? 1 : 0; return RCF_OK; }
     return RCF_ERR_MODE;
 }
 

@@ -146,6 +146,7 @@ struct RcfK {
     int* sync;     // fused forward: [0] ticket, [1..nfd] pass-1 arrival counters, [1+nfd..] ready flags
     int lag;       // fused forward: pass 2 of frame-direction t is scheduled LAG slots after its pass 1
     int l2_hints;  // pass 2 streams flow/residual with an L2 evict-first policy (keeps the masks resident)
+    int pdl;          // launch with programmatic stream serialization (kernels call rcf_pdl_prologue() first)
     int mlp_smem;     // segment kernels stage the MLP weights in shared memory (Cf % 4 == 0 and Cf <= 128)
     int single_pass;  // theta supplied and D == 0: no pass 1; S_k comes out of pass 2 (k_finalize stores it)
     // forward outputs
@@ -168,6 +169,29 @@ struct RcfK {
 };
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch ----------------------------------------------------------------------------------
+// The library's kernels form dependent chains of 6-7 launches per call, most of them microseconds long; inside a CUDA
+// graph the hand-over between two of them costs ~1.5-2 us.  Launched with the programmatic-stream-serialization attribute
+// a kernel may be scheduled while its predecessor drains; every kernel therefore starts with rcf_pdl_prologue():
+// `launch_dependents` (lets the successor's CTAs take the SM slots this grid no longer needs; it fires once every CTA
+// of this grid has executed it or exited) followed by `wait` (blocks until the predecessor has completed and its writes are
+// visible).  Nothing is read or written before the wait, so results are unchanged; without the attribute both are no-ops.
+__device__ __forceinline__ void rcf_pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t rcf_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int pdl,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ----------------------------------------------------------------------------
 template <int PX> struct Pack;
 template <> struct Pack<4> {
@@ -341,6 +365,8 @@ __device__ __forceinline__ void loss_terms(float d, const RcfK& a, float& phi, f
     }
 }
 #endif  // __CUDACC__
+
+int rcf_pdl_enabled();   // RCF_OPT_PDL (rcf_capi.cu)
 
 // launchers (one translation unit each)
 cudaError_t rcf_launch_moments(const RcfK& a, bool vec, cudaStream_t s);

@@ -17,6 +17,7 @@
 
 template <int K, int D, int PX, bool VIS>
 __global__ void __launch_bounds__(RCF_BLOCK, (D <= 2) ? 2 : 1) k_loss(const RcfK a) {
+    rcf_pdl_prologue();
     __shared__ float cf[K * rcf_cf(D)];
     __shared__ float red[RCF_WARPS][rcf_gm(K, D)];
     // Traverse in the REVERSE order of pass 1 (k_moments runs fd 0..n-1, chunks ascending): the masks read last by
@@ -31,11 +32,11 @@ static cudaError_t launch_kd(const RcfK& a, bool vec, cudaStream_t s) {
     const bool vis = a.vis_gt || a.vis_pred || a.vis_agg || a.vis_res || a.vis_aff;
     constexpr int VPX = K <= 4 ? 4 : 2;     // pixels per thread on the vector path (register budget)
     if (vis) {
-        if (vec) k_loss<K, D, VPX, true><<<grid, block, 0, s>>>(a);
-        else k_loss<K, D, 1, true><<<grid, block, 0, s>>>(a);
+        if (vec) rcf_launch(k_loss<K, D, VPX, true>, grid, block, 0, s, a.pdl, a);
+        else rcf_launch(k_loss<K, D, 1, true>, grid, block, 0, s, a.pdl, a);
     } else {
-        if (vec) k_loss<K, D, VPX, false><<<grid, block, 0, s>>>(a);
-        else k_loss<K, D, 1, false><<<grid, block, 0, s>>>(a);
+        if (vec) rcf_launch(k_loss<K, D, VPX, false>, grid, block, 0, s, a.pdl, a);
+        else rcf_launch(k_loss<K, D, 1, false>, grid, block, 0, s, a.pdl, a);
     }
     return cudaGetLastError();
 }

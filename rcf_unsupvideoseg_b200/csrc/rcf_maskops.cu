@@ -34,6 +34,7 @@ constexpr int MASK_CHUNK = 2048;
 
 template <int K, int PX>
 __global__ void __launch_bounds__(RCF_BLOCK) k_mask_fwd(const MaskK a) {
+    asm volatile("griddepcontrol.launch_dependents;");      // k_mask_entropy_final may be scheduled while this grid drains
     constexpr int ITER = MASK_CHUNK / (RCF_BLOCK * PX);
     __shared__ float red[RCF_WARPS];
     const int fr = blockIdx.y, tid = threadIdx.x;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_fwd(const MaskK a) {
 }
 
 __global__ void __launch_bounds__(256) k_mask_entropy_final(const MaskK a) {
+    rcf_pdl_prologue();
     // one CTA: fp64 sum of the per-CTA partials in a fixed order
     __shared__ double red[8];
     const int n = a.nframes * a.nchunk, tid = threadIdx.x;
@@ -203,8 +205,7 @@ extern "C" int rcf_mask_prep_forward(const float* logits, float* masks, float* e
     cudaError_t e = cudaErrorInvalidValue;
     MASK_K_SWITCH(launch_fwd, a, vec, s)
     if (e != cudaSuccess) return (int)e;
-    k_mask_entropy_final<<<1, 256, 0, s>>>(a);
-    return (int)cudaGetLastError();
+    return (int)rcf_launch(k_mask_entropy_final, 1, 256, 0, s, rcf_pdl_enabled(), a);
 }
 
 extern "C" int rcf_mask_prep_backward(const float* masks, const float* grad_masks, const float* grad_entropy, float* dlogits,

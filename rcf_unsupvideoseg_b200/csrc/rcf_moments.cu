@@ -12,6 +12,7 @@
 
 template <int K, int D, int PX>
 __global__ void __launch_bounds__(RCF_BLOCK, (D == 2 && K <= 4) ? 3 : 1) k_moments(const RcfK a) {
+    rcf_pdl_prologue();
     __shared__ float red[RCF_WARPS][K * rcf_ns(D)];
     moments_tile<K, D, PX>(a, blockIdx.y, blockIdx.x, red);
 }
@@ -19,8 +20,8 @@ __global__ void __launch_bounds__(RCF_BLOCK, (D == 2 && K <= 4) ? 3 : 1) k_momen
 template <int K, int D>
 static cudaError_t launch_kd(const RcfK& a, bool vec, cudaStream_t s) {
     dim3 grid(a.nchunk1, a.nfd), block(RCF_BLOCK);
-    if (vec) k_moments<K, D, 4><<<grid, block, 0, s>>>(a);
-    else k_moments<K, D, 1><<<grid, block, 0, s>>>(a);
+    if (vec) rcf_launch(k_moments<K, D, 4>, grid, block, 0, s, a.pdl, a);
+    else rcf_launch(k_moments<K, D, 1>, grid, block, 0, s, a.pdl, a);
     return cudaGetLastError();
 }
 

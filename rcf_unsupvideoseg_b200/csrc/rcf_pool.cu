@@ -15,6 +15,7 @@
 // the mask tile feeds FB global loads (LDS bandwidth, not HBM, was the limiter with FB = 1).
 template <int K, int PX, int CHUNK>
 __global__ void __launch_bounds__(RCF_BLOCK) k_pool(const RcfK a, int f_per_cta) {
+    rcf_pdl_prologue();
     constexpr int FB = 4;
     __shared__ __align__(16) float ms[K][CHUNK];
     const int fd = blockIdx.y;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool(const RcfK a, int f_per_cta)
 
 template <int K, int PX>
 __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
+    rcf_pdl_prologue();
     extern __shared__ float cs[];   // [Cf*K]
     const int fd = blockIdx.y;
     const int dir = fd / a.B;
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd(const RcfK a) {
 // Forward: per-thread accumulators acc[4 channels][K], no shuffles; the groups are combined through shared memory.
 template <int K>
 __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
+    rcf_pdl_prologue();
     const int CHUNK = a.poolchunk;
     extern __shared__ float sm[];
     float* msT = sm;                         // [CHUNK][K]   mask tile, pixel-major
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
 // back to the NCHW gradient planes with coalesced stores.
 template <int K>
 __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
+    rcf_pdl_prologue();
     const int TP = a.pooltp;                 // pixels per CTA
     extern __shared__ float sm[];
     float* msT = sm;                         // [TP][K]
@@ -408,6 +412,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
 // Chunk partials of the pooling -> pooled sums, one warp per (frame-direction, channel, segment): thousands of warps
 // instead of one CTA per frame-direction walking hundreds of chunks serially inside k_segment_fwd.
 __global__ void __launch_bounds__(256) k_pool_reduce(const RcfK a) {
+    rcf_pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nout = a.nfd * a.Cf * a.K;
     if (warp >= nout) return;
@@ -418,6 +423,7 @@ __global__ void __launch_bounds__(256) k_pool_reduce(const RcfK a) {
 // bias gradient of the last conv: two fixed-order levels over the per-CTA partials of k_pool_bwd_nhwc;
 // level 1 = one warp per (frame-direction, channel)
 __global__ void __launch_bounds__(256) k_bias_grad_fd(const RcfK a) {
+    rcf_pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.nfd * a.Cf) return;
     const int fd = warp / a.Cf, f = warp - fd * a.Cf;
@@ -425,6 +431,7 @@ __global__ void __launch_bounds__(256) k_bias_grad_fd(const RcfK a) {
     if (lane == 0) a.dbfd[warp] = v;
 }
 __global__ void k_bias_grad_final(const RcfK a) {
+    rcf_pdl_prologue();
     for (int f = threadIdx.x; f < a.Cf; f += blockDim.x) {
         double v = 0.0;
         for (int fd = 0; fd < a.nfd; ++fd) v += a.dbfd[(size_t)fd * a.Cf + f];
@@ -437,7 +444,7 @@ static cudaError_t launch_pool_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
     const int groups = RCF_BLOCK / (a.Cf / 4);
     const size_t smem = ((size_t)a.poolchunk * K + (size_t)groups * a.Cf * K) * sizeof(float);
     dim3 grid(a.nchunkp, a.nfd), block(RCF_BLOCK);
-    k_pool_nhwc<K><<<grid, block, smem, s>>>(a);
+    rcf_launch(k_pool_nhwc<K>, grid, block, smem, s, a.pdl, a);
     return cudaGetLastError();
 }
 
@@ -445,13 +452,13 @@ template <int K>
 static cudaError_t launch_pool_bwd_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
     dim3 grid(a.nblkpb, a.nfd), block(RCF_BLOCK);
     const size_t tile = (size_t)2 * a.pooltp * K, red = 1024;     // mask + dM tiles; [groups][Cf] = 1024 floats for the bias partial
-    k_pool_bwd_nhwc<K><<<grid, block, (tile > red ? tile : red) * sizeof(float), s>>>(a);
+    rcf_launch(k_pool_bwd_nhwc<K>, grid, block, (tile > red ? tile : red) * sizeof(float), s, a.pdl, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !a.dfeat_bias) return e;
-    k_bias_grad_fd<<<(a.nfd * a.Cf * 32 + 255) / 256, 256, 0, s>>>(a);
+    rcf_launch(k_bias_grad_fd, (a.nfd * a.Cf * 32 + 255) / 256, 256, 0, s, a.pdl, a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_bias_grad_final<<<1, 256, 0, s>>>(a);
+    rcf_launch(k_bias_grad_final, 1, 256, 0, s, a.pdl, a);
     return cudaGetLastError();
 }
 
@@ -464,8 +471,8 @@ static cudaError_t launch_pool_k(const RcfK& a, bool vec, cudaStream_t s) {
     while (base * fsplit < 4 * 148 && a.Cf / (fsplit * 2) >= 4) fsplit *= 2;
     const int f_per_cta = (a.Cf + fsplit - 1) / fsplit;
     dim3 grid(a.nchunkp, a.nfd, (a.Cf + f_per_cta - 1) / f_per_cta), block(RCF_BLOCK);
-    if (vec) k_pool<K, 4, CHUNK><<<grid, block, 0, s>>>(a, f_per_cta);
-    else k_pool<K, 1, CHUNK><<<grid, block, 0, s>>>(a, f_per_cta);
+    if (vec) rcf_launch(k_pool<K, 4, CHUNK>, grid, block, 0, s, a.pdl, a, f_per_cta);
+    else rcf_launch(k_pool<K, 1, CHUNK>, grid, block, 0, s, a.pdl, a, f_per_cta);
     return cudaGetLastError();
 }
 
@@ -476,8 +483,8 @@ static cudaError_t launch_pool_bwd_k(const RcfK& a, bool vec, cudaStream_t s) {
     const int px = vec ? 4 : 1;
     dim3 grid((a.P + RCF_BLOCK * px - 1) / (RCF_BLOCK * px), a.nfd), block(RCF_BLOCK);
     const size_t smem = (size_t)a.Cf * K * sizeof(float);
-    if (vec) k_pool_bwd<K, 4><<<grid, block, smem, s>>>(a);
-    else k_pool_bwd<K, 1><<<grid, block, smem, s>>>(a);
+    if (vec) rcf_launch(k_pool_bwd<K, 4>, grid, block, smem, s, a.pdl, a);
+    else rcf_launch(k_pool_bwd<K, 1>, grid, block, smem, s, a.pdl, a);
     return cudaGetLastError();
 }
 
@@ -502,7 +509,7 @@ cudaError_t rcf_launch_pool(const RcfK& a, bool vec, cudaStream_t s) {
     const cudaError_t e = launch_pool_dispatch(a, vec, s);
     if (e != cudaSuccess) return e;
     const int nout = a.nfd * a.Cf * a.K;
-    k_pool_reduce<<<(nout * 32 + 255) / 256, 256, 0, s>>>(a);
+    rcf_launch(k_pool_reduce, (nout * 32 + 255) / 256, 256, 0, s, a.pdl, a);
     return cudaGetLastError();
 }
 cudaError_t rcf_launch_pool_bwd(const RcfK& a, bool vec, cudaStream_t s) {

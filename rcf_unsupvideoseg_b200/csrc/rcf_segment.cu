@@ -15,6 +15,7 @@
 
 template <int D>
 __global__ void __launch_bounds__(RCF_BLOCK) k_segment_fwd(const RcfK a) {
+    rcf_pdl_prologue();
     constexpr int NS = rcf_ns(D), SEGD = rcf_segd(D), CF = rcf_cf(D);
     __shared__ double stat[RCF_SEG_MAXSTAT];
     __shared__ double theta_s[2 * RCF_MAX_K];
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_fwd(const RcfK a) {
 }
 
 __global__ void __launch_bounds__(RCF_BLOCK) k_finalize(const RcfK a, int GM) {
+    rcf_pdl_prologue();
     const int fd = blockIdx.x;
     __shared__ double out[1 + 3 * RCF_MAX_K + 2 * RCF_MAX_K * 5];
     reduce_partials(a.part2 + (size_t)fd * GM * a.nchunk2, GM, a.nchunk2, out);
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_finalize(const RcfK a, int GM) {
 }
 
 __global__ void k_loss_sum(const RcfK a, int GM) {
+    rcf_pdl_prologue();
     // one warp per direction; lanes stride over the batch, fp64 butterfly; loss[ndir] = fp32 sum of the directions (:397)
     const int dir = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ float ldir[2];
@@ -136,6 +139,7 @@ __global__ void k_loss_sum(const RcfK a, int GM) {
 
 template <int D>
 __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
+    rcf_pdl_prologue();
     constexpr int SEGD = rcf_segd(D), CB = rcf_cb(D);
     __shared__ double thbar[2 * RCF_MAX_K];      // [c*K + k]
     __shared__ double inner[RCF_MAX_K];          // <SFubar,SFu> + <Suubar,Suu>
@@ -274,6 +278,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
 // per chunk instead of one per term) and every output is accumulated by ONE thread in segment order: deterministic.
 constexpr int MPG_RB = 4, MPG_SC = 32;
 __global__ void __launch_bounds__(256) k_mlp_param_grad(const RcfK a) {
+    rcf_pdl_prologue();
     const int Cf = a.Cf, nseg = a.nfd * a.K, tid = threadIdx.x;
     const bool w2blk = blockIdx.x == gridDim.x - 1;
     extern __shared__ double sm[];                 // right[SC][Cf] | left[SC][RB]
@@ -367,9 +372,9 @@ cudaError_t rcf_launch_segment_fwd(const RcfK& a, cudaStream_t s) {
     }
     if (e0 != cudaSuccess) return e0;
     switch (a.D) {
-        case 0: k_segment_fwd<0><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
-        case 2: k_segment_fwd<2><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
-        case 5: k_segment_fwd<5><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
+        case 0: rcf_launch(k_segment_fwd<0>, a.nfd, RCF_BLOCK, dyn, s, a.pdl, a); break;
+        case 2: rcf_launch(k_segment_fwd<2>, a.nfd, RCF_BLOCK, dyn, s, a.pdl, a); break;
+        case 5: rcf_launch(k_segment_fwd<5>, a.nfd, RCF_BLOCK, dyn, s, a.pdl, a); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -377,10 +382,10 @@ cudaError_t rcf_launch_segment_fwd(const RcfK& a, cudaStream_t s) {
 
 cudaError_t rcf_launch_finalize(const RcfK& a, cudaStream_t s) {
     const int GM = rcf_gm(a.K, a.D);
-    k_finalize<<<a.nfd, RCF_BLOCK, 0, s>>>(a, GM);
+    rcf_launch(k_finalize, a.nfd, RCF_BLOCK, 0, s, a.pdl, a, GM);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_loss_sum<<<1, 64, 0, s>>>(a, GM);
+    rcf_launch(k_loss_sum, 1, 64, 0, s, a.pdl, a, GM);
     return cudaGetLastError();
 }
 
@@ -394,9 +399,9 @@ cudaError_t rcf_launch_segment_bwd(const RcfK& a, cudaStream_t s) {
     }
     if (e0 != cudaSuccess) return e0;
     switch (a.D) {
-        case 0: k_segment_bwd<0><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
-        case 2: k_segment_bwd<2><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
-        case 5: k_segment_bwd<5><<<a.nfd, RCF_BLOCK, dyn, s>>>(a); break;
+        case 0: rcf_launch(k_segment_bwd<0>, a.nfd, RCF_BLOCK, dyn, s, a.pdl, a); break;
+        case 2: rcf_launch(k_segment_bwd<2>, a.nfd, RCF_BLOCK, dyn, s, a.pdl, a); break;
+        case 5: rcf_launch(k_segment_bwd<5>, a.nfd, RCF_BLOCK, dyn, s, a.pdl, a); break;
         default: return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaGetLastError();
@@ -405,7 +410,7 @@ cudaError_t rcf_launch_segment_bwd(const RcfK& a, cudaStream_t s) {
         const size_t sm = (size_t)MPG_SC * (a.Cf + MPG_RB) * sizeof(double);
         e = seg_allow_smem(k_mlp_param_grad, sm);
         if (e != cudaSuccess) return e;
-        k_mlp_param_grad<<<(a.Cf + MPG_RB - 1) / MPG_RB + 1, 256, sm, s>>>(a);
+        rcf_launch(k_mlp_param_grad, (a.Cf + MPG_RB - 1) / MPG_RB + 1, 256, sm, s, a.pdl, a);
         e = cudaGetLastError();
     }
     return e;

@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
 // (8 x LDG.128 + 8 sign words per lane) are issued before the first group is consumed.
 template <int KS>
 __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_bwd_mma(const StemK a) {
+    rcf_pdl_prologue();
     using TL = StemTile<KS>;
     constexpr int NT = 2 * KS * KS, NO = NT + 1, NJ = (NO + 7) / 8, NOP = NJ * 8, SW = TL::SW, TSZ = TL::TSZ;
     constexpr int Cf = STEM_MMA_CF;
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_bwd_mma(c
 
 __global__ void __launch_bounds__(256) k_stem_bwd_final(const float* __restrict__ part, int nparts, int Cf, int NT,
                                                         float* __restrict__ dw, float* __restrict__ db) {
+    rcf_pdl_prologue();
     const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;   // warp per output f*(NT+1)+t
     if (o >= Cf * (NT + 1)) return;
     const double v = warp_sum_strided(part + o, nparts, (long long)Cf * (NT + 1), lane);
@@ -585,8 +587,7 @@ static int launch_stem_bwd_mma(const StemK& a, int g, cudaStream_t s) {
     constexpr int NJ = (2 * KS * KS + 1 + 7) / 8;
     const size_t smem = (size_t)RCF_WARPS * 32 * NJ * 8 * sizeof(float);
     RCF_CUDA(cudaFuncSetAttribute(k_stem_bwd_mma<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_stem_bwd_mma<KS><<<g, RCF_BLOCK, smem, s>>>(a);
-    return (int)cudaGetLastError();
+    return (int)rcf_launch(k_stem_bwd_mma<KS>, g, RCF_BLOCK, smem, s, rcf_pdl_enabled(), a);
 }
 
 extern "C" int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W,
@@ -633,7 +634,6 @@ extern "C" int rcf_stem_backward(const float* const* flow, const int64_t* flow_b
         RCF_CUDA(cudaGetLastError());
     }
     const int nout = Cf * (NT + 1);
-    k_stem_bwd_final<<<(nout * 32 + 255) / 256, 256, 0, s>>>(a.part, g, Cf, NT, dw, db);
-    RCF_CUDA(cudaGetLastError());
+    RCF_CUDA(rcf_launch(k_stem_bwd_final, (nout * 32 + 255) / 256, 256, 0, s, rcf_pdl_enabled(), (const float*)a.part, g, Cf, NT, dw, db));
     return RCF_OK;
 }

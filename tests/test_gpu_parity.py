@@ -462,3 +462,50 @@ def test_head_paths_agree_stem_on_off(rcf):
     assert rel_l2(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) < 2e-5
     for a_, b_ in zip(res[0][2], res[1][2]):
         assert rel_l2(a_.cpu().numpy(), b_.cpu().numpy()) < 2e-4
+
+
+def test_programmatic_dependent_launch_is_bit_identical(rcf):
+    """RCF_OPT_PDL only changes WHEN a kernel may be scheduled (every kernel waits for its predecessor before touching
+    memory): full head, forward + backward, eager and replayed from a CUDA graph, must not change a single bit."""
+    lib = rcf.load_library()
+    g = Golden("affine_l1")
+    res = []
+    try:
+        for pdl in (1, 0):
+            assert lib.rcf_debug_set_option(5, pdl) == 0
+            head = build_head(rcf, g)
+            flows, loss, grads = run_head(head, g.inputs, g.gbar)
+            torch.cuda.synchronize()
+            res.append([loss["seg"].detach().clone(), grads["d_masks"].clone(), *[p.grad.clone() for p in head.parameters()]])
+    finally:
+        lib.rcf_debug_set_option(5, 1)
+    for a_, b_ in zip(*res):
+        assert torch.equal(a_, b_)
+    # many back-to-back steps inside one CUDA graph: a missing wait would show up as a race
+    B, K, H, W = 4, 4, 64, 80
+    masks, fw, bw, rfw, rbw = _torch_inputs(B, K, H, W, seed=21)
+    th = [torch.randn(B, 2, K, device="cuda") for _ in range(2)]
+    spec = rcf.LossSpec(K=K, H=H, W=W, D=2, Cf=0, clamp_t=20.0)
+    m = masks.clone().requires_grad_(True)
+
+    def step():
+        loss, _ = rcf.rcf_motion_loss(spec, m, [fw[:, 0], bw[:, 0]], [rfw, rbw], thetas=th)
+        (gm,) = torch.autograd.grad(loss.sum(), m)
+        return loss, gm
+
+    ref_loss, ref_g = step()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = [step() for _ in range(4)]
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    for l_, g_ in outs:
+        assert torch.equal(l_, ref_loss) and torch.equal(g_, ref_g)
