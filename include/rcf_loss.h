@@ -201,17 +201,30 @@ RCF_API int rcf_resize_bilinear_forward(const float* const* in, float* const* ou
 RCF_API int rcf_resize_bilinear_backward(const float* const* grad_out, float* const* grad_in, int nten, int planes, int h,
                                          int w, int H, int W, int align_corners, void* stream);
 
-/* ---- caller-side mask preparation (reference models/rcf_model.py:433-434, :376-378) ----------------
- * logits / masks / grad_masks / dlogits: dense [nframes, K, P] fp32 (the reference's [B, I, K, H, W] with nframes = B*I,
- * P = H*W).  Forward: masks = softmax over K (:433) and entropy[0] = -(masks * log_softmax(masks)).sum(K).mean() --
- * including the reference's log-softmax OF the probabilities (:434) -- in one pass; ws from
- * rcf_mask_prep_workspace_floats.  Backward: dlogits = softmax-backward of (grad_masks + grad_entropy * dEntropy/dmasks)
- * in one pass; grad_masks (the motion loss's mask gradient) and grad_entropy (device scalar) may each be NULL. */
+/* ---- caller-side mask preparation and mask losses ------------------------------------------------
+ * Reference: models/rcf_model.py:433-434 (softmax over K, log-softmax OF the result), :376-378 (entropy loss),
+ * :380-408 (PL / CRF positive/negative weighted MSE on the object channel), models/compactness_head.py:33-56
+ * (compactness of one channel).  logits / masks / grad_masks / dlogits: dense [nframes, K, H*W] fp32 (the reference's
+ * [B, I, K, H, W] with nframes = B*I); target: [nframes, H*W] (pl_masks / crf_masks).
+ * Forward, one pass: masks = softmax over K; losses[0] = -(masks * log_softmax(masks)).sum(K).mean();
+ * losses[1] = compactness of channel compact_channel (0 when off); losses[2] = pl_pos_weight * mean(max(t-m,0)^2) +
+ * pl_neg_weight * mean(min(t-m,0)^2) with m = masks[:, pl_channel] and t = target (> pl_threshold when that is != -1).
+ * frame_stats [nframes, 2] receives the per-frame centroid (needed by the backward when compactness is on).
+ * Backward, one pass: dlogits = softmax-backward of (grad_masks + sum_i grad_losses[i] * dlosses[i]/dmasks); grad_masks
+ * (the motion loss's mask gradient) and grad_losses (device float[3]) may each be NULL. */
+typedef struct RcfMaskCfg {
+    int32_t nframes, K, H, W;
+    int32_t compact_channel;   /* -1: off                                  (compactness_head.py:19-27)  */
+    int32_t pl_channel;        /* object channel of the PL/CRF loss, -1: off (rcf_model.py:388, :403)    */
+    float pl_threshold;        /* pl_mask_pos_th / crf_mask_pos_th; -1: target used as it is (:384, :399) */
+    float pl_pos_weight;       /* pl_pos_weight / crf_pos_weight             (:393, :408)                 */
+    float pl_neg_weight;
+} RcfMaskCfg;
 RCF_API int rcf_mask_prep_workspace_floats(int nframes, int P, size_t* nfloats);
-RCF_API int rcf_mask_prep_forward(const float* logits, float* masks, float* entropy, float* ws, int nframes, int K, int P,
-                                  void* stream);
-RCF_API int rcf_mask_prep_backward(const float* masks, const float* grad_masks, const float* grad_entropy, float* dlogits,
-                                   int nframes, int K, int P, void* stream);
+RCF_API int rcf_mask_losses_forward(const RcfMaskCfg* cfg, const float* logits, const float* target, float* masks,
+                                    float* losses, float* frame_stats, float* ws, void* stream);
+RCF_API int rcf_mask_losses_backward(const RcfMaskCfg* cfg, const float* masks, const float* target, const float* grad_masks,
+                                     const float* grad_losses, const float* frame_stats, float* dlogits, void* stream);
 
 /* Measurement hook (bench.py): record the two caller-owned cudaEvent_t handles immediately before and
  * after the launch of streaming kernel `which` in the following rcf_forward / rcf_backward calls of this

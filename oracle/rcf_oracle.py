@@ -447,27 +447,72 @@ def synthetic_inputs(B, K, H, W, seed=0, resid_hw=None, mask_sharpness=1.0, dtyp
 
 
 # ----------------------------------------------------------------------------------------------
-# caller-side mask preparation (models/rcf_model.py:433-434, :376-378) -- SURVEY 8f rank 2
+# caller-side mask preparation and mask losses -- SURVEY 8f rank 2
+#   models/rcf_model.py:433-434 (softmax, log-softmax of the result), :376-378 (entropy), :380-408 (PL / CRF loss),
+#   models/compactness_head.py:33-56 (compactness)
 # ----------------------------------------------------------------------------------------------
-def mask_prep_forward(logits):
-    """logits [B,I,K,H,W] -> (masks, entropy): softmax over K (:433), log_softmax OF the masks (:434, as written) and
-    -(masks * log_masks).sum(2).mean() (:376-378)."""
+def _pl_target(target, th):
+    return target if th == -1 else (target > th).astype(target.dtype)
+
+
+def mask_losses_forward(logits, compact_channel=None, target=None, object_channel=None, pl_th=-1.0, wpos=1.0, wneg=1.0):
+    """logits [B,I,K,H,W] -> (masks, dict(entropy, compactness, pl), centres [B*I,2])."""
     x = logits - logits.max(axis=2, keepdims=True)
     e = np.exp(x)
     m = e / e.sum(axis=2, keepdims=True)
     lse = np.log(np.exp(m).sum(axis=2, keepdims=True))
-    ls = m - lse
-    return m, float(-(m * ls).sum(axis=2).mean())
+    ls = m - lse                                                     # :434 log_softmax OF the masks
+    out = {"entropy": float(-(m * ls).sum(axis=2).mean()), "compactness": 0.0, "pl": 0.0}       # :376-378
+    B, I, K, H, W = m.shape
+    centres = np.zeros((B * I, 2))
+    if compact_channel is not None:                                  # compactness_head.py:29-56
+        mc = m[:, :, compact_channel].reshape(B * I, H, W)
+        cnt = mc.sum(axis=(1, 2), keepdims=True)
+        # the reference builds the coordinates in fp32 (torch.arange(..., dtype=torch.float) / mask_H, :38-40)
+        y = (np.arange(H, dtype=np.float32) / np.float32(H)).astype(np.float64)[None, :, None]
+        xx = (np.arange(W, dtype=np.float32) / np.float32(W)).astype(np.float64)[None, None, :]
+        yc = (y * mc).sum(axis=(1, 2), keepdims=True) / cnt
+        xc = (xx * mc).sum(axis=(1, 2), keepdims=True) / cnt
+        out["compactness"] = float((((y - yc) ** 2 + (xx - xc) ** 2) * mc).mean())
+        centres = np.concatenate([yc.reshape(-1, 1), xc.reshape(-1, 1)], 1)
+    if target is not None and object_channel is not None:            # rcf_model.py:380-408
+        t = _pl_target(target, pl_th)
+        d = t - m[:, :, object_channel]
+        out["pl"] = float((np.maximum(d, 0) ** 2).mean() * wpos + (np.minimum(d, 0) ** 2).mean() * wneg)
+    return m, out, centres
 
 
-def mask_prep_backward(masks, g_masks, g_entropy):
-    """d(loss)/d(logits) given d/d(masks) (or None) and the scalar d/d(entropy) (or None)."""
+def mask_losses_backward(masks, g_masks=None, g_entropy=None, g_compact=None, g_pl=None, compact_channel=None, target=None,
+                         object_channel=None, pl_th=-1.0, wpos=1.0, wneg=1.0):
+    """d(loss)/d(logits) for upstream gradients on the masks and on each scalar loss (None = not used)."""
     m = masks
-    npix = m.size / m.shape[2]
+    B, I, K, H, W = m.shape
+    npix = B * I * H * W
     g = np.zeros_like(m) if g_masks is None else g_masks.astype(m.dtype).copy()
     if g_entropy is not None:
         lse = np.log(np.exp(m).sum(axis=2, keepdims=True))
         ls = m - lse
         q = np.exp(ls)
         g = g - g_entropy / npix * (ls + m - q * m.sum(axis=2, keepdims=True))
+    if g_compact is not None and compact_channel is not None:
+        mc = m[:, :, compact_channel].reshape(B * I, H, W)
+        cnt = mc.sum(axis=(1, 2), keepdims=True)
+        y = (np.arange(H, dtype=np.float32) / np.float32(H)).astype(np.float64)[None, :, None]
+        xx = (np.arange(W, dtype=np.float32) / np.float32(W)).astype(np.float64)[None, None, :]
+        yc = (y * mc).sum(axis=(1, 2), keepdims=True) / cnt
+        xc = (xx * mc).sum(axis=(1, 2), keepdims=True) / cnt
+        # the centroid's dependence on m cancels: sum_q m_q (y_q - yc) = 0
+        g[:, :, compact_channel] += (g_compact / npix * ((y - yc) ** 2 + (xx - xc) ** 2)).reshape(B, I, H, W)
+    if g_pl is not None and target is not None and object_channel is not None:
+        d = _pl_target(target, pl_th) - m[:, :, object_channel]
+        g[:, :, object_channel] += g_pl / npix * (-2.0) * (wpos * np.maximum(d, 0) + wneg * np.minimum(d, 0))
     return m * (g - (m * g).sum(axis=2, keepdims=True))
+
+
+def mask_prep_forward(logits):
+    m, out, _ = mask_losses_forward(logits)
+    return m, out["entropy"]
+
+
+def mask_prep_backward(masks, g_masks, g_entropy):
+    return mask_losses_backward(masks, g_masks=g_masks, g_entropy=g_entropy)

@@ -35,6 +35,12 @@ class RcfDesc(C.Structure):
     ]
 
 
+class RcfMaskCfg(C.Structure):
+    _fields_ = [("nframes", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("compact_channel", C.c_int32), ("pl_channel", C.c_int32),
+                ("pl_threshold", C.c_float), ("pl_pos_weight", C.c_float), ("pl_neg_weight", C.c_float)]
+
+
 class RcfInputs(C.Structure):
     _fields_ = [
         ("mask", _ptr2), ("flow", _ptr2), ("resid", _ptr2), ("feat", _ptr2), ("theta", _ptr2),
@@ -58,7 +64,7 @@ EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "r
                     "rcf_debug_time_kernel", "rcf_flow_warp_forward", "rcf_flow_warp_backward", "rcf_corresponding_map",
                     "rcf_debug_set_option", "rcf_stem_forward", "rcf_stem_workspace_bytes", "rcf_stem_backward",
                     "rcf_resize_bilinear_forward", "rcf_resize_bilinear_backward",
-                    "rcf_mask_prep_workspace_floats", "rcf_mask_prep_forward", "rcf_mask_prep_backward")
+                    "rcf_mask_prep_workspace_floats", "rcf_mask_losses_forward", "rcf_mask_losses_backward")
 
 _lib = None
 _lock = threading.Lock()
@@ -126,10 +132,12 @@ def load_library(build_if_missing: bool = True):
                            C.c_int, C.c_int, C.c_void_p]
         lib.rcf_mask_prep_workspace_floats.restype = C.c_int
         lib.rcf_mask_prep_workspace_floats.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t)]
-        lib.rcf_mask_prep_forward.restype = C.c_int
-        lib.rcf_mask_prep_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
-        lib.rcf_mask_prep_backward.restype = C.c_int
-        lib.rcf_mask_prep_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.rcf_mask_losses_forward.restype = C.c_int
+        lib.rcf_mask_losses_forward.argtypes = [C.POINTER(RcfMaskCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.rcf_mask_losses_backward.restype = C.c_int
+        lib.rcf_mask_losses_backward.argtypes = [C.POINTER(RcfMaskCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rcf_debug_set_option.restype = C.c_int
         lib.rcf_debug_set_option.argtypes = [C.c_int, C.c_int]
         if lib.rcf_abi_version() != RCF_ABI_VERSION:

@@ -13,41 +13,62 @@
 //        dE/dm_j    = -(ls_j + m_j - q_j * Sm) / Npix
 //        gm_j       = gmask_j + gE * dE/dm_j
 //        dlogit_j   = m_j * (gm_j - sum_k m_k gm_k)
+// The same read of the mask tensor also feeds the other caller-side mask losses the shipped configs enable:
+//   compactness (models/compactness_head.py:33-56; STv2 stage 1, w_compactness 1.0): soft centroid of one channel per
+//       frame and mean(((y-yc)^2 + (x-xc)^2) * m) -- four moment sums per frame in the forward pass; the dependence of the
+//       centroid on m cancels in the gradient (sum_q m_q (y_q - yc) = 0), so dL/dm_p = ((y_p-yc)^2 + (x_p-xc)^2) / Npix;
+//   PL / CRF loss (models/rcf_model.py:380-408; stages 2.1 / 2.2): positive/negative weighted MSE between the object
+//       channel and a (optionally thresholded) target mask.
 // HBM-bound: 8K B/px forward, 12K B/px backward (fp32), 128-bit accesses, no intermediates.
 #include "rcf_common.cuh"
 
 namespace {
 
+// per-CTA partial sums: entropy, compactness moments (S, Sy, Sx, Sq) of the compact channel, PL/CRF squared errors
+constexpr int MASK_NP = 7;
+
 struct MaskK {
     const float* logits;
     float* masks;
-    float* part;         // [nframes * nchunk]
-    float* entropy;      // [1]
+    float* part;         // [nframes * nchunk][MASK_NP]
+    float* losses;       // [3]: entropy, compactness, pl/crf
+    float* fstats;       // [nframes][2]: (y_center, x_center) of the compact channel (forward -> backward)
     const float* gmasks; // may be null
-    const float* gent;   // device scalar, may be null
+    const float* glosses;// device [3] (d/d entropy, d/d compactness, d/d pl), may be null
     float* dlogits;
-    int nframes, P, nchunk;
+    const float* target; // PL / CRF masks [nframes, P] or null
+    int nframes, P, H, W, nchunk;
+    int compact_ch;      // -1: off
+    int pl_ch;           // object channel (PL / CRF loss), -1: off
+    int pl_binarize;     // target = target > pl_th
+    float pl_th, pl_wpos, pl_wneg;
     float inv_npix;      // 1 / (nframes * P)
+    float inv_h, inv_w;
 };
 
 constexpr int MASK_CHUNK = 2048;
 
 template <int K, int PX>
 __global__ void __launch_bounds__(RCF_BLOCK) k_mask_fwd(const MaskK a) {
-    asm volatile("griddepcontrol.launch_dependents;");      // k_mask_entropy_final may be scheduled while this grid drains
+    asm volatile("griddepcontrol.launch_dependents;");      // k_mask_final may be scheduled while this grid drains
     constexpr int ITER = MASK_CHUNK / (RCF_BLOCK * PX);
-    __shared__ float red[RCF_WARPS];
+    __shared__ float red[RCF_WARPS][MASK_NP];
     const int fr = blockIdx.y, tid = threadIdx.x;
     const float* __restrict__ lg = a.logits + (size_t)fr * K * a.P;
     float* __restrict__ mk = a.masks + (size_t)fr * K * a.P;
-    float ent = 0.0f;
+    const float* __restrict__ tg = a.target ? a.target + (size_t)fr * a.P : nullptr;
+    float acc[MASK_NP];
+#pragma unroll
+    for (int i = 0; i < MASK_NP; ++i) acc[i] = 0.0f;
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
         const int p = blockIdx.x * MASK_CHUNK + (it * RCF_BLOCK + tid) * PX;
         if (p < a.P) {
-            float x[K][PX];
+            float x[K][PX], t[PX];
 #pragma unroll
             for (int k = 0; k < K; ++k) Pack<PX>::ld(x[k], lg + (size_t)k * a.P + p);
+            if (tg) Pack<PX>::ld(t, tg + p);
+            int row = p / a.W, col = p - row * a.W;
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
                 float mx = x[0][j];
@@ -57,7 +78,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_fwd(const MaskK a) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) { x[k][j] = __expf(x[k][j] - mx); s += x[k][j]; }
                 const float inv = 1.0f / s;
-                float s2 = 0.0f, dot = 0.0f, sm = 0.0f;
+                float s2 = 0.0f, dot = 0.0f, sm = 0.0f, mc = 0.0f, mo = 0.0f;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const float m = x[k][j] * inv;
@@ -65,39 +86,77 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_fwd(const MaskK a) {
                     s2 += __expf(m);              // m in [0, 1]: no max subtraction needed
                     dot = fmaf(m, m, dot);
                     sm += m;
+                    mc = (k == a.compact_ch) ? m : mc;
+                    mo = (k == a.pl_ch) ? m : mo;
                 }
                 // -(sum_k m_k (m_k - lse)) = lse * sum m - sum m^2
-                ent += __logf(s2) * sm - dot;
+                acc[0] += __logf(s2) * sm - dot;
+                if (a.compact_ch >= 0) {          // compactness_head.py:33-56: soft count and first/second moments
+                    const float yy = (float)row * a.inv_h, xx = (float)col * a.inv_w;
+                    acc[1] += mc;
+                    acc[2] = fmaf(mc, yy, acc[2]);
+                    acc[3] = fmaf(mc, xx, acc[3]);
+                    acc[4] = fmaf(mc, fmaf(yy, yy, xx * xx), acc[4]);
+                }
+                if (tg) {                          // rcf_model.py:380-408: weighted MSE towards the PL / CRF mask
+                    const float tv = a.pl_binarize ? (t[j] > a.pl_th ? 1.0f : 0.0f) : t[j];
+                    const float d = tv - mo;
+                    const float dp = fmaxf(d, 0.0f), dn = fminf(d, 0.0f);
+                    acc[5] = fmaf(dp, dp, acc[5]);
+                    acc[6] = fmaf(dn, dn, acc[6]);
+                }
+                if (++col == a.W) { col = 0; ++row; }
             }
 #pragma unroll
             for (int k = 0; k < K; ++k) Pack<PX>::st(mk + (size_t)k * a.P + p, x[k]);
         }
     }
-    ent = warp_sum(ent);
-    if ((tid & 31) == 0) red[tid >> 5] = ent;
+    warp_reduce_store<MASK_NP>(acc, tid & 31, red[tid >> 5]);
     __syncthreads();
-    if (tid == 0) {
+    if (tid < MASK_NP) {
         float v = 0.0f;
 #pragma unroll
-        for (int w = 0; w < RCF_WARPS; ++w) v += red[w];
-        a.part[(size_t)fr * a.nchunk + blockIdx.x] = v;
+        for (int w = 0; w < RCF_WARPS; ++w) v += red[w][tid];
+        a.part[((size_t)fr * a.nchunk + blockIdx.x) * MASK_NP + tid] = v;
     }
 }
 
-__global__ void __launch_bounds__(256) k_mask_entropy_final(const MaskK a) {
+// one CTA: fp64 sums of the per-CTA partials in a fixed order; one warp per frame for the compactness centres
+__global__ void __launch_bounds__(256) k_mask_final(const MaskK a) {
     rcf_pdl_prologue();
-    // one CTA: fp64 sum of the per-CTA partials in a fixed order
-    __shared__ double red[8];
-    const int n = a.nframes * a.nchunk, tid = threadIdx.x;
-    double v = 0.0;
-    for (int i = tid; i < n; i += 256) v += (double)__ldcg(a.part + i);
-    v = warp_sum_d(v);
-    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __shared__ double red[8][4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};      // entropy, compactness, pl_pos, pl_neg
+    for (int f = warp; f < a.nframes; f += 8) {
+        double v[MASK_NP];
+#pragma unroll
+        for (int i = 0; i < MASK_NP; ++i) v[i] = 0.0;
+        for (int c = lane; c < a.nchunk; c += 32) {
+            const float* q = a.part + ((size_t)f * a.nchunk + c) * MASK_NP;
+#pragma unroll
+            for (int i = 0; i < MASK_NP; ++i) v[i] += (double)__ldcg(q + i);
+        }
+#pragma unroll
+        for (int i = 0; i < MASK_NP; ++i) v[i] = warp_sum_d(v[i]);
+        tot[0] += v[0]; tot[2] += v[5]; tot[3] += v[6];
+        if (a.compact_ch >= 0) {
+            const double yc = v[2] / v[1], xc = v[3] / v[1];
+            tot[1] += v[4] - (v[2] * v[2] + v[3] * v[3]) / v[1];       // sum m ((y-yc)^2 + (x-xc)^2)
+            if (lane == 0 && a.fstats) { a.fstats[2 * f] = (float)yc; a.fstats[2 * f + 1] = (float)xc; }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[warp][i] = tot[i];
+    }
     __syncthreads();
     if (tid == 0) {
-        double t = 0.0;
-        for (int w = 0; w < 8; ++w) t += red[w];
-        a.entropy[0] = (float)(t * (double)a.inv_npix);
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < 8; ++w)
+            for (int i = 0; i < 4; ++i) t[i] += red[w][i];
+        a.losses[0] = (float)(t[0] * (double)a.inv_npix);
+        a.losses[1] = (float)(t[1] * (double)a.inv_npix);
+        a.losses[2] = (float)((t[2] * (double)a.pl_wpos + t[3] * (double)a.pl_wneg) * (double)a.inv_npix);
     }
 }
 
@@ -107,13 +166,18 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_bwd(const MaskK a) {
     const int fr = blockIdx.y, tid = threadIdx.x;
     const float* __restrict__ mk = a.masks + (size_t)fr * K * a.P;
     const float* __restrict__ gm = a.gmasks ? a.gmasks + (size_t)fr * K * a.P : nullptr;
+    const float* __restrict__ tg = a.target ? a.target + (size_t)fr * a.P : nullptr;
     float* __restrict__ dl = a.dlogits + (size_t)fr * K * a.P;
-    const float ge = a.gent ? -__ldg(a.gent) * a.inv_npix : 0.0f;
+    const float ge = a.glosses ? -__ldg(a.glosses) * a.inv_npix : 0.0f;
+    const float gc = (a.glosses && a.compact_ch >= 0) ? __ldg(a.glosses + 1) * a.inv_npix : 0.0f;
+    const float gp = (a.glosses && tg) ? -2.0f * __ldg(a.glosses + 2) * a.inv_npix : 0.0f;
+    const float yc = (a.compact_ch >= 0 && a.fstats) ? __ldg(a.fstats + 2 * fr) : 0.0f;
+    const float xc = (a.compact_ch >= 0 && a.fstats) ? __ldg(a.fstats + 2 * fr + 1) : 0.0f;
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
         const int p = blockIdx.x * MASK_CHUNK + (it * RCF_BLOCK + tid) * PX;
         if (p < a.P) {
-            float m[K][PX], g[K][PX];
+            float m[K][PX], g[K][PX], t[PX];
 #pragma unroll
             for (int k = 0; k < K; ++k) Pack<PX>::ld(m[k], mk + (size_t)k * a.P + p);
 #pragma unroll
@@ -124,6 +188,8 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_bwd(const MaskK a) {
                     for (int j = 0; j < PX; ++j) g[k][j] = 0.0f;
                 }
             }
+            if (tg) Pack<PX>::ld(t, tg + p);
+            int row = p / a.W, col = p - row * a.W;
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
                 float s2 = 0.0f, sm = 0.0f;
@@ -131,16 +197,32 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_bwd(const MaskK a) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) { e[k] = __expf(m[k][j]); s2 += e[k]; sm += m[k][j]; }
                 const float lse = __logf(s2), inv2 = 1.0f / s2;
+                // extra per-channel gradient terms (compactness on compact_ch, PL / CRF on pl_ch)
+                const float dy = (float)row * a.inv_h - yc, dx = (float)col * a.inv_w - xc;
+                const float gcomp = gc * fmaf(dy, dy, dx * dx);
+                float gpl = 0.0f;
+                if (tg) {
+                    float mo = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) mo = (k == a.pl_ch) ? m[k][j] : mo;
+                    const float tv = a.pl_binarize ? (t[j] > a.pl_th ? 1.0f : 0.0f) : t[j];
+                    const float d = tv - mo;
+                    gpl = gp * (a.pl_wpos * fmaxf(d, 0.0f) + a.pl_wneg * fminf(d, 0.0f));
+                }
                 float dot = 0.0f;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const float mkj = m[k][j];
                     const float dE = (mkj - lse) + mkj - e[k] * inv2 * sm;     // ls_j + m_j - q_j * Sm
-                    g[k][j] = fmaf(ge, dE, g[k][j]);
-                    dot = fmaf(mkj, g[k][j], dot);
+                    float gk = fmaf(ge, dE, g[k][j]);
+                    gk += (k == a.compact_ch) ? gcomp : 0.0f;
+                    gk += (k == a.pl_ch) ? gpl : 0.0f;
+                    g[k][j] = gk;
+                    dot = fmaf(mkj, gk, dot);
                 }
 #pragma unroll
                 for (int k = 0; k < K; ++k) g[k][j] = m[k][j] * (g[k][j] - dot);
+                if (++col == a.W) { col = 0; ++row; }
             }
 #pragma unroll
             for (int k = 0; k < K; ++k) Pack<PX>::st(dl + (size_t)k * a.P + p, g[k]);
@@ -163,12 +245,23 @@ cudaError_t launch_bwd(const MaskK& a, bool vec, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-int mask_check(int nframes, int K, long long P) {
-    if (nframes < 1 || nframes > 65535 || K < 1 || P < 1 || P > 0x7fffffffLL / 4) return RCF_ERR_SHAPE;
+int mask_check(int nframes, int K, int H, int W) {
+    if (nframes < 1 || nframes > 65535 || K < 1 || H < 1 || W < 1 || (long long)H * W > 0x7fffffffLL / 4) return RCF_ERR_SHAPE;
     if (K > RCF_MAX_K) return RCF_ERR_UNSUPPORTED;
     return RCF_OK;
 }
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+void fill_cfg(MaskK& a, const RcfMaskCfg& c) {
+    a.nframes = c.nframes; a.H = c.H; a.W = c.W; a.P = c.H * c.W;
+    a.nchunk = (a.P + MASK_CHUNK - 1) / MASK_CHUNK;
+    a.compact_ch = (c.compact_channel >= 0 && c.compact_channel < c.K) ? c.compact_channel : -1;
+    a.pl_ch = (c.pl_channel >= 0 && c.pl_channel < c.K) ? c.pl_channel : -1;
+    a.pl_binarize = c.pl_threshold != -1.0f;      // reference: `if self.pl_mask_pos_th != -1`
+    a.pl_th = c.pl_threshold; a.pl_wpos = c.pl_pos_weight; a.pl_wneg = c.pl_neg_weight;
+    a.inv_npix = (float)(1.0 / ((double)c.nframes * (double)a.P));
+    a.inv_h = 1.0f / (float)c.H; a.inv_w = 1.0f / (float)c.W;
+}
 
 #define MASK_K_SWITCH(fn, ...)                     \
     switch (K) {                                   \
@@ -187,37 +280,47 @@ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 extern "C" int rcf_mask_prep_workspace_floats(int nframes, int P, size_t* nfloats) {
     if (!nfloats) return RCF_ERR_NULL;
     if (nframes < 1 || P < 1) return RCF_ERR_SHAPE;
-    *nfloats = (size_t)nframes * ((P + MASK_CHUNK - 1) / MASK_CHUNK);
+    *nfloats = (size_t)nframes * ((P + MASK_CHUNK - 1) / MASK_CHUNK) * MASK_NP;
     return RCF_OK;
 }
 
-extern "C" int rcf_mask_prep_forward(const float* logits, float* masks, float* entropy, float* ws, int nframes, int K, int P,
-                                     void* stream) {
-    const int v = mask_check(nframes, K, P);
+extern "C" int rcf_mask_losses_forward(const RcfMaskCfg* cfg, const float* logits, const float* target, float* masks,
+                                       float* losses, float* frame_stats, float* ws, void* stream) {
+    if (!cfg) return RCF_ERR_NULL;
+    const int K = cfg->K;
+    const int v = mask_check(cfg->nframes, K, cfg->H, cfg->W);
     if (v != RCF_OK) return v;
-    if (!logits || !masks || !entropy || !ws) return RCF_ERR_NULL;
+    if (!logits || !masks || !losses || !ws) return RCF_ERR_NULL;
     MaskK a{};
-    a.logits = logits; a.masks = masks; a.entropy = entropy; a.part = ws;
-    a.nframes = nframes; a.P = P; a.nchunk = (P + MASK_CHUNK - 1) / MASK_CHUNK;
-    a.inv_npix = (float)(1.0 / ((double)nframes * (double)P));
-    const bool vec = P % 4 == 0 && al16(logits) && al16(masks);
+    fill_cfg(a, *cfg);
+    if (a.compact_ch >= 0 && !frame_stats) return RCF_ERR_NULL;
+    a.logits = logits; a.masks = masks; a.losses = losses; a.part = ws; a.fstats = frame_stats;
+    a.target = (a.pl_ch >= 0) ? target : nullptr;
+    if (a.pl_ch >= 0 && !target) return RCF_ERR_NULL;
+    const bool vec = a.P % 4 == 0 && al16(logits) && al16(masks) && (!a.target || al16(a.target));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaErrorInvalidValue;
     MASK_K_SWITCH(launch_fwd, a, vec, s)
     if (e != cudaSuccess) return (int)e;
-    return (int)rcf_launch(k_mask_entropy_final, 1, 256, 0, s, rcf_pdl_enabled(), a);
+    return (int)rcf_launch(k_mask_final, 1, 256, 0, s, rcf_pdl_enabled(), a);
 }
 
-extern "C" int rcf_mask_prep_backward(const float* masks, const float* grad_masks, const float* grad_entropy, float* dlogits,
-                                      int nframes, int K, int P, void* stream) {
-    const int v = mask_check(nframes, K, P);
+extern "C" int rcf_mask_losses_backward(const RcfMaskCfg* cfg, const float* masks, const float* target,
+                                        const float* grad_masks, const float* grad_losses, const float* frame_stats,
+                                        float* dlogits, void* stream) {
+    if (!cfg) return RCF_ERR_NULL;
+    const int K = cfg->K;
+    const int v = mask_check(cfg->nframes, K, cfg->H, cfg->W);
     if (v != RCF_OK) return v;
     if (!masks || !dlogits) return RCF_ERR_NULL;
     MaskK a{};
-    a.masks = const_cast<float*>(masks); a.gmasks = grad_masks; a.gent = grad_entropy; a.dlogits = dlogits;
-    a.nframes = nframes; a.P = P; a.nchunk = (P + MASK_CHUNK - 1) / MASK_CHUNK;
-    a.inv_npix = (float)(1.0 / ((double)nframes * (double)P));
-    const bool vec = P % 4 == 0 && al16(masks) && al16(dlogits) && (!grad_masks || al16(grad_masks));
+    fill_cfg(a, *cfg);
+    a.masks = const_cast<float*>(masks); a.gmasks = grad_masks; a.glosses = grad_losses; a.dlogits = dlogits;
+    a.fstats = const_cast<float*>(frame_stats);
+    a.target = (a.pl_ch >= 0) ? target : nullptr;
+    if (a.pl_ch >= 0 && !target) return RCF_ERR_NULL;
+    if (a.compact_ch >= 0 && grad_losses && !frame_stats) return RCF_ERR_NULL;
+    const bool vec = a.P % 4 == 0 && al16(masks) && al16(dlogits) && (!grad_masks || al16(grad_masks)) && (!a.target || al16(a.target));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaErrorInvalidValue;
     MASK_K_SWITCH(launch_bwd, a, vec, s)
