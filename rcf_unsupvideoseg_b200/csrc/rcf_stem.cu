@@ -235,15 +235,32 @@ constexpr int STEM_MMA_CF = 64;
 // words, so the MMA operands that come from it cost two LDS and no ALU work.  The loads of the NEXT tile are issued
 // before the current tile is computed and committed to shared memory afterwards (software pipeline: the HBM latency of
 // this read-once input is hidden behind the MMAs instead of being paid at a barrier).
+// tile index -> (image, tile origin) without integer divisions (they cost ~25 instructions each, per thread and tile):
+// float reciprocal + one correction step, exact for the < 2^22 tiles a launch can have
+struct TileDecode {
+    int tx, tpi;
+    float inv_tx, inv_tpi;
+    __device__ __forceinline__ TileDecode(int tx_, int ty_) : tx(tx_), tpi(tx_ * ty_), inv_tx(1.0f / (float)tx_), inv_tpi(1.0f / (float)(tx_ * ty_)) {}
+    static __device__ __forceinline__ int fdiv(int x, int d, float inv) {
+        int q = (int)((float)x * inv);
+        q -= (q * d > x) ? 1 : 0;
+        q += ((q + 1) * d <= x) ? 1 : 0;
+        return q;
+    }
+    __device__ __forceinline__ void operator()(int tl, int& n, int& y0, int& x0) const {
+        n = fdiv(tl, tpi, inv_tpi);
+        const int r = tl - n * tpi, yi = fdiv(r, tx, inv_tx);
+        y0 = yi * STEM_TH; x0 = (r - yi * tx) * STEM_TW;
+    }
+};
+
 template <int KS>
 struct StemTile {
     static constexpr int SW = STEM_TW + KS - 1, SH = STEM_TH + KS - 1, TSZ = 2 * SH * SW, R = (KS - 1) / 2;
     static constexpr int NE = (TSZ + RCF_BLOCK - 1) / RCF_BLOCK;
     float pre[NE];
-    __device__ __forceinline__ void fetch(const StemK& a, int tl, int tx, int ty) {
-        const int n = tl / (tx * ty), r = tl - n * tx * ty;
-        const int y0 = (r / tx) * STEM_TH, x0 = (r - (r / tx) * tx) * STEM_TW;
-        const int dir = n / a.B, b = n - dir * a.B;
+    __device__ __forceinline__ void fetch(const StemK& a, int n, int y0, int x0) {
+        const int dir = n >= a.B ? 1 : 0, b = n - dir * a.B;
         const float* __restrict__ fl = (dir ? a.flow[1] : a.flow[0]) + (long long)b * (dir ? a.flow_bs[1] : a.flow_bs[0]);
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
@@ -324,15 +341,18 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
     if (tid == 0) { Thi[TSZ] = __float_as_uint(1.0f); Tlo[TSZ] = 0u; Thi[TSZ + 1] = 0u; Tlo[TSZ + 1] = 0u; }
 
     TL st;
-    int tl = blockIdx.x;
-    if (tl < a.ntiles) st.fetch(a, tl, tx, ty);
+    const TileDecode dec(tx, ty);
+    int tl = blockIdx.x, n = 0, y0 = 0, x0 = 0, nn = 0, ny0 = 0, nx0 = 0;
+    if (tl < a.ntiles) { dec(tl, nn, ny0, nx0); st.fetch(a, nn, ny0, nx0); }
     for (; tl < a.ntiles; tl += gridDim.x) {
-        const int n = tl / (tx * ty), r = tl - n * tx * ty;
-        const int y0 = (r / tx) * STEM_TH, x0 = (r - (r / tx) * tx) * STEM_TW;
+        n = nn; y0 = ny0; x0 = nx0;
         __syncthreads();                               // previous tile fully consumed
         st.commit(a, Thi, Tlo);
         __syncthreads();
-        if (tl + (int)gridDim.x < a.ntiles) st.fetch(a, tl + gridDim.x, tx, ty);     // in flight while this tile is computed
+        if (tl + (int)gridDim.x < a.ntiles) {          // next tile's loads in flight while this tile is computed
+            dec(tl + gridDim.x, nn, ny0, nx0);
+            st.fetch(a, nn, ny0, nx0);
+        }
         float* const img = a.act + (long long)n * a.P * Cf + half * 32 + 4 * t;
         uint32_t* const simg = a.sign_out ? a.sign_out + (long long)n * a.P * 2 + half : nullptr;
 #pragma unroll 1
@@ -420,36 +440,43 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_bwd_mma(c
     if (tid == 0) { Thi[TSZ] = __float_as_uint(1.0f); Tlo[TSZ] = 0u; Thi[TSZ + 1] = 0u; Tlo[TSZ + 1] = 0u; }
 
     TL st;
-    int tl = blockIdx.x;
-    if (tl < a.ntiles) st.fetch(a, tl, tx, ty);
+    const TileDecode dec(tx, ty);
+    int tl = blockIdx.x, n = 0, y0 = 0, x0 = 0, nn = 0, ny0 = 0, nx0 = 0;
+    if (tl < a.ntiles) { dec(tl, nn, ny0, nx0); st.fetch(a, nn, ny0, nx0); }
+    const long long rstride = (long long)a.W * Cf;     // one image row of dact, in floats
     for (; tl < a.ntiles; tl += gridDim.x) {      // fixed tile -> CTA assignment (reproducible)
-        const int n = tl / (tx * ty), r = tl - n * tx * ty;
-        const int y0 = (r / tx) * STEM_TH, x0 = (r - (r / tx) * tx) * STEM_TW;
+        n = nn; y0 = ny0; x0 = nx0;
         __syncthreads();
         st.commit(a, Thi, Tlo);
         __syncthreads();
-        if (tl + (int)gridDim.x < a.ntiles) st.fetch(a, tl + gridDim.x, tx, ty);
-        const float* const dimg = a.dact + (long long)n * a.P * Cf + half * 32 + 4 * g;
-        const uint32_t* const simg = a.sign_in + (long long)n * a.P * 2 + half;
+        if (tl + (int)gridDim.x < a.ntiles) {
+            dec(tl + gridDim.x, nn, ny0, nx0);
+            st.fetch(a, nn, ny0, nx0);
+        }
+        // this warp always works on the column block lx0 = 8 * gset of the tile and walks its 8 rows (group q = gset + 4 * ly)
+        const int lx0 = gset * 8, xA = x0 + lx0 + t;
+        const bool inx[2] = {xA < a.W, xA + 4 < a.W};
+        const float* const dcol = a.dact + ((long long)n * a.P + (long long)y0 * a.W + xA) * Cf + half * 32 + 4 * g;
+        const uint32_t* const scol = a.sign_in + ((long long)n * a.P + (long long)y0 * a.W + xA) * 2 + half;
 #pragma unroll 1
         for (int i0 = 0; i0 < 8; i0 += GB) {
             float4 d4[GB][2];
             uint32_t sg[GB][2];
 #pragma unroll
             for (int u = 0; u < GB; ++u) {
-                const int q = gset + 4 * (i0 + u), ly = q >> 2, lx0 = (q & 3) * 8;
-                const int y = y0 + ly, xA = x0 + lx0 + t;
+                const bool iny = y0 + i0 + u < a.H;
+                const float* dp = dcol + (long long)(i0 + u) * rstride;
+                const uint32_t* sp = scol + (long long)(i0 + u) * a.W * 2;
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const bool in = y < a.H && xA + 4 * e < a.W;
-                    const int pofs = y * a.W + xA + 4 * e;
-                    d4[u][e] = in ? __ldg(reinterpret_cast<const float4*>(dimg + (long long)pofs * Cf)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    sg[u][e] = in ? __ldg(simg + (long long)pofs * 2) : 0u;
+                    const bool in = iny && inx[e];
+                    d4[u][e] = in ? __ldg(reinterpret_cast<const float4*>(dp + 4 * e * Cf)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    sg[u][e] = in ? __ldg(sp + 8 * e) : 0u;
                 }
             }
 #pragma unroll
             for (int u = 0; u < GB; ++u) {
-                const int q = gset + 4 * (i0 + u), ly = q >> 2, lx0 = (q & 3) * 8;
+                const int ly = i0 + u;
                 if (y0 + ly >= a.H || x0 + lx0 >= a.W) continue;          // warp-uniform
                 float v[2][4];
 #pragma unroll

@@ -7,6 +7,10 @@ import collections
 import os
 import sys
 
+# per-kernel durations are only exclusive without programmatic dependent launch (a dependent kernel that was scheduled
+# early would be charged for the time it spends waiting for its predecessor)
+os.environ.setdefault("RCF_PDL", "0")
+
 import torch
 from torch.profiler import ProfilerActivity, profile
 
