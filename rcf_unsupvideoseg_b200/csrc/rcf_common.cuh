@@ -101,7 +101,7 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.poolchunk = pc;
     L.nblkpb = (L.P + L.pooltp - 1) / L.pooltp;
     L.w_dbpart = o;  o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * L.nblkpb * d.Cf * sizeof(float) : 0));   // per-CTA bias-gradient partials
-    L.w_dbfd = o;    o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * d.Cf * sizeof(double) : 0));
+    L.w_dbfd = o;    o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * 16 * d.Cf * sizeof(double) : 0));   // <= 16 splits per fd
     L.w_poolsum = o; o = rcf_align256(o + nseg * d.Cf * sizeof(double));
     L.w_bytes = o ? o : 256;
     return L;
@@ -162,7 +162,7 @@ struct RcfK {
     float *dw1, *db1, *dw2, *db2;
     float* dfeat_bias;        // [Cf] or null
     float* dbpart;            // ws: [nfd][nblkpb][Cf]
-    double* dbfd;             // ws: [nfd][Cf]
+    double* dbfd;             // ws: [nfd * S][Cf], S <= 16 splits of the partial rows
     double* poolsum;          // ws: [nfd][Cf*K] pooled sums (un-normalised), reduced over chunks by k_pool_reduce
     int nblkpb;
     int poolchunk, pooltp;    // pixels per CTA of k_pool_nhwc / k_pool_bwd_nhwc
