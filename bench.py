@@ -505,7 +505,79 @@ def extras(pkg, dev):
         except Exception as ex:  # noqa: BLE001
             out[name] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
             torch.cuda.empty_cache()
+    out.update(caller_side_step(pkg, dev))
     return out
+
+
+def caller_side_step(pkg, dev):
+    """The caller-side slice of RCFModel.forward_train around the head at the DAVIS stage-1 training shape
+    (configs/rcf/rcf_stage1.yaml: B=8, mask_size 96x96, residual predicted at 48x48, w_seg 1, w_entropy 0.05):
+    logits -> softmax (+ log_softmax of it, entropy loss) -> head (residual resize 48->96 inside) -> total loss ->
+    gradients w.r.t. logits, residuals and head parameters.  ours = mask_losses + drop-in head; baseline = the ATen op
+    sequence of models/rcf_model.py:433-434, :376-378 + the op-for-op port of the head, eager on the same GPU."""
+    import torch
+    import torch.nn.functional as F
+
+    from oracle.torch_port import PortedHead
+    from rcf_unsupvideoseg_b200.mask_ops import mask_losses
+    name = "davis_stage1_caller_side_step_B8_96x96_resid48"
+    try:
+        B_, K_, H_, W_ = 8, 4, 96, 96
+        g = torch.Generator(device=dev).manual_seed(0)
+        logits = (torch.randn(B_, 2, K_, H_, W_, device=dev, generator=g) * 2).requires_grad_(True)
+        fw = torch.randn(B_, 1, 2, H_, W_, device=dev, generator=g) * 8
+        bw = torch.randn(B_, 1, 2, H_, W_, device=dev, generator=g) * 8
+        r1 = (torch.randn(B_, 2 * K_, H_ // 2, W_ // 2, device=dev, generator=g) * 5).requires_grad_(True)
+        r2 = (torch.randn(B_, 2 * K_, H_ // 2, W_ // 2, device=dev, generator=g) * 5).requires_grad_(True)
+        imgs = torch.zeros(B_, 2, 3, 8, 8)
+        kw = dict(mask_layer=K_, mask_size=(H_, W_), free_residual=True, clamp_flow_t=20.0, allow_residual_resize=True)
+        res = {}
+        for impl in ("ours", "torch_eager_port"):
+            torch.manual_seed(1)
+            if impl == "ours":
+                head = pkg.FlowAggregationHeadWithResidual(args=None, create_flownet=True, **kw).to(dev)
+                head.return_flows = False
+            else:
+                head = PortedHead(**kw).to(dev)
+            params = list(head.parameters())
+
+            def fn():
+                if impl == "ours":
+                    masks, ml = mask_losses(logits)
+                    ent = ml["entropy"]
+                else:
+                    masks = F.softmax(logits, dim=2)
+                    ent = -(masks * F.log_softmax(masks, dim=2)).sum(dim=2).mean()
+                _, l = head(imgs, masks, fw, bw, r1, r2)
+                torch.autograd.grad(l["seg"] + 0.05 * ent, [logits, r1, r2, *params])
+
+            ms = _time_cuda(fn, 50)
+            res[impl] = {"ms_per_step": ms, "samples_per_s": B_ / ms * 1e3}
+            if impl == "ours":
+                try:      # the same step replayed from one CUDA graph
+                    import gc
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        fn()
+                    torch.cuda.current_stream().wait_stream(side)
+                    gc.collect()
+                    torch.cuda.synchronize()
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg):
+                        fn()
+                    ms_g = _time_cuda(cg.replay, 50)
+                    res["ours_cuda_graph"] = {"ms_per_step": ms_g, "samples_per_s": B_ / ms_g * 1e3}
+                except Exception as ex:  # noqa: BLE001
+                    res["ours_cuda_graph"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+                    torch.cuda.synchronize()
+            del head, params
+            torch.cuda.empty_cache()
+        res["speedup_vs_torch_eager"] = res["torch_eager_port"]["ms_per_step"] / res["ours"]["ms_per_step"]
+        return {name: res}
+    except Exception as ex:  # noqa: BLE001
+        torch.cuda.empty_cache()
+        return {name: {"error": f"{type(ex).__name__}: {ex}"[:200]}}
 
 
 def main():
