@@ -46,7 +46,10 @@ def test_ctypes_structs_match_c_layout():
 #include "rcf_loss.h"
 #define F(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
 int main(void) {
-  printf("RcfDesc %zu\nRcfInputs %zu\nRcfVisOut %zu\nRcfGrads %zu\n", sizeof(RcfDesc), sizeof(RcfInputs), sizeof(RcfVisOut), sizeof(RcfGrads));
+  printf("RcfDesc %zu\nRcfInputs %zu\nRcfVisOut %zu\nRcfGrads %zu\nRcfMaskCfg %zu\n", sizeof(RcfDesc), sizeof(RcfInputs), sizeof(RcfVisOut), sizeof(RcfGrads), sizeof(RcfMaskCfg));
+  F(RcfDesc,grad_loss_total);
+  F(RcfMaskCfg,nframes); F(RcfMaskCfg,K); F(RcfMaskCfg,H); F(RcfMaskCfg,W); F(RcfMaskCfg,compact_channel); F(RcfMaskCfg,pl_channel);
+  F(RcfMaskCfg,pl_threshold); F(RcfMaskCfg,pl_pos_weight); F(RcfMaskCfg,pl_neg_weight);
   F(RcfDesc,B); F(RcfDesc,K); F(RcfDesc,H); F(RcfDesc,W); F(RcfDesc,Cf); F(RcfDesc,D); F(RcfDesc,ndir); F(RcfDesc,theta_mode);
   F(RcfDesc,robust); F(RcfDesc,unbounded_residual); F(RcfDesc,eps); F(RcfDesc,q); F(RcfDesc,resid_scale); F(RcfDesc,pred_div);
   F(RcfDesc,clamp_t); F(RcfDesc,inv_n); F(RcfDesc,mask_bstride); F(RcfDesc,flow_bstride); F(RcfDesc,resid_bstride);
@@ -63,7 +66,8 @@ int main(void) {
         exe = os.path.join(td, "layout")
         subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
         out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
-    structs = {"RcfDesc": _lib.RcfDesc, "RcfInputs": _lib.RcfInputs, "RcfVisOut": _lib.RcfVisOut, "RcfGrads": _lib.RcfGrads}
+    structs = {"RcfDesc": _lib.RcfDesc, "RcfInputs": _lib.RcfInputs, "RcfVisOut": _lib.RcfVisOut, "RcfGrads": _lib.RcfGrads,
+               "RcfMaskCfg": _lib.RcfMaskCfg}
     for line in out.splitlines():
         name, val = line.split()
         if "." in name:

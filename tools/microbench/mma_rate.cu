@@ -27,6 +27,11 @@ __global__ void __launch_bounds__(256) k(float* out, long long* clk) {
             else if (MODE == 3)
                 asm volatile("mma.sync.aligned.m16n8k4.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                              : "+f"(d[c][0]), "+f"(d[c][1]), "+f"(d[c][2]), "+f"(d[c][3]) : "r"(a0), "r"(a1), "r"(b0));
+            else if (MODE == 6) {       // packed fp32x2 FMA (sm_100 FFMA2): 2 per chain slot = 4 FMAs per lane
+                float2* ff = reinterpret_cast<float2*>(d[c]);
+                ff[0] = __ffma2_rn(ff[0], make_float2(1.0001f, 1.0002f), make_float2(0.5f, 0.25f));
+                ff[1] = __ffma2_rn(ff[1], make_float2(1.0001f, 1.0002f), make_float2(0.5f, 0.25f));
+            }
             else if (MODE == 5) {       // fp64 FMA: 2 per chain slot (d[c][0..1] and d[c][2..3] viewed as doubles)
                 double* dd = reinterpret_cast<double*>(d[c]);
                 dd[0] = fma(dd[0], 1.0001, 0.5);
@@ -71,6 +76,7 @@ int main() {
         run<2>("mma.m16n8k16 f16", 16 * 8 * 16, c);
         run<4>("ffma x4 (per lane)", 32 * 4, c);
         run<5>("dfma x2 (per lane)", 32 * 2, c);
+        run<6>("ffma2 x2 (per lane)", 32 * 4, c);
     }
     return 0;
 }
