@@ -148,6 +148,25 @@ def load_library(build_if_missing: bool = True):
     return _lib
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(dev):
+    """`with torch.cuda.device(dev)` only when dev is not already current: the context manager costs ~10 us of host time
+    per use, and a step of the drop-in head enters it 8 times (launch-bound at the 96x96 / 48x48 training shapes)."""
+    import torch
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return _NO_GUARD if torch.cuda.current_device() == idx else torch.cuda.device(idx)
+
+
 def check(code: int, what: str):
     if code != 0:
         msg = load_library().rcf_error_string(code).decode()

@@ -194,7 +194,7 @@ class RcfMotionLossFn(torch.autograd.Function):
             desc.vis_scale[0], desc.vis_scale[1] = spec.vis_scale
 
         stream = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(lib.rcf_forward(C.byref(desc), C.byref(inp), loss_buf.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
                                        C.byref(vis_struct) if vis_struct is not None else None, stream), "rcf_forward")
 
@@ -295,7 +295,7 @@ class RcfMotionLossFn(torch.autograd.Function):
                 gl = gl + grad_total.detach().to(torch.float32)
             gl = gl.contiguous()
         stream = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(lib.rcf_backward(C.byref(desc), C.byref(inp), gl.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
                                         C.byref(grads), stream), "rcf_backward")
         return (None, d_masks, d_feat, d_fb, *dw, *([None] * ndir), *d_resids, *d_thetas)

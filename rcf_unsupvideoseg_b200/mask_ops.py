@@ -43,7 +43,7 @@ class _MaskLossesFn(torch.autograd.Function):
         n = C.c_size_t()
         _lib.check(lib.rcf_mask_prep_workspace_floats(B * I, H * W, C.byref(n)), "rcf_mask_prep_workspace_floats")
         ws = torch.empty(n.value, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib.check(lib.rcf_mask_losses_forward(C.byref(cfg), x.data_ptr(), tgt.data_ptr() if tgt is not None else None,
                                                    masks.data_ptr(), losses.data_ptr(), fstats.data_ptr(), ws.data_ptr(),
                                                    torch.cuda.current_stream(x.device).cuda_stream), "rcf_mask_losses_forward")
@@ -63,7 +63,7 @@ class _MaskLossesFn(torch.autograd.Function):
         gm = g_masks.float().contiguous() if g_masks is not None else None
         gl = g_losses.detach().float().contiguous() if g_losses is not None else None
         dl = torch.empty_like(masks)
-        with torch.cuda.device(masks.device):
+        with _lib.device_guard(masks.device):
             _lib.check(lib.rcf_mask_losses_backward(C.byref(ctx.cfg), masks.data_ptr(), rest[0].data_ptr() if rest else None,
                                                     gm.data_ptr() if gm is not None else None,
                                                     gl.data_ptr() if gl is not None else None, fstats.data_ptr(),

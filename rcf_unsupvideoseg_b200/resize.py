@@ -33,7 +33,7 @@ class _ResizeFn(torch.autograd.Function):
         H, W = int(size[0]), int(size[1])
         xv = [x.detach().float().contiguous() for x in xs]
         outs = [torch.empty(B, Cc, H, W, dtype=torch.float32, device=x0.device) for _ in xs]
-        with torch.cuda.device(x0.device):
+        with _lib.device_guard(x0.device):
             _lib.check(lib.rcf_resize_bilinear_forward(_ptrs(xv), _ptrs(outs), len(xs), B * Cc, h, w, H, W,
                                                        int(bool(align_corners)),
                                                        torch.cuda.current_stream(x0.device).cuda_stream),
@@ -52,7 +52,7 @@ class _ResizeFn(torch.autograd.Function):
         if idx:
             gv = [gs[i].float().contiguous() for i in idx]
             gi = [torch.empty(B, Cc, h, w, dtype=torch.float32, device=gv[0].device) for _ in idx]
-            with torch.cuda.device(gv[0].device):
+            with _lib.device_guard(gv[0].device):
                 _lib.check(lib.rcf_resize_bilinear_backward(_ptrs(gv), _ptrs(gi), len(idx), B * Cc, h, w, H, W, int(align),
                                                             torch.cuda.current_stream(gv[0].device).cuda_stream),
                            "rcf_resize_bilinear_backward")

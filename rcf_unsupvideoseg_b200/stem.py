@@ -48,7 +48,7 @@ class _StemFn(torch.autograd.Function):
         sign = torch.empty(ndir * B * H * W * 2, dtype=torch.int32, device=dev) if Cf == 64 else None
         ptrs = (C.c_void_p * 2)(*[f.data_ptr() for f in fl], *([None] * (2 - ndir)))
         strides = (C.c_int64 * 2)(*[f.stride(0) for f in fl], *([0] * (2 - ndir)))
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(lib.rcf_stem_forward(ptrs, strides, ndir, B, H, W, Cf, ks, w.data_ptr(), b.data_ptr(),
                                             float(clamp_t), float(slope), act.data_ptr(),
                                             sign.data_ptr() if sign is not None else None,
@@ -73,7 +73,7 @@ class _StemFn(torch.autograd.Function):
         db = torch.empty(Cf, dtype=torch.float32, device=dev)
         ptrs = (C.c_void_p * 2)(*[f.data_ptr() for f in fl], *([None] * (2 - ndir)))
         strides = (C.c_int64 * 2)(*[f.stride(0) for f in fl], *([0] * (2 - ndir)))
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(lib.rcf_stem_backward(ptrs, strides, ndir, B, H, W, Cf, ks, clamp_t, slope,
                                              None if ctx.has_sign else kept.data_ptr(),
                                              kept.data_ptr() if ctx.has_sign else None, g.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),

@@ -43,7 +43,7 @@ class _FlowWarpFn(torch.autograd.Function):
         B, C, H, W = xc.shape
         assert fc.shape == (B, 2, H, W), f"flow shape {tuple(fc.shape)} vs input {tuple(xc.shape)}"
         out = torch.empty_like(xc)
-        with torch.cuda.device(xc.device):
+        with _lib.device_guard(xc.device):
             _lib.check(lib.rcf_flow_warp_forward(xc.data_ptr(), fc.data_ptr(), out.data_ptr(), B, C, H, W, int(border),
                                                  torch.cuda.current_stream(xc.device).cuda_stream), "rcf_flow_warp_forward")
         ctx.save_for_backward(xc, fc)
@@ -59,7 +59,7 @@ class _FlowWarpFn(torch.autograd.Function):
         g = gout.float().contiguous()
         gx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
         gf = torch.empty_like(fc) if ctx.needs_input_grad[1] else None
-        with torch.cuda.device(xc.device):
+        with _lib.device_guard(xc.device):
             _lib.check(lib.rcf_flow_warp_backward(xc.data_ptr(), fc.data_ptr(), g.data_ptr(),
                                                   gx.data_ptr() if gx is not None else None,
                                                   gf.data_ptr() if gf is not None else None, B, C, H, W, int(ctx.border),
@@ -85,7 +85,7 @@ def get_corresponding_map(data):
     B, _, H, W = d.shape
     out = torch.empty(B, 1, H, W, dtype=torch.float32, device=d.device)
     scratch = torch.empty(B * H * W, dtype=torch.int64, device=d.device)
-    with torch.cuda.device(d.device):
+    with _lib.device_guard(d.device):
         _lib.check(lib.rcf_corresponding_map(d.data_ptr(), out.data_ptr(), scratch.data_ptr(), B, H, W,
                                              torch.cuda.current_stream(d.device).cuda_stream), "rcf_corresponding_map")
     return out.type_as(data)
