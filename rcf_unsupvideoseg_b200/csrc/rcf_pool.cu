@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
 // the latter reduced over the Cf/4 threads of a pixel with shuffles and accumulated in a shared tile that is written
 // back to the NCHW gradient planes with coalesced stores.
 template <int K>
-__global__ void __launch_bounds__(RCF_BLOCK) k_pool_bwd_nhwc(const RcfK a) {
+__global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
     rcf_pdl_prologue();
     const int TP = a.pooltp;                 // pixels per CTA
     extern __shared__ float sm[];
