@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
 //   dW2[c][j] = sum_s thbar[s][c] * lrelu(hpre[s][j]),  db2[c] = sum_s thbar[s][c]         (last block)
 // The operands are staged through shared memory in chunks of SC segments with coalesced loads (one global round trip
 // per chunk instead of one per term) and every output is accumulated by ONE thread in segment order: deterministic.
-constexpr int MPG_RB = 4, MPG_SC = 32;
+constexpr int MPG_RB = 4, MPG_SC = 64;
 __global__ void __launch_bounds__(256) k_mlp_param_grad(const RcfK a) {
     rcf_pdl_prologue();
     const int Cf = a.Cf, nseg = a.nfd * a.K, tid = threadIdx.x;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) k_mlp_param_grad(const RcfK a) {
     for (int s0 = 0; s0 < nseg; s0 += MPG_SC) {
         const int ns = min(MPG_SC, nseg - s0);
         __syncthreads();
-        double lv = 0.0;                                  // ns * nrow <= 128: one element per thread
+        double lv = 0.0;                                  // ns * nrow <= 256: one element per thread
         if (tid < ns * nrow) {
             const int s = tid / nrow, r = tid - s * nrow;
             lv = w2blk ? __ldcg(a.thbar + (size_t)(s0 + s) * 2 + r) : __ldcg(a.dh + (size_t)(s0 + s) * Cf + i0 + r);

@@ -23,7 +23,9 @@ ap.add_argument("--H", type=int, default=96); ap.add_argument("--W", type=int, d
 ap.add_argument("--Cf", type=int, default=64); ap.add_argument("--ks", type=int, default=3)
 ap.add_argument("--affine", action="store_true"); ap.add_argument("--resize", action="store_true")
 ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--cudnn-benchmark", action="store_true", help="torch.backends.cudnn.benchmark = True (algorithm search)")
 a = ap.parse_args()
+torch.backends.cudnn.benchmark = bool(a.cudnn_benchmark)
 dev = torch.device("cuda")
 B, K, H, W = a.B, a.K, a.H, a.W
 kw = dict(free_residual_with_affine=True) if a.affine else dict(free_residual=True)
