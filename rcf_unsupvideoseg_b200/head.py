@@ -30,8 +30,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .function import LossSpec, rcf_motion_loss
+from .conv_overlap import conv2d_dual_stream
 from .resize import resize_bilinear_multi
-from .stem import flow_stem, stem_supported
+from .stem import flow_stem, flow_stem_conv, stem_supported
 
 logger = logging.getLogger("main")
 
@@ -142,6 +143,12 @@ class FlowAggregationHeadWithResidual(nn.Module):
         self.channels_last_features = True
         #   handwritten_stem=False sends the first conv + LeakyReLU through cuDNN/ATen instead of csrc/rcf_stem.cu.
         self.handwritten_stem = True
+        #   overlap_conv_backward=True (experiment, off): stem + second conv become one autograd node whose backward issues the
+        #   conv's weight gradient on a side stream beside its data gradient + the stem's gradients (stem.py::_StemConvFn,
+        #   conv_overlap.py).  Measured on B200 at the training shapes: -1..-2 % inside a CUDA graph (the cuDNN kernels
+        #   already occupy every SM, there is little left to overlap) and +15-20 % host time per eager step (stream
+        #   switches), so the default stays the plain single-stream backward.
+        self.overlap_conv_backward = False
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -181,8 +188,14 @@ class FlowAggregationHeadWithResidual(nn.Module):
         if self._use_channels_last() and stem_flows is not None and self.handwritten_stem \
                 and stem_supported(self.num_flow_feat_channels, seq[0].kernel_size[0]) and seq[0].bias is not None:
             c2 = seq[2]
-            act1 = flow_stem(stem_flows, seq[0].weight, seq[0].bias, stem_clamp, seq[1].negative_slope)
-            feat = F.conv2d(act1, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
+            if self.overlap_conv_backward and torch.is_grad_enabled() and c2.weight.requires_grad \
+                    and (seq[0].weight.requires_grad or seq[0].bias.requires_grad):
+                # stem + conv2 as one autograd node whose backward runs conv2's wgrad beside dgrad + stem gradients
+                feat = flow_stem_conv(stem_flows, seq[0].weight, seq[0].bias, stem_clamp, seq[1].negative_slope,
+                                      c2.weight, c2.stride, c2.padding, c2.dilation, c2.groups)
+            else:
+                act1 = flow_stem(stem_flows, seq[0].weight, seq[0].bias, stem_clamp, seq[1].negative_slope)
+                feat = self._conv2(act1, c2)
             if c2.bias is None:
                 return feat, None
             if feat.is_contiguous(memory_format=torch.channels_last):
@@ -198,13 +211,19 @@ class FlowAggregationHeadWithResidual(nn.Module):
             # removes ATen's separate bias-add and bias-gradient reduction kernels over the [B,Cf,H,W] map.
             flow = flow.contiguous(memory_format=torch.channels_last)
             c2 = seq[2]
-            feat = F.conv2d(seq[1](seq[0](flow)), c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
+            feat = self._conv2(seq[1](seq[0](flow)), c2)
             if c2.bias is None:
                 return feat, None
             if feat.is_contiguous(memory_format=torch.channels_last):
                 return feat, c2.bias
             return feat + c2.bias.view(1, -1, 1, 1), None       # cuDNN answered in NCHW: plain bias add
         return seq[2](seq[1](seq[0](flow))), None
+
+    def _conv2(self, x, c2):
+        """bias-free second conv; with overlap_conv_backward its data- and weight-gradient kernels run on two streams."""
+        if self.overlap_conv_backward and x.is_cuda and torch.is_grad_enabled() and (x.requires_grad or c2.weight.requires_grad):
+            return conv2d_dual_stream(x, c2.weight, c2.stride, c2.padding, c2.dilation, c2.groups)
+        return F.conv2d(x, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
 
     @staticmethod
     def _clamped(f, t):
