@@ -201,6 +201,13 @@ RCF_API int rcf_resize_bilinear_forward(const float* const* in, float* const* ou
 RCF_API int rcf_resize_bilinear_backward(const float* const* grad_out, float* const* grad_in, int nten, int planes, int h,
                                          int w, int H, int W, int align_corners, void* stream);
 
+/* RAFT flow staging: in [N, h, w, C] (HWC as np.load returns it, dataset/data.py:114-133; C <= 4) -> out [N, C, H, W]:
+ * per-channel scale (HOST float[C] or NULL; FlowTransform.scale_flow, dataset/transforms.py:842-849), HWC -> CHW
+ * (np.transpose(flow, (2,0,1)), :850) and the bilinear resize to mask_size (models/rcf_model.py:438-442) in one pass.
+ * No gradient: the RAFT flow is ground truth. */
+RCF_API int rcf_flow_stage_hwc(const float* in, float* out, int N, int C, int h, int w, int H, int W, int align_corners,
+                               const float* channel_scale_host, void* stream);
+
 /* ---- caller-side mask preparation and mask losses ------------------------------------------------
  * Reference: models/rcf_model.py:433-434 (softmax over K, log-softmax OF the result), :376-378 (entropy loss),
  * :380-408 (PL / CRF positive/negative weighted MSE on the object channel), models/compactness_head.py:33-56

@@ -63,7 +63,7 @@ class RcfGrads(C.Structure):
 EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "rcf_forward", "rcf_backward",
                     "rcf_debug_time_kernel", "rcf_flow_warp_forward", "rcf_flow_warp_backward", "rcf_corresponding_map",
                     "rcf_debug_set_option", "rcf_stem_forward", "rcf_stem_workspace_bytes", "rcf_stem_backward",
-                    "rcf_resize_bilinear_forward", "rcf_resize_bilinear_backward",
+                    "rcf_resize_bilinear_forward", "rcf_resize_bilinear_backward", "rcf_flow_stage_hwc",
                     "rcf_mask_prep_workspace_floats", "rcf_mask_losses_forward", "rcf_mask_losses_backward")
 
 _lib = None
@@ -130,6 +130,9 @@ def load_library(build_if_missing: bool = True):
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                            C.c_int, C.c_int, C.c_void_p]
+        lib.rcf_flow_stage_hwc.restype = C.c_int
+        lib.rcf_flow_stage_hwc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.POINTER(C.c_float), C.c_void_p]
         lib.rcf_mask_prep_workspace_floats.restype = C.c_int
         lib.rcf_mask_prep_workspace_floats.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         lib.rcf_mask_losses_forward.restype = C.c_int

@@ -145,6 +145,38 @@ __global__ void __launch_bounds__(256) k_resize_bwd_2x(const ResizeK a) {
     gi[p] = acc;
 }
 
+// RAFT flows as stored on disk / produced by the loader: [N, h, w, C] (HWC, C = 2; dataset/data.py:114-133), optionally
+// scaled per channel (FlowTransform.scale_flow, dataset/transforms.py:831-851), transposed to NCHW (np.transpose(flow,
+// (2,0,1)), :850) and resized to mask_size (models/rcf_model.py:438-442) -- three passes in the reference, one here.
+// One thread per output pixel; the C channels of a source pixel are adjacent, so the four taps are four short vector reads.
+struct StageK {
+    const float* src;     // [N, h, w, C]
+    float* dst;           // [N, C, H, W]
+    int C, h, w, H, W, align;
+    float sy, sx;
+    float cscale[4];
+};
+
+__global__ void __launch_bounds__(256) k_flow_stage_hwc(const StageK a) {
+    const int P = a.H * a.W;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const size_t n = blockIdx.y;
+    const float* __restrict__ in = a.src + n * (size_t)a.h * a.w * a.C;
+    float* __restrict__ out = a.dst + n * (size_t)a.C * P;
+    const int y = p / a.W, x = p - y * a.W;
+    const Tap1 ty = make_tap1(a.sy, y, a.h, a.align), tx = make_tap1(a.sx, x, a.w, a.align);
+    const float* p00 = in + ((size_t)ty.i0 * a.w + tx.i0) * a.C;
+    const float* p01 = in + ((size_t)ty.i0 * a.w + tx.i1) * a.C;
+    const float* p10 = in + ((size_t)ty.i1 * a.w + tx.i0) * a.C;
+    const float* p11 = in + ((size_t)ty.i1 * a.w + tx.i1) * a.C;
+    for (int c = 0; c < a.C; ++c) {
+        const float v = ty.l0 * (tx.l0 * __ldg(p00 + c) + tx.l1 * __ldg(p01 + c))
+                      + ty.l1 * (tx.l0 * __ldg(p10 + c) + tx.l1 * __ldg(p11 + c));
+        out[(size_t)c * P + p] = v * a.cscale[c];
+    }
+}
+
 float host_scale(int n_in, int n_out, int align) {
     if (align) return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.0f;
     return (float)n_in / (float)n_out;
@@ -195,5 +227,19 @@ extern "C" int rcf_resize_bilinear_backward(const float* const* grad_out, float*
         k_resize_bwd_2x<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     else
         k_resize_bwd<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int rcf_flow_stage_hwc(const float* in, float* out, int N, int C, int h, int w, int H, int W, int align_corners,
+                                  const float* channel_scale_host, void* stream) {
+    if (!in || !out) return RCF_ERR_NULL;
+    if (N < 1 || N > 65535 || C < 1 || C > 4 || h < 1 || w < 1 || H < 1 || W < 1) return RCF_ERR_SHAPE;
+    if ((long long)h * w > 0x7fffffffLL / 16 || (long long)H * W > 0x7fffffffLL / 4) return RCF_ERR_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3u) return RCF_ERR_ALIGN;
+    StageK a{};
+    a.src = in; a.dst = out; a.C = C; a.h = h; a.w = w; a.H = H; a.W = W; a.align = align_corners ? 1 : 0;
+    a.sy = host_scale(h, H, a.align); a.sx = host_scale(w, W, a.align);
+    for (int c = 0; c < 4; ++c) a.cscale[c] = (channel_scale_host && c < C) ? channel_scale_host[c] : 1.0f;
+    k_flow_stage_hwc<<<dim3((H * W + 255) / 256, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return (int)cudaGetLastError();
 }

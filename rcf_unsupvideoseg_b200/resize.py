@@ -69,3 +69,22 @@ def resize_bilinear_multi(xs: Sequence[torch.Tensor], size, align_corners: bool 
 def resize_bilinear(x: torch.Tensor, size, align_corners: bool = False) -> torch.Tensor:
     """Drop-in for F.interpolate(x, size, mode='bilinear', align_corners=align_corners) on fp32 CUDA tensors."""
     return resize_bilinear_multi([x], size, align_corners)[0]
+
+
+def stage_flow_hwc(flow_hwc: torch.Tensor, size, align_corners: bool = False, channel_scale=None) -> torch.Tensor:
+    """RAFT flow as the loader holds it, [N, h, w, 2] (HWC; dataset/data.py:114-133) -> [N, 2, H, W] at `size`:
+    optional per-channel scale (FlowTransform.scale_flow), the HWC -> CHW transpose (dataset/transforms.py:850) and the
+    bilinear resize of models/rcf_model.py:438-442 in one kernel.  No gradient (ground truth)."""
+    lib = _lib.load_library()
+    if not flow_hwc.is_cuda:
+        raise RuntimeError("stage_flow_hwc: CUDA tensors required (no CPU fallback)")
+    assert flow_hwc.dim() == 4 and flow_hwc.shape[-1] <= 4, "flow [N, h, w, C<=4]"
+    x = flow_hwc.detach().float().contiguous()
+    N, h, w, Cc = x.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty(N, Cc, H, W, dtype=torch.float32, device=x.device)
+    cs = (C.c_float * Cc)(*[float(v) for v in channel_scale]) if channel_scale is not None else None
+    with _lib.device_guard(x.device):
+        _lib.check(lib.rcf_flow_stage_hwc(x.data_ptr(), out.data_ptr(), N, Cc, h, w, H, W, int(bool(align_corners)), cs,
+                                          torch.cuda.current_stream(x.device).cuda_stream), "rcf_flow_stage_hwc")
+    return out

@@ -75,3 +75,27 @@ def test_resize_two_tensors_one_launch_and_partial_grads():
     assert torch.allclose(ga, 4 * torch.ones_like(ga), atol=1e-5)        # 2x upsampling: every input pixel carries total weight 2*2
     with pytest.raises(RuntimeError):
         resize_bilinear(torch.zeros(1, 1, 4, 4), (8, 8))                 # CPU tensor: no fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(3, 2, 30, 53, 12, 12, False, None), (2, 2, 48, 85, 96, 96, True, (1.5, 0.75)),
+                                  (1, 2, 480, 854, 96, 96, False, (0.2, 0.2))])
+def test_stage_flow_hwc_matches_reference_op_sequence(case):
+    """scale (FlowTransform.scale_flow) + np.transpose(flow, (2,0,1)) (dataset/transforms.py:842-850) + bilinear resize
+    (models/rcf_model.py:438-442) against the oracle and against the same sequence in ATen."""
+    from rcf_unsupvideoseg_b200.resize import stage_flow_hwc
+    N, C_, h, w, H, W, align, cs = case
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randn(N, h, w, C_, device="cuda", generator=gen) * 6
+    y = stage_flow_hwc(x, (H, W), align, cs)
+    ref_in = x.double().cpu().numpy()
+    if cs is not None:
+        ref_in = ref_in * np.asarray(cs)
+    y_o = O.bilinear_resize(np.transpose(ref_in, (0, 3, 1, 2)), (H, W), align)
+    # the source positions are computed in fp32 as ATen does; at column ~850 an fp32 ulp is 6e-5 pixels and the input is
+    # white noise, so the fp64 oracle is matched to ~1e-4 there (1e-6 where the positions are small)
+    tol = 1e-3 if max(h, w) > 256 else 1e-5
+    assert y.shape == (N, C_, H, W) and rel_l2(y.cpu().numpy(), y_o) < tol
+    xt = x * torch.tensor(cs, device="cuda") if cs is not None else x
+    y_t = F.interpolate(xt.permute(0, 3, 1, 2).contiguous(), (H, W), mode="bilinear", align_corners=align)
+    assert rel_l2(y.cpu().numpy(), y_t.cpu().numpy()) < (1e-4 if max(h, w) > 256 else 1e-6)   # FMA contraction of the position
