@@ -14,7 +14,7 @@
 #define RCF_WARPS (RCF_BLOCK / 32)
 
 // pixels handled by one CTA of each streaming kernel
-#define RCF_CHUNK_MOM 4096   // pass 1 (moments)
+#define RCF_CHUNK_MOM 4096   // pass 1 (moments); the affine fit (D == 2) takes 8192: see rcf_chunk_mom
 #define RCF_CHUNK_LOSS 2048  // pass 2 (reconstruct + loss + gradient moments)
 #define RCF_CHUNK_BWD 1024   // backward (no reduction)
 
@@ -23,6 +23,10 @@
 // ---- sizes of the small per-segment records ------------------------------------------------
 // pass-1 statistics per (fd,k): [0] S, [1..2] sum m*F_c, [3..3+D) sum m*u_d,
 //   [3+D .. 3+3D) sum m*F_c*u_d (c*D+d), [3+3D ..) sum m*u_d*u_e packed d<=e
+// pixels per CTA of pass 1: with the affine fit a CTA ends with a 48-accumulator reduction (~150 instructions per thread);
+// twice the pixels per CTA halves that overhead: C2 affine 0.459 -> 0.443 ms, FBMS K=3 0.388 -> 0.373 ms; K = 8 (64-bit
+// packs, two segment groups) got slower with it (1.68 -> 1.81 ms) and keeps 4096
+RCF_HD constexpr int rcf_chunk_mom(int D, int K) { return (D == 2 && K <= 4) ? 2 * RCF_CHUNK_MOM : RCF_CHUNK_MOM; }
 RCF_HD constexpr int rcf_ns(int D) { return D == 0 ? 1 : 3 + 3 * D + D * (D + 1) / 2; }
 // pass-2 gradient moments per fd: [0] sum phi, [1 + c*K + k] sum w_c m_k,
 //   D > 0: [1 + 2K + (k*2+c)*D + d] sum w_c m_k (u_d - mu_kd)
@@ -75,7 +79,7 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.cf = rcf_cf(d.D);
     L.cb = rcf_cb(d.D);
     L.segd = rcf_segd(d.D);
-    L.nchunk1 = (L.P + RCF_CHUNK_MOM - 1) / RCF_CHUNK_MOM;
+    L.nchunk1 = (L.P + rcf_chunk_mom(d.D, d.K) - 1) / rcf_chunk_mom(d.D, d.K);
     L.nchunk2 = (L.P + RCF_CHUNK_LOSS - 1) / RCF_CHUNK_LOSS;
     L.nchunkb = (L.P + RCF_CHUNK_BWD - 1) / RCF_CHUNK_BWD;
     const int pc = rcf_pool_chunk(d.K, d.feat_nhwc, L.P, L.nfd);

@@ -8,7 +8,9 @@
 template <int K, int D, int PX>
 __device__ __forceinline__ void moments_tile(const RcfK& a, int fd, int chunk, float (*red)[K * rcf_ns(D)]) {
     constexpr int NS = rcf_ns(D);
-    constexpr int ITER = RCF_CHUNK_MOM / (RCF_BLOCK * PX);
+    constexpr int CHUNK = rcf_chunk_mom(D, K);
+    constexpr int ITER = CHUNK / (RCF_BLOCK * PX);
+    constexpr int UNR = (CHUNK > RCF_CHUNK_MOM) ? 2 : ITER;     // the long affine chunk is unrolled by 2 (register budget of 3 CTAs/SM)
     constexpr int DD = D > 0 ? D : 1;
     constexpr int KG = (D == 5) ? 1 : (K < 4 ? K : 4);
 
@@ -18,7 +20,7 @@ __device__ __forceinline__ void moments_tile(const RcfK& a, int fd, int chunk, f
     const float* __restrict__ mask = a.mask[dir] + (long long)b * a.mask_bs[dir];
     const float* __restrict__ flow = a.flow[dir] + (long long)b * a.flow_bs[dir];
     const int P = a.P;
-    const int p0 = chunk * RCF_CHUNK_MOM;
+    const int p0 = chunk * CHUNK;
 
 #pragma unroll 1
     for (int k0 = 0; k0 < K; k0 += KG) {
@@ -48,7 +50,7 @@ __device__ __forceinline__ void moments_tile(const RcfK& a, int fd, int chunk, f
 #pragma unroll
                     for (int j = 0; j < PX; ++j) acc[k] += mm[it][k][j];
         } else {
-#pragma unroll
+#pragma unroll UNR
         for (int it = 0; it < ITER; ++it) {
             const int p = p0 + (it * RCF_BLOCK + tid) * PX;
             if (p < P) {
