@@ -406,7 +406,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "pcie_gbs_each_way": [h2d / e2e_ms / 1e6, d2h / e2e_ms / 1e6],
                     "note": "PCIe-bound; copies of neighbouring steps overlap compute on 3 streams"},
-            "gpu_launches": 6 * args.steps,   # k_segment_fwd, k_loss, k_finalize, k_loss_sum | k_segment_bwd, k_bwd
+            "gpu_launches": 5 * args.steps,   # k_loss, k_finalize, k_loss_sum | k_segment_bwd, k_bwd (single-pass forward)
             "roofline": {"bound": "hbm", "kernel": "k_bwd<K=4,D=0,PX=4> (streaming backward)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": read_traffic("k_bwd<4, 0, 4>"),
                          "peak_source": peak_src, "kernel_ms": kb_mean, "kernel_ms_min": kb_ms[0],

@@ -33,7 +33,11 @@ __global__ void __launch_bounds__(RCF_BLOCK, (D <= 2) ? 2 : 1) k_bwd(const RcfK 
     float* __restrict__ dmask = a.dmask[dir] ? a.dmask[dir] + (long long)b * a.dmask_bs[dir] : nullptr;
     float* __restrict__ dresid = a.dresid[dir] ? a.dresid[dir] + (long long)b * a.dresid_bs[dir] : nullptr;
 
-    for (int i = tid; i < K * CF; i += RCF_BLOCK) cf[i] = a.coef[(size_t)fd * K * CF + i];
+    if (D == 0 && a.single_pass) {      // theta supplied, single-pass forward: no k_segment_fwd ran, coef = theta
+        for (int i = tid; i < K * CF; i += RCF_BLOCK) cf[i] = __ldg(a.theta[dir] + (size_t)b * 2 * K + (i & 1) * K + (i >> 1));
+    } else {
+        for (int i = tid; i < K * CF; i += RCF_BLOCK) cf[i] = a.coef[(size_t)fd * K * CF + i];
+    }
     for (int i = tid; i < K * CB; i += RCF_BLOCK) cb[i] = a.coefb[(size_t)fd * K * CB + i];
     __syncthreads();
     const float gs = a.gscale[fd];

@@ -188,8 +188,8 @@ extern "C" int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     a.single_pass = (desc->theta_mode == 0 && desc->D == 0 && g_single_pass) ? 1 : 0;
     if (a.single_pass) {
-        // theta supplied, no affine fit: nothing in pass 2 depends on pass 1, so the forward reads every input once
-        RCF_CUDA(rcf_launch_segment_fwd(a, s));
+        // theta supplied, no affine fit: nothing in pass 2 depends on pass 1, so the forward reads every input once; the
+        // coefficient pack is just theta, which k_loss / k_bwd read directly (no k_segment_fwd launch either)
         { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_loss(a, vec, s)); }
     } else if (desc->theta_mode == 0 && vec && g_fused_forward) {
         // one launch: pass 1, per-segment solve and pass 2, ordered for L2 reuse of the masks (rcf_forward_fused.cu)
@@ -216,6 +216,7 @@ extern "C" int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const floa
     RcfK a;
     fill_common(a, *desc, *in, L, const_cast<void*>(ctx), ws);
     a.grad_loss = grad_loss;
+    a.single_pass = (desc->theta_mode == 0 && desc->D == 0 && g_single_pass) ? 1 : 0;   // as in rcf_forward: coef = theta
     a.grad_total = desc->grad_loss_total ? 1 : 0;
     bool vec = vec_ok_inputs(*desc, *in, false);
     bool vec_pool = vec_ok_inputs(*desc, *in, true);

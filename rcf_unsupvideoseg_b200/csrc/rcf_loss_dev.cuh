@@ -17,7 +17,11 @@ __device__ __forceinline__ void loss_tile(const RcfK& a, int fd, int chunk, floa
     const float* __restrict__ flow = a.flow[dir] + (long long)b * a.flow_bs[dir];
     const float* __restrict__ resid = a.resid[dir] + (long long)b * a.resid_bs[dir];
 
-    for (int i = tid; i < K * CF; i += RCF_BLOCK) cf[i] = __ldcg(a.coef + (size_t)fd * K * CF + i);
+    if (D == 0 && a.single_pass) {      // theta supplied: the coefficient pack {theta_0k, theta_1k} straight from theta [B,2,K]
+        for (int i = tid; i < K * CF; i += RCF_BLOCK) cf[i] = __ldg(a.theta[dir] + (size_t)b * 2 * K + (i & 1) * K + (i >> 1));
+    } else {
+        for (int i = tid; i < K * CF; i += RCF_BLOCK) cf[i] = __ldcg(a.coef + (size_t)fd * K * CF + i);
+    }
     __syncthreads();
 
     const long long vis_off = (long long)b * a.vis_bs + (long long)dir * a.vis_ds;
