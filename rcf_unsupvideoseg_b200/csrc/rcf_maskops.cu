@@ -7,7 +7,8 @@
 //   :376-378  entropy           = -(all_pred_mask * log_all_pred_mask).sum(dim=2).mean()
 // ATen runs this as softmax, log_softmax, mul, sum, mean (+ their five backward kernels, + the add that merges the two
 // gradient streams into the softmax backward).  Here:
-//   k_mask_fwd : one read of the logits -> masks written once + per-CTA entropy partials (fixed-order reduction)
+//   k_mask_fwd : one read of the logits -> masks written once + per-CTA partials of every loss (fixed-order reduction:
+//                k_mask_frame sums a frame's partials, k_mask_final sums the frames)
 //   k_mask_bwd : one read of (masks, dL/dmasks) -> dL/dlogits, with the entropy gradient folded in:
 //        ls = log_softmax(m), q = exp(ls), Sm = sum_k m_k
 //        dE/dm_j    = -(ls_j + m_j - q_j * Sm) / Npix
@@ -33,6 +34,7 @@ struct MaskK {
     float* part;         // [nframes * nchunk][MASK_NP]
     float* losses;       // [3]: entropy, compactness, pl/crf
     float* fstats;       // [nframes][2]: (y_center, x_center) of the compact channel (forward -> backward)
+    double* ftot;        // ws tail: [nframes][4] per-frame loss terms
     const float* gmasks; // may be null
     const float* glosses;// device [3] (d/d entropy, d/d compactness, d/d pl), may be null
     float* dlogits;
@@ -121,39 +123,57 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_fwd(const MaskK a) {
     }
 }
 
-// one CTA: fp64 sums of the per-CTA partials in a fixed order; one warp per frame for the compactness centres
-__global__ void __launch_bounds__(256) k_mask_final(const MaskK a) {
+// Level 1, one CTA per frame: fp64 sums of that frame's per-CTA partials (thread = chunk, fixed-order block reduction),
+// the compactness centroid of the frame, and the frame's four loss terms -> ftot[frame][4].
+__global__ void __launch_bounds__(256) k_mask_frame(const MaskK a) {
     rcf_pdl_prologue();
-    __shared__ double red[8][4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double tot[4] = {0.0, 0.0, 0.0, 0.0};      // entropy, compactness, pl_pos, pl_neg
-    for (int f = warp; f < a.nframes; f += 8) {
-        double v[MASK_NP];
+    __shared__ double red[8][MASK_NP];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double v[MASK_NP];
 #pragma unroll
-        for (int i = 0; i < MASK_NP; ++i) v[i] = 0.0;
-        for (int c = lane; c < a.nchunk; c += 32) {
-            const float* q = a.part + ((size_t)f * a.nchunk + c) * MASK_NP;
+    for (int i = 0; i < MASK_NP; ++i) v[i] = 0.0;
+    for (int c = tid; c < a.nchunk; c += 256) {
+        const float* q = a.part + ((size_t)f * a.nchunk + c) * MASK_NP;
 #pragma unroll
-            for (int i = 0; i < MASK_NP; ++i) v[i] += (double)__ldcg(q + i);
-        }
-#pragma unroll
-        for (int i = 0; i < MASK_NP; ++i) v[i] = warp_sum_d(v[i]);
-        tot[0] += v[0]; tot[2] += v[5]; tot[3] += v[6];
-        if (a.compact_ch >= 0) {
-            const double yc = v[2] / v[1], xc = v[3] / v[1];
-            tot[1] += v[4] - (v[2] * v[2] + v[3] * v[3]) / v[1];       // sum m ((y-yc)^2 + (x-xc)^2)
-            if (lane == 0 && a.fstats) { a.fstats[2 * f] = (float)yc; a.fstats[2 * f + 1] = (float)xc; }
-        }
+        for (int i = 0; i < MASK_NP; ++i) v[i] += (double)__ldcg(q + i);
     }
+#pragma unroll
+    for (int i = 0; i < MASK_NP; ++i) v[i] = warp_sum_d(v[i]);
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) red[warp][i] = tot[i];
+        for (int i = 0; i < MASK_NP; ++i) red[warp][i] = v[i];
     }
     __syncthreads();
     if (tid == 0) {
-        double t[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int w = 0; w < 8; ++w)
-            for (int i = 0; i < 4; ++i) t[i] += red[w][i];
+        double t[MASK_NP];
+#pragma unroll
+        for (int i = 0; i < MASK_NP; ++i) {
+            t[i] = 0.0;
+            for (int w = 0; w < 8; ++w) t[i] += red[w][i];
+        }
+        double comp = 0.0;
+        if (a.compact_ch >= 0) {
+            const double yc = t[2] / t[1], xc = t[3] / t[1];
+            comp = t[4] - (t[2] * t[2] + t[3] * t[3]) / t[1];               // sum m ((y-yc)^2 + (x-xc)^2)
+            if (a.fstats) { a.fstats[2 * f] = (float)yc; a.fstats[2 * f + 1] = (float)xc; }
+        }
+        double* o = a.ftot + (size_t)f * 4;
+        o[0] = t[0]; o[1] = comp; o[2] = t[5]; o[3] = t[6];
+    }
+}
+
+// Level 2, one warp: the frames in a fixed order.
+__global__ void __launch_bounds__(32) k_mask_final(const MaskK a) {
+    rcf_pdl_prologue();
+    const int lane = threadIdx.x;
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int f = lane; f < a.nframes; f += 32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] += a.ftot[(size_t)f * 4 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = warp_sum_d(t[i]);
+    if (lane == 0) {
         a.losses[0] = (float)(t[0] * (double)a.inv_npix);
         a.losses[1] = (float)(t[1] * (double)a.inv_npix);
         a.losses[2] = (float)((t[2] * (double)a.pl_wpos + t[3] * (double)a.pl_wneg) * (double)a.inv_npix);
@@ -280,7 +300,10 @@ void fill_cfg(MaskK& a, const RcfMaskCfg& c) {
 extern "C" int rcf_mask_prep_workspace_floats(int nframes, int P, size_t* nfloats) {
     if (!nfloats) return RCF_ERR_NULL;
     if (nframes < 1 || P < 1) return RCF_ERR_SHAPE;
-    *nfloats = (size_t)nframes * ((P + MASK_CHUNK - 1) / MASK_CHUNK) * MASK_NP;
+    // per-CTA partials (rounded up to an even count so the fp64 tail is 8-byte aligned) + per-frame totals [nframes][4] fp64
+    size_t np = (size_t)nframes * ((P + MASK_CHUNK - 1) / MASK_CHUNK) * MASK_NP;
+    np += np & 1;
+    *nfloats = np + (size_t)nframes * 8;
     return RCF_OK;
 }
 
@@ -295,6 +318,12 @@ extern "C" int rcf_mask_losses_forward(const RcfMaskCfg* cfg, const float* logit
     fill_cfg(a, *cfg);
     if (a.compact_ch >= 0 && !frame_stats) return RCF_ERR_NULL;
     a.logits = logits; a.masks = masks; a.losses = losses; a.part = ws; a.fstats = frame_stats;
+    {
+        size_t np = (size_t)a.nframes * a.nchunk * MASK_NP;
+        np += np & 1;
+        if (reinterpret_cast<uintptr_t>(ws) & 7u) return RCF_ERR_ALIGN;
+        a.ftot = reinterpret_cast<double*>(ws + np);
+    }
     a.target = (a.pl_ch >= 0) ? target : nullptr;
     if (a.pl_ch >= 0 && !target) return RCF_ERR_NULL;
     const bool vec = a.P % 4 == 0 && al16(logits) && al16(masks) && (!a.target || al16(a.target));
@@ -302,7 +331,9 @@ extern "C" int rcf_mask_losses_forward(const RcfMaskCfg* cfg, const float* logit
     cudaError_t e = cudaErrorInvalidValue;
     MASK_K_SWITCH(launch_fwd, a, vec, s)
     if (e != cudaSuccess) return (int)e;
-    return (int)rcf_launch(k_mask_final, 1, 256, 0, s, rcf_pdl_enabled(), a);
+    e = rcf_launch(k_mask_frame, a.nframes, 256, 0, s, rcf_pdl_enabled(), a);
+    if (e != cudaSuccess) return (int)e;
+    return (int)rcf_launch(k_mask_final, 1, 32, 0, s, rcf_pdl_enabled(), a);
 }
 
 extern "C" int rcf_mask_losses_backward(const RcfMaskCfg* cfg, const float* masks, const float* target,
