@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(256) k_resize_fwd(const ResizeK a) {
     const int p = (blockIdx.x * blockDim.x + threadIdx.x) * PX;
     if (p >= P) return;
     const size_t plane = blockIdx.y;
-    const float* __restrict__ in = a.src[blockIdx.z] + plane * (size_t)a.h * a.w;
-    float* __restrict__ out = a.dst[blockIdx.z] + plane * (size_t)P;
+    const float* __restrict__ in = (blockIdx.z ? a.src[1] : a.src[0]) + plane * (size_t)a.h * a.w;
+    float* __restrict__ out = (blockIdx.z ? a.dst[1] : a.dst[0]) + plane * (size_t)P;
     int y = p / a.W, x = p - y * a.W;
     Tap1 ty = make_tap1(a.sy, y, a.h, a.align);
     float v[PX];
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(256) k_resize_bwd(const ResizeK a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.h * a.w) return;
     const size_t plane = blockIdx.y;
-    const float* __restrict__ g = a.src[blockIdx.z] + plane * (size_t)a.H * a.W;
-    float* __restrict__ gi = a.dst[blockIdx.z] + plane * (size_t)a.h * a.w;
+    const float* __restrict__ g = (blockIdx.z ? a.src[1] : a.src[0]) + plane * (size_t)a.H * a.W;
+    float* __restrict__ gi = (blockIdx.z ? a.dst[1] : a.dst[0]) + plane * (size_t)a.h * a.w;
     const int j = p / a.w, i = p - j * a.w;
     int ylo, yhi, xlo, xhi;
     cand_range(a.sy, j, a.H, a.align, ylo, yhi);
@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(256) k_resize_fwd_2x(const ResizeK a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.h * a.w) return;
     const size_t plane = blockIdx.y;
-    const float* __restrict__ in = a.src[blockIdx.z] + plane * (size_t)a.h * a.w;
-    float* __restrict__ out = a.dst[blockIdx.z] + plane * (size_t)a.H * a.W;
+    const float* __restrict__ in = (blockIdx.z ? a.src[1] : a.src[0]) + plane * (size_t)a.h * a.w;
+    float* __restrict__ out = (blockIdx.z ? a.dst[1] : a.dst[0]) + plane * (size_t)a.H * a.W;
     const int r = p / a.w, j = p - r * a.w;
     const int rm = max(r - 1, 0), rp = min(r + 1, a.h - 1), jm = max(j - 1, 0), jp = min(j + 1, a.w - 1);
     float v[3][3];
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(256) k_resize_bwd_2x(const ResizeK a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.h * a.w) return;
     const size_t plane = blockIdx.y;
-    const float* __restrict__ g = a.src[blockIdx.z] + plane * (size_t)a.H * a.W;
-    float* __restrict__ gi = a.dst[blockIdx.z] + plane * (size_t)a.h * a.w;
+    const float* __restrict__ g = (blockIdx.z ? a.src[1] : a.src[0]) + plane * (size_t)a.H * a.W;
+    float* __restrict__ gi = (blockIdx.z ? a.dst[1] : a.dst[0]) + plane * (size_t)a.h * a.w;
     const int j = p / a.w, i = p - j * a.w;
     int yi[4], xi[4];
     float wy[4], wx[4];
