@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_stem_fwd(const StemK a) {
     const int nf4 = Cf >> 2, groups = RCF_BLOCK / nf4;
     const int c4 = tid % nf4, grp = tid / nf4;
     const int x0 = blockIdx.x * STEM_TW, y0 = blockIdx.y * STEM_TH;
-    const float* __restrict__ fl = a.flow[dir] + (long long)b * a.flow_bs[dir];
+    const float* __restrict__ fl = (dir ? a.flow[1] : a.flow[0]) + (long long)b * (dir ? a.flow_bs[1] : a.flow_bs[0]);
     stage_tile<KS>(a, fl, x0, y0, tile);
     float w[4][NT], bias[4];
 #pragma unroll
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_stem_bwd(const StemK a) {
         const int n = tl / (tx * ty), r = tl - n * tx * ty;
         const int y0 = (r / tx) * STEM_TH, x0 = (r - (r / tx) * tx) * STEM_TW;
         const int dir = n / a.B, b = n - dir * a.B;
-        const float* __restrict__ fl = a.flow[dir] + (long long)b * a.flow_bs[dir];
+        const float* __restrict__ fl = (dir ? a.flow[1] : a.flow[0]) + (long long)b * (dir ? a.flow_bs[1] : a.flow_bs[0]);
         __syncthreads();                               // previous tile fully consumed
         stage_tile<KS>(a, fl, x0, y0, tile);
         __syncthreads();
