@@ -208,7 +208,9 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_bwd(const MaskK a) {
                     for (int j = 0; j < PX; ++j) g[k][j] = 0.0f;
                 }
             }
-            if (tg) Pack<PX>::ld(t, tg + p);
+            float mob[PX];      // the object channel, re-read (L1 hit): selecting m[pl_ch] from registers makes nvcc spill m[][] to a
+                                // local array and index it (80-128 B stack frame for K > 4)
+            if (tg) { Pack<PX>::ld(t, tg + p); Pack<PX>::ld(mob, mk + (size_t)a.pl_ch * a.P + p); }
             int row = p / a.W, col = p - row * a.W;
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
@@ -222,9 +224,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_bwd(const MaskK a) {
                 const float gcomp = gc * fmaf(dy, dy, dx * dx);
                 float gpl = 0.0f;
                 if (tg) {
-                    float mo = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) mo = (k == a.pl_ch) ? m[k][j] : mo;
+                    const float mo = mob[j];
                     const float tv = a.pl_binarize ? (t[j] > a.pl_th ? 1.0f : 0.0f) : t[j];
                     const float d = tv - mo;
                     gpl = gp * (a.pl_wpos * fmaxf(d, 0.0f) + a.pl_wneg * fminf(d, 0.0f));
