@@ -215,10 +215,11 @@ RCF_API int rcf_flow_stage_hwc(const float* in, float* out, int N, int C, int h,
  * [B, I, K, H, W] with nframes = B*I); target: [nframes, H*W] (pl_masks / crf_masks).
  * Forward, one pass: masks = softmax over K; losses[0] = -(masks * log_softmax(masks)).sum(K).mean();
  * losses[1] = compactness of channel compact_channel (0 when off); losses[2] = pl_pos_weight * mean(max(t-m,0)^2) +
- * pl_neg_weight * mean(min(t-m,0)^2) with m = masks[:, pl_channel] and t = target (> pl_threshold when that is != -1).
+ * pl_neg_weight * mean(min(t-m,0)^2) with m = masks[:, pl_channel] and t = target (> pl_threshold when that is != -1);
+ * losses[3] = get_sharpen_loss (:350-374): KL(log_softmax(masks) || sharpen(masks, T)) or the object-aware hinge.
  * frame_stats [nframes, 2] receives the per-frame centroid (needed by the backward when compactness is on).
  * Backward, one pass: dlogits = softmax-backward of (grad_masks + sum_i grad_losses[i] * dlosses[i]/dmasks); grad_masks
- * (the motion loss's mask gradient) and grad_losses (device float[3]) may each be NULL. */
+ * (the motion loss's mask gradient) and grad_losses (device float[4]) may each be NULL.  losses is float[4]. */
 typedef struct RcfMaskCfg {
     int32_t nframes, K, H, W;
     int32_t compact_channel;   /* -1: off                                  (compactness_head.py:19-27)  */
@@ -226,6 +227,9 @@ typedef struct RcfMaskCfg {
     float pl_threshold;        /* pl_mask_pos_th / crf_mask_pos_th; -1: target used as it is (:384, :399) */
     float pl_pos_weight;       /* pl_pos_weight / crf_pos_weight             (:393, :408)                 */
     float pl_neg_weight;
+    int32_t sharpen_mode;      /* 0 off | 1 KL to sharpen(masks, T) (:370-373, utils/loss_utils.py:105-108) | 2 object-aware hinge (:362-369) */
+    int32_t sharpen_channel;   /* object channel of mode 2 */
+    float t_sharpen;           /* t_sharpen (:40, default 0.25) */
 } RcfMaskCfg;
 RCF_API int rcf_mask_prep_workspace_floats(int nframes, int P, size_t* nfloats);
 RCF_API int rcf_mask_losses_forward(const RcfMaskCfg* cfg, const float* logits, const float* target, float* masks,

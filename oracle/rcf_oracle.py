@@ -455,14 +455,32 @@ def _pl_target(target, th):
     return target if th == -1 else (target > th).astype(target.dtype)
 
 
-def mask_losses_forward(logits, compact_channel=None, target=None, object_channel=None, pl_th=-1.0, wpos=1.0, wneg=1.0):
-    """logits [B,I,K,H,W] -> (masks, dict(entropy, compactness, pl), centres [B*I,2])."""
+def _sharpen(p, T, axis):
+    """utils/loss_utils.py:105-108"""
+    sp = p ** (1.0 / T)
+    return sp / sp.sum(axis=axis, keepdims=True)
+
+
+def mask_losses_forward(logits, compact_channel=None, target=None, object_channel=None, pl_th=-1.0, wpos=1.0, wneg=1.0,
+                        sharpen=None, t_sharpen=0.25):
+    """logits [B,I,K,H,W] -> (masks, dict(entropy, compactness, pl, sharpen), centres [B*I,2]).
+    sharpen: None | 'kl' | 'object_hinge' (models/rcf_model.py:350-374)."""
     x = logits - logits.max(axis=2, keepdims=True)
     e = np.exp(x)
     m = e / e.sum(axis=2, keepdims=True)
     lse = np.log(np.exp(m).sum(axis=2, keepdims=True))
     ls = m - lse                                                     # :434 log_softmax OF the masks
-    out = {"entropy": float(-(m * ls).sum(axis=2).mean()), "compactness": 0.0, "pl": 0.0}       # :376-378
+    out = {"entropy": float(-(m * ls).sum(axis=2).mean()), "compactness": 0.0, "pl": 0.0, "sharpen": 0.0}       # :376-378
+    if sharpen == 'kl':                                              # :370-373; F.kl_div(input, target) = target*(log target - input)
+        t = _sharpen(m, t_sharpen, 2)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            kl = np.where(t > 0, t * (np.log(t) - ls), 0.0)
+        out["sharpen"] = float(kl.mean())
+    elif sharpen == 'object_hinge':                                  # :362-369
+        other = m.copy()
+        other[:, :, object_channel] = 0.0
+        diff = np.abs(m[:, :, object_channel] - other.max(axis=2))
+        out["sharpen"] = float(np.maximum(t_sharpen - diff, 0.0).mean())
     B, I, K, H, W = m.shape
     centres = np.zeros((B * I, 2))
     if compact_channel is not None:                                  # compactness_head.py:29-56
@@ -483,7 +501,7 @@ def mask_losses_forward(logits, compact_channel=None, target=None, object_channe
 
 
 def mask_losses_backward(masks, g_masks=None, g_entropy=None, g_compact=None, g_pl=None, compact_channel=None, target=None,
-                         object_channel=None, pl_th=-1.0, wpos=1.0, wneg=1.0):
+                         object_channel=None, pl_th=-1.0, wpos=1.0, wneg=1.0, g_sharpen=None, sharpen=None, t_sharpen=0.25):
     """d(loss)/d(logits) for upstream gradients on the masks and on each scalar loss (None = not used)."""
     m = masks
     B, I, K, H, W = m.shape
@@ -506,6 +524,15 @@ def mask_losses_backward(masks, g_masks=None, g_entropy=None, g_compact=None, g_
     if g_pl is not None and target is not None and object_channel is not None:
         d = _pl_target(target, pl_th) - m[:, :, object_channel]
         g[:, :, object_channel] += g_pl / npix * (-2.0) * (wpos * np.maximum(d, 0) + wneg * np.minimum(d, 0))
+    if g_sharpen is not None and sharpen == 'kl':
+        # target detached; d/d(ls_k) = -t_k / Nel, ls = m - lse(m)  =>  d/dm_j = -(t_j - q_j) / Nel
+        q = np.exp(m - np.log(np.exp(m).sum(axis=2, keepdims=True)))
+        g = g - g_sharpen / m.size * (_sharpen(m, t_sharpen, 2) - q)
+    elif g_sharpen is not None and sharpen == 'object_hinge':
+        other = m.copy()
+        other[:, :, object_channel] = 0.0
+        d = m[:, :, object_channel] - other.max(axis=2)
+        g[:, :, object_channel] += g_sharpen / npix * np.where(t_sharpen - np.abs(d) > 0, -np.sign(d), 0.0)
     return m * (g - (m * g).sum(axis=2, keepdims=True))
 
 

@@ -38,7 +38,8 @@ class RcfDesc(C.Structure):
 class RcfMaskCfg(C.Structure):
     _fields_ = [("nframes", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("compact_channel", C.c_int32), ("pl_channel", C.c_int32),
-                ("pl_threshold", C.c_float), ("pl_pos_weight", C.c_float), ("pl_neg_weight", C.c_float)]
+                ("pl_threshold", C.c_float), ("pl_pos_weight", C.c_float), ("pl_neg_weight", C.c_float),
+                ("sharpen_mode", C.c_int32), ("sharpen_channel", C.c_int32), ("t_sharpen", C.c_float)]
 
 
 class RcfInputs(C.Structure):

@@ -25,18 +25,19 @@
 
 namespace {
 
-// per-CTA partial sums: entropy, compactness moments (S, Sy, Sx, Sq) of the compact channel, PL/CRF squared errors
-constexpr int MASK_NP = 7;
+// per-CTA partial sums: entropy, compactness moments (S, Sy, Sx, Sq) of the compact channel, PL/CRF squared errors (pos, neg),
+// sharpening loss
+constexpr int MASK_NP = 8;
 
 struct MaskK {
     const float* logits;
     float* masks;
     float* part;         // [nframes * nchunk][MASK_NP]
-    float* losses;       // [3]: entropy, compactness, pl/crf
+    float* losses;       // [4]: entropy, compactness, pl/crf, sharpen
     float* fstats;       // [nframes][2]: (y_center, x_center) of the compact channel (forward -> backward)
-    double* ftot;        // ws tail: [nframes][4] per-frame loss terms
+    double* ftot;        // ws tail: [nframes][8] per-frame loss terms (5 used)
     const float* gmasks; // may be null
-    const float* glosses;// device [3] (d/d entropy, d/d compactness, d/d pl), may be null
+    const float* glosses;// device [4] (d/d entropy, d/d compactness, d/d pl, d/d sharpen), may be null
     float* dlogits;
     const float* target; // PL / CRF masks [nframes, P] or null
     int nframes, P, H, W, nchunk;
@@ -44,6 +45,10 @@ struct MaskK {
     int pl_ch;           // object channel (PL / CRF loss), -1: off
     int pl_binarize;     // target = target > pl_th
     float pl_th, pl_wpos, pl_wneg;
+    int sharpen_mode;    // 0 off, 1 KL to the sharpened masks (rcf_model.py:370-373), 2 object-aware hinge (:362-369)
+    int sharpen_ch;      // object channel of mode 2
+    float t_sharpen, inv_t;
+    int K;
     float inv_npix;      // 1 / (nframes * P)
     float inv_h, inv_w;
 };
@@ -107,6 +112,32 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_fwd(const MaskK a) {
                     acc[5] = fmaf(dp, dp, acc[5]);
                     acc[6] = fmaf(dn, dn, acc[6]);
                 }
+                if (a.sharpen_mode == 1) {
+                    // target = sharpen(m, T) = m^(1/T) / sum m^(1/T) (utils/loss_utils.py:105-108, detached);
+                    // F.kl_div(log_softmax(m), target, 'none') = target * (log target - (m - lse)), averaged over all elements
+                    const float lse = __logf(s2);
+                    float lg[K], spw = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { lg[k] = __logf(x[k][j]) * a.inv_t; spw += __expf(lg[k]); }
+                    const float lsp = __logf(spw);
+                    float term = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const float lt = lg[k] - lsp;                      // log target_k
+                        const float tk = __expf(lt);
+                        term += (tk > 0.0f) ? tk * (lt - (x[k][j] - lse)) : 0.0f;
+                    }
+                    acc[7] += term;
+                } else if (a.sharpen_mode == 2) {
+                    // hinge on |m_obj - max of the other (detached) channels| (rcf_model.py:362-369)
+                    float mobj = 0.0f, mx = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        mobj = (k == a.sharpen_ch) ? x[k][j] : mobj;
+                        mx = (k == a.sharpen_ch) ? mx : fmaxf(mx, x[k][j]);
+                    }
+                    acc[7] += fmaxf(a.t_sharpen - fabsf(mobj - mx), 0.0f);
+                }
                 if (++col == a.W) { col = 0; ++row; }
             }
 #pragma unroll
@@ -157,8 +188,8 @@ __global__ void __launch_bounds__(256) k_mask_frame(const MaskK a) {
             comp = t[4] - (t[2] * t[2] + t[3] * t[3]) / t[1];               // sum m ((y-yc)^2 + (x-xc)^2)
             if (a.fstats) { a.fstats[2 * f] = (float)yc; a.fstats[2 * f + 1] = (float)xc; }
         }
-        double* o = a.ftot + (size_t)f * 4;
-        o[0] = t[0]; o[1] = comp; o[2] = t[5]; o[3] = t[6];
+        double* o = a.ftot + (size_t)f * 8;
+        o[0] = t[0]; o[1] = comp; o[2] = t[5]; o[3] = t[6]; o[4] = t[7];
     }
 }
 
@@ -166,17 +197,19 @@ __global__ void __launch_bounds__(256) k_mask_frame(const MaskK a) {
 __global__ void __launch_bounds__(32) k_mask_final(const MaskK a) {
     rcf_pdl_prologue();
     const int lane = threadIdx.x;
-    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    double t[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     for (int f = lane; f < a.nframes; f += 32) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) t[i] += a.ftot[(size_t)f * 4 + i];
+        for (int i = 0; i < 5; ++i) t[i] += a.ftot[(size_t)f * 8 + i];
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) t[i] = warp_sum_d(t[i]);
+    for (int i = 0; i < 5; ++i) t[i] = warp_sum_d(t[i]);
     if (lane == 0) {
         a.losses[0] = (float)(t[0] * (double)a.inv_npix);
         a.losses[1] = (float)(t[1] * (double)a.inv_npix);
         a.losses[2] = (float)((t[2] * (double)a.pl_wpos + t[3] * (double)a.pl_wneg) * (double)a.inv_npix);
+        // KL: mean over all B*I*K*H*W elements; hinge: mean over B*I*H*W pixels
+        a.losses[3] = (float)(t[4] * (double)a.inv_npix / (a.sharpen_mode == 1 ? (double)a.K : 1.0));
     }
 }
 
@@ -191,6 +224,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_bwd(const MaskK a) {
     const float ge = a.glosses ? -__ldg(a.glosses) * a.inv_npix : 0.0f;
     const float gc = (a.glosses && a.compact_ch >= 0) ? __ldg(a.glosses + 1) * a.inv_npix : 0.0f;
     const float gp = (a.glosses && tg) ? -2.0f * __ldg(a.glosses + 2) * a.inv_npix : 0.0f;
+    const float gsh = (a.glosses && a.sharpen_mode) ? __ldg(a.glosses + 3) * a.inv_npix / (a.sharpen_mode == 1 ? (float)K : 1.0f) : 0.0f;
     const float yc = (a.compact_ch >= 0 && a.fstats) ? __ldg(a.fstats + 2 * fr) : 0.0f;
     const float xc = (a.compact_ch >= 0 && a.fstats) ? __ldg(a.fstats + 2 * fr + 1) : 0.0f;
 #pragma unroll
@@ -229,12 +263,37 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_mask_bwd(const MaskK a) {
                     const float d = tv - mo;
                     gpl = gp * (a.pl_wpos * fmaxf(d, 0.0f) + a.pl_wneg * fminf(d, 0.0f));
                 }
+                // sharpening: KL -> d/dm_j = -(target_j - q_j) / Nel (target detached); hinge -> -sign(m_obj - mx) on the object channel
+                float tsh[K];
+                float ghinge = 0.0f;
+                if (a.sharpen_mode == 1) {
+                    float spw = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { tsh[k] = __expf(__logf(m[k][j]) * a.inv_t); spw += tsh[k]; }
+                    const float isp = 1.0f / spw;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) tsh[k] = -gsh * (tsh[k] * isp - e[k] * inv2);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) tsh[k] = 0.0f;
+                    if (a.sharpen_mode == 2) {
+                        float mobj = 0.0f, mx = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            mobj += (k == a.sharpen_ch) ? e[k] : 0.0f;           // exp is monotone: compare exp(m) to stay in registers
+                            mx = (k == a.sharpen_ch) ? mx : fmaxf(mx, e[k]);
+                        }
+                        const float d = __logf(mobj) - __logf(fmaxf(mx, 1.0f));      // = m_obj - max_other (exp(0) = 1 when K == 1)
+                        ghinge = (a.t_sharpen - fabsf(d) > 0.0f) ? -gsh * ((d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f)) : 0.0f;
+                    }
+                }
                 float dot = 0.0f;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const float mkj = m[k][j];
                     const float dE = (mkj - lse) + mkj - e[k] * inv2 * sm;     // ls_j + m_j - q_j * Sm
-                    float gk = fmaf(ge, dE, g[k][j]);
+                    float gk = fmaf(ge, dE, g[k][j]) + tsh[k];
+                    gk += (k == a.sharpen_ch && a.sharpen_mode == 2) ? ghinge : 0.0f;
                     gk += (k == a.compact_ch) ? gcomp : 0.0f;
                     gk += (k == a.pl_ch) ? gpl : 0.0f;
                     g[k][j] = gk;
@@ -281,6 +340,10 @@ void fill_cfg(MaskK& a, const RcfMaskCfg& c) {
     a.pl_th = c.pl_threshold; a.pl_wpos = c.pl_pos_weight; a.pl_wneg = c.pl_neg_weight;
     a.inv_npix = (float)(1.0 / ((double)c.nframes * (double)a.P));
     a.inv_h = 1.0f / (float)c.H; a.inv_w = 1.0f / (float)c.W;
+    a.K = c.K;
+    a.sharpen_mode = (c.sharpen_mode == 1 || (c.sharpen_mode == 2 && c.sharpen_channel >= 0 && c.sharpen_channel < c.K)) ? c.sharpen_mode : 0;
+    a.sharpen_ch = a.sharpen_mode == 2 ? c.sharpen_channel : -1;
+    a.t_sharpen = c.t_sharpen; a.inv_t = c.t_sharpen > 0.0f ? 1.0f / c.t_sharpen : 1.0f;
 }
 
 #define MASK_K_SWITCH(fn, ...)                     \
@@ -303,7 +366,7 @@ extern "C" int rcf_mask_prep_workspace_floats(int nframes, int P, size_t* nfloat
     // per-CTA partials (rounded up to an even count so the fp64 tail is 8-byte aligned) + per-frame totals [nframes][4] fp64
     size_t np = (size_t)nframes * ((P + MASK_CHUNK - 1) / MASK_CHUNK) * MASK_NP;
     np += np & 1;
-    *nfloats = np + (size_t)nframes * 8;
+    *nfloats = np + (size_t)nframes * 16;
     return RCF_OK;
 }
 

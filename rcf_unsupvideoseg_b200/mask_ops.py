@@ -7,6 +7,7 @@ replaces (models/rcf_model.py, models/compactness_head.py)
     :433      all_pred_mask = F.softmax(all_pred_mask, dim=2)
     :434      log_all_pred_mask = F.log_softmax(all_pred_mask, dim=2)            # (sic) log-softmax of the probabilities
     :376-378  get_entropy_loss = -(all_pred_mask * log_all_pred_mask).sum(dim=2).mean()
+    :350-374  get_sharpen_loss: KL to the sharpened masks (utils.sharpen) or the object-aware hinge
     :380-408  get_pl_loss / get_crf_loss: pos/neg weighted MSE of the object channel towards a (thresholded) target mask
     compactness_head.py:33-56  CompactnessHead.get_compactness_loss
 `masks` goes to the motion loss (FlowAggregationHeadWithResidual); the losses are weighted and summed by the caller
@@ -25,7 +26,8 @@ from . import _lib
 
 class _MaskLossesFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, target, compact_channel: int, pl_channel: int, pl_th: float, wpos: float, wneg: float):
+    def forward(ctx, logits, target, compact_channel: int, pl_channel: int, pl_th: float, wpos: float, wneg: float,
+                sharpen_mode: int, sharpen_channel: int, t_sharpen: float):
         lib = _lib.load_library()
         if not logits.is_cuda:
             raise RuntimeError("mask_losses: CUDA tensors required (no CPU fallback)")
@@ -36,9 +38,10 @@ class _MaskLossesFn(torch.autograd.Function):
         if pl_channel >= 0:
             assert target is not None and tuple(target.shape) == (B, I, H, W), "target [B, I, H, W]"
             tgt = target.detach().float().contiguous()
-        cfg = _lib.RcfMaskCfg(B * I, K, H, W, compact_channel, pl_channel, pl_th, wpos, wneg)
+        cfg = _lib.RcfMaskCfg(B * I, K, H, W, compact_channel, pl_channel, pl_th, wpos, wneg, sharpen_mode, sharpen_channel,
+                              t_sharpen)
         masks = torch.empty_like(x)
-        losses = torch.empty(3, dtype=torch.float32, device=x.device)
+        losses = torch.empty(4, dtype=torch.float32, device=x.device)
         fstats = torch.empty(B * I, 2, dtype=torch.float32, device=x.device)
         n = C.c_size_t()
         _lib.check(lib.rcf_mask_prep_workspace_floats(B * I, H * W, C.byref(n)), "rcf_mask_prep_workspace_floats")
@@ -59,7 +62,7 @@ class _MaskLossesFn(torch.autograd.Function):
         lib = _lib.load_library()
         masks, fstats, *rest = ctx.saved_tensors
         if g_masks is None and g_losses is None:
-            return (None,) * 7
+            return (None,) * 10
         gm = g_masks.float().contiguous() if g_masks is not None else None
         gl = g_losses.detach().float().contiguous() if g_losses is not None else None
         dl = torch.empty_like(masks)
@@ -69,24 +72,32 @@ class _MaskLossesFn(torch.autograd.Function):
                                                     gl.data_ptr() if gl is not None else None, fstats.data_ptr(),
                                                     dl.data_ptr(), torch.cuda.current_stream(masks.device).cuda_stream),
                        "rcf_mask_losses_backward")
-        return (dl, None, None, None, None, None, None)
+        return (dl,) + (None,) * 9
 
 
 def mask_losses(logits: torch.Tensor, *, compact_channel: Optional[int] = None, pl_masks: Optional[torch.Tensor] = None,
                 object_channel: Optional[int] = None, pl_mask_pos_th: float = -1.0, pl_pos_weight: float = 1.0,
-                pl_neg_weight: float = 1.0) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
-    """logits [B, I, K, H, W] -> (masks, {'entropy', 'compactness', 'pl'}).
+                pl_neg_weight: float = 1.0, sharpen: Optional[str] = None, t_sharpen: float = 0.25
+                ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """logits [B, I, K, H, W] -> (masks, {'entropy', 'compactness', 'pl', 'sharpen'}).
 
     compact_channel: channel of CompactnessHead (None: loss not computed, entry is 0).
     pl_masks [B, I, H, W] + object_channel: PL (or CRF) target and the object channel; pl_mask_pos_th = -1 uses the target
     as it is, any other value binarises it (`pl_masks > th`), exactly as get_pl_loss / get_crf_loss do.
+    sharpen: None | 'kl' (get_sharpen_loss with object_aware_sharpening=False: KL to utils.sharpen(masks, t_sharpen)) |
+    'object_hinge' (object_aware_sharpening=True; needs object_channel).
     """
+    assert sharpen in (None, 'kl', 'object_hinge')
+    smode = {None: 0, 'kl': 1, 'object_hinge': 2}[sharpen]
+    if smode == 2:
+        assert object_channel is not None, "sharpen='object_hinge' needs object_channel"
     use_pl = pl_masks is not None and object_channel is not None
     masks, losses, _ = _MaskLossesFn.apply(logits, pl_masks if use_pl else None,
                                            -1 if compact_channel is None else int(compact_channel),
                                            int(object_channel) if use_pl else -1, float(pl_mask_pos_th),
-                                           float(pl_pos_weight), float(pl_neg_weight))
-    return masks, {"entropy": losses[0], "compactness": losses[1], "pl": losses[2]}
+                                           float(pl_pos_weight), float(pl_neg_weight), smode,
+                                           int(object_channel) if smode == 2 else -1, float(t_sharpen))
+    return masks, {"entropy": losses[0], "compactness": losses[1], "pl": losses[2], "sharpen": losses[3]}
 
 
 def softmax_entropy(logits: torch.Tensor):

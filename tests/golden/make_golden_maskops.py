@@ -28,7 +28,8 @@ def load(path, name):
 def extract_methods(path, names):
     src = open(path).read()
     tree = ast.parse(src)
-    ns = {"torch": torch, "F": F}
+    lu = load("/root/reference/utils/loss_utils.py", "ref_loss_utils_for_sharpen")
+    ns = {"torch": torch, "F": F, "utils": types.SimpleNamespace(sharpen=lu.sharpen)}
     for node in ast.walk(tree):
         if isinstance(node, ast.FunctionDef) and node.name in names:
             code = ast.get_source_segment(src, node)
@@ -40,7 +41,7 @@ def extract_methods(path, names):
 
 def main():
     ch = load(os.path.join(REF, "compactness_head.py"), "ref_compactness_head")
-    ns = extract_methods(os.path.join(REF, "rcf_model.py"), {"get_entropy_loss", "get_pl_loss", "get_crf_loss"})
+    ns = extract_methods(os.path.join(REF, "rcf_model.py"), {"get_entropy_loss", "get_pl_loss", "get_crf_loss", "get_sharpen_loss"})
     out = {}
     cases = [dict(name="k4", shape=(2, 2, 4, 12, 16), compact=0, oc=2, th=-1.0, wp=1.0, wn=1.0),
              dict(name="k3_th", shape=(2, 2, 3, 9, 7), compact=1, oc=0, th=0.5, wp=2.0, wn=0.5),
@@ -65,7 +66,14 @@ def main():
         comp = head.get_compactness_loss(all_pred_mask)
         coef = (0.7, 1.3, 2.1)
         total = (all_pred_mask * w_mask).sum() + coef[0] * ent + coef[1] * comp + coef[2] * pl_loss
-        (gl,) = torch.autograd.grad(total, logits)
+        (gl,) = torch.autograd.grad(total, logits, retain_graph=True)
+        # get_sharpen_loss (:350-374), both live variants, each differentiated on its own
+        for tag, oa in (("kl", False), ("object_hinge", True)):
+            self_sh = types.SimpleNamespace(object_aware_sharpening=oa, t_sharpen=0.25)
+            sh = ns["get_sharpen_loss"](self_sh, all_pred_mask, log_all_pred_mask, object_channel=c["oc"])
+            (gsh,) = torch.autograd.grad(1.7 * sh, logits, retain_graph=True)
+            out[f"{c['name']}.sharpen.{tag}"] = np.array(float(sh))
+            out[f"{c['name']}.sharpen.{tag}.dlogits"] = gsh.numpy()
         n = c["name"]
         out[f"{n}.logits"], out[f"{n}.w_mask"], out[f"{n}.pl"] = logits.detach().numpy(), w_mask.numpy(), pl.numpy()
         out[f"{n}.masks"] = all_pred_mask.detach().numpy()

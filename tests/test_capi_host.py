@@ -50,6 +50,7 @@ int main(void) {
   F(RcfDesc,grad_loss_total);
   F(RcfMaskCfg,nframes); F(RcfMaskCfg,K); F(RcfMaskCfg,H); F(RcfMaskCfg,W); F(RcfMaskCfg,compact_channel); F(RcfMaskCfg,pl_channel);
   F(RcfMaskCfg,pl_threshold); F(RcfMaskCfg,pl_pos_weight); F(RcfMaskCfg,pl_neg_weight);
+  F(RcfMaskCfg,sharpen_mode); F(RcfMaskCfg,sharpen_channel); F(RcfMaskCfg,t_sharpen);
   F(RcfDesc,B); F(RcfDesc,K); F(RcfDesc,H); F(RcfDesc,W); F(RcfDesc,Cf); F(RcfDesc,D); F(RcfDesc,ndir); F(RcfDesc,theta_mode);
   F(RcfDesc,robust); F(RcfDesc,unbounded_residual); F(RcfDesc,eps); F(RcfDesc,q); F(RcfDesc,resid_scale); F(RcfDesc,pred_div);
   F(RcfDesc,clamp_t); F(RcfDesc,inv_n); F(RcfDesc,mask_bstride); F(RcfDesc,flow_bstride); F(RcfDesc,resid_bstride);

@@ -37,6 +37,35 @@ def test_mask_losses_oracle_matches_reference(gm, n):
     assert rel_l2(g, gm[f"{n}.dlogits"]) < 1e-11
 
 
+@pytest.mark.parametrize("n", CASES)
+@pytest.mark.parametrize("mode", ["kl", "object_hinge"])
+def test_sharpen_oracle_matches_reference(gm, n, mode):
+    """RCFModel.get_sharpen_loss (:350-374), both live variants, from the unmodified reference function"""
+    compact, oc, th, wp, wn, coef = _cfg(gm, n)
+    m, losses, _ = O.mask_losses_forward(gm[f"{n}.logits"], object_channel=oc, sharpen=mode, t_sharpen=0.25)
+    ref = float(gm[f"{n}.sharpen.{mode}"])
+    assert abs(losses["sharpen"] - ref) <= 1e-12 * abs(ref) + 1e-15
+    g = O.mask_losses_backward(m, object_channel=oc, g_sharpen=1.7, sharpen=mode, t_sharpen=0.25)
+    assert rel_l2(g, gm[f"{n}.sharpen.{mode}.dlogits"]) < 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", CASES)
+@pytest.mark.parametrize("mode", ["kl", "object_hinge"])
+def test_sharpen_kernels_match_reference_fixtures(gm, n, mode):
+    from rcf_unsupvideoseg_b200.mask_ops import mask_losses
+    compact, oc, th, wp, wn, coef = _cfg(gm, n)
+    logits = torch.from_numpy(gm[f"{n}.logits"]).float().cuda().requires_grad_(True)
+    masks, losses = mask_losses(logits, object_channel=oc, sharpen=mode, t_sharpen=0.25)
+    (g,) = torch.autograd.grad(1.7 * losses["sharpen"], logits)
+    ref = float(gm[f"{n}.sharpen.{mode}"])
+    assert abs(float(losses["sharpen"]) - ref) <= 2e-5 * abs(ref) + 1e-8
+    # the hinge gradient is a sign: pixels within fp32 rounding of the kink (|m_obj - max| == t) may flip
+    tol = 2e-5 if mode == "kl" else 2e-2
+    assert rel_l2(g.cpu().numpy(), gm[f"{n}.sharpen.{mode}.dlogits"]) < tol
+    assert rel_l2(masks.detach().cpu().numpy(), gm[f"{n}.masks"]) < 1e-6
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 def test_mask_prep_oracle_matches_reference_ops(shape):
     """entropy-only wrapper against models/rcf_model.py:433-434 and :376-378 restated with torch ops"""
