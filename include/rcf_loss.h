@@ -191,6 +191,22 @@ RCF_API int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstr
                               int ks, float clamp_t, float slope, const float* act, const uint32_t* sign, const float* dact,
                               float* dw, float* db, void* ws, void* stream);
 
+/* ---- second layer of flow_feat_before_agg (reference :89-91): Conv2d(64 -> 64, 3x3, padding 1, no bias here) on the
+ * 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32 accumulation in tensor memory; csrc/rcf_conv64.cu).
+ * Replaces the cuDNN kernels ATen picks for nn.Conv2d.forward / its data gradient.  in / out: channels-last
+ * [nimg, H, W, 64] fp32, dense, 16-byte aligned.  wpack: RCF_CONV64_WPACK_BYTES device bytes filled by
+ * rcf_conv64_pack_weights from the [64,64,3,3] fp32 weight; transpose_flip = 1 packs the operator of the DATA GRADIENT
+ * (din = conv(dout, W^T flipped)), so rcf_conv64_forward computes it with the same kernel.
+ * nprod: bf16 products per fp32 product: 3 = fp32-grade (x = hi + lo split of both operands, ~1e-5), 2 = weights split,
+ * activations rounded to bf16 (TF32 class), 1 = plain bf16 (autocast class). */
+#define RCF_CONV64_WPACK_BYTES (9 * 16384)
+RCF_API int rcf_conv64_pack_weights(const float* w, void* wpack, int transpose_flip, void* stream);
+RCF_API int rcf_conv64_forward(const float* in, const void* wpack, float* out, int nimg, int H, int W, int nprod,
+                               void* stream);
+/* Test hook (synchronises the device): 1 if a tcgen05 kernel of this process reported a barrier time-out since the
+ * previous call (a protocol bug: results of that launch are invalid), 0 otherwise. */
+RCF_API int rcf_debug_conv64_status(void);
+
 /* ---- input staging: bilinear resize of dense NCHW fp32 planes ------------------------------------
  * Replaces F.interpolate(all_pred_residual, mask_size, mode='bilinear') of the head (reference :271-273, :294-296;
  * align_corners = 0) and mmseg's resize() of the RAFT flows in the caller (models/rcf_model.py:438-442; align_corners

@@ -65,7 +65,8 @@ EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "r
                     "rcf_debug_time_kernel", "rcf_flow_warp_forward", "rcf_flow_warp_backward", "rcf_corresponding_map",
                     "rcf_debug_set_option", "rcf_stem_forward", "rcf_stem_workspace_bytes", "rcf_stem_backward",
                     "rcf_resize_bilinear_forward", "rcf_resize_bilinear_backward", "rcf_flow_stage_hwc",
-                    "rcf_mask_prep_workspace_floats", "rcf_mask_losses_forward", "rcf_mask_losses_backward")
+                    "rcf_mask_prep_workspace_floats", "rcf_mask_losses_forward", "rcf_mask_losses_backward",
+                    "rcf_conv64_pack_weights", "rcf_conv64_forward", "rcf_debug_conv64_status")
 
 _lib = None
 _lock = threading.Lock()
@@ -142,6 +143,12 @@ def load_library(build_if_missing: bool = True):
         lib.rcf_mask_losses_backward.restype = C.c_int
         lib.rcf_mask_losses_backward.argtypes = [C.POINTER(RcfMaskCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.rcf_conv64_pack_weights.restype = C.c_int
+        lib.rcf_conv64_pack_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.rcf_conv64_forward.restype = C.c_int
+        lib.rcf_conv64_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.rcf_debug_conv64_status.restype = C.c_int
+        lib.rcf_debug_conv64_status.argtypes = []
         lib.rcf_debug_set_option.restype = C.c_int
         lib.rcf_debug_set_option.argtypes = [C.c_int, C.c_int]
         if lib.rcf_abi_version() != RCF_ABI_VERSION:

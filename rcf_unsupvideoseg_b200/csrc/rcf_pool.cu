@@ -468,6 +468,14 @@ static cudaError_t launch_pool_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
     const int groups = RCF_BLOCK / (a.Cf / 4);
     const size_t smem = ((size_t)a.poolchunk * K + (size_t)groups * a.Cf * K) * sizeof(float);
     dim3 grid(a.nchunkp, a.nfd), block(RCF_BLOCK);
+    if (smem > 48 * 1024) {     // K = 7, 8 with 1024-pixel chunks: above the default dynamic shared-memory limit
+        static bool allowed = false;
+        if (!allowed) {
+            const cudaError_t e = cudaFuncSetAttribute(k_pool_nhwc<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (e != cudaSuccess) return e;
+            allowed = true;
+        }
+    }
     rcf_launch(k_pool_nhwc<K>, grid, block, smem, s, a.pdl, a);
     return cudaGetLastError();
 }
@@ -476,7 +484,16 @@ template <int K>
 static cudaError_t launch_pool_bwd_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
     dim3 grid(a.nblkpb, a.nfd), block(RCF_BLOCK);
     const size_t tile = (size_t)2 * a.pooltp * K, red = 1024;     // mask + dM tiles; [groups][Cf] = 1024 floats for the bias partial
-    rcf_launch(k_pool_bwd_nhwc<K>, grid, block, (tile > red ? tile : red) * sizeof(float), s, a.pdl, a);
+    const size_t smem = (tile > red ? tile : red) * sizeof(float);
+    if (smem > 48 * 1024) {
+        static bool allowed = false;
+        if (!allowed) {
+            const cudaError_t e = cudaFuncSetAttribute(k_pool_bwd_nhwc<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+            if (e != cudaSuccess) return e;
+            allowed = true;
+        }
+    }
+    rcf_launch(k_pool_bwd_nhwc<K>, grid, block, smem, s, a.pdl, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !a.dfeat_bias) return e;
     int S = (64 + a.nfd - 1) / a.nfd; S = S < 1 ? 1 : (S > 16 ? 16 : S);

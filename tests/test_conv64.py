@@ -1,0 +1,65 @@
+"""tcgen05 implicit-GEMM convolution (csrc/rcf_conv64.cu) against ATen in fp64 (GPU box only)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = {3: 3e-5, 2: 4e-3, 1: 8e-3}     # rel-L2 against the fp64 result, per number of bf16 products
+
+
+@pytest.fixture(scope="module")
+def c64():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import rcf_unsupvideoseg_b200 as pkg
+    pkg.load_library()
+    from rcf_unsupvideoseg_b200 import conv64
+    return conv64
+
+
+def _rel(a, b):
+    return float((a.double() - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("N,H,W", [(1, 8, 8), (2, 19, 23), (3, 48, 48), (2, 96, 96), (1, 70, 130), (1, 3, 200), (5, 33, 7)])
+@pytest.mark.parametrize("nprod", [3, 2, 1])
+def test_conv64_forward_and_data_gradient_vs_fp64(c64, N, H, W, nprod):
+    from rcf_unsupvideoseg_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + H * 10 + W)
+    x = torch.randn(N, 64, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24).cuda()
+    gy = torch.randn(N, 64, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    y = c64.conv64_raw(x, c64.pack_weights(w, False), nprod)
+    dx = c64.conv64_raw(gy, c64.pack_weights(w, True), nprod)
+    torch.cuda.synchronize()
+    assert _lib.load_library().rcf_debug_conv64_status() == 0, "barrier time-out inside the tcgen05 kernel"
+    xd = x.double().requires_grad_(True)
+    yd = F.conv2d(xd, w.double(), None, 1, 1)
+    (dxd,) = torch.autograd.grad(yd, xd, gy.double())
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert _rel(y, yd) <= TOL[nprod], (_rel(y, yd), nprod)
+    assert _rel(dx, dxd) <= TOL[nprod], (_rel(dx, dxd), nprod)
+
+
+def test_conv64_autograd_function(c64):
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn(2, 64, 21, 35, generator=g).cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = (torch.randn(64, 64, 3, 3, generator=g) / 24).cuda().requires_grad_(True)
+    gy = torch.randn(2, 64, 21, 35, generator=g).cuda()
+    y = c64.conv64(x, w, 3)
+    dx, dw = torch.autograd.grad(y, (x, w), gy)
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    dxd, dwd = torch.autograd.grad(F.conv2d(xd, wd, None, 1, 1), (xd, wd), gy.double())
+    assert _rel(y, F.conv2d(xd, wd, None, 1, 1).detach()) <= TOL[3]
+    assert _rel(dx, dxd) <= TOL[3]
+    assert _rel(dw, dwd) <= 1e-3          # cuDNN weight gradient (TF32 unless disabled) until the tcgen05 one is in
+
+
+def test_conv64_is_bit_reproducible(c64):
+    x = torch.randn(2, 64, 40, 52, device="cuda").contiguous(memory_format=torch.channels_last)
+    w = torch.randn(64, 64, 3, 3, device="cuda") / 24
+    wp = c64.pack_weights(w, False)
+    a = c64.conv64_raw(x, wp, 2)
+    b = c64.conv64_raw(x, wp, 2)
+    assert torch.equal(a, b)

@@ -1,0 +1,43 @@
+"""Times the tcgen05 conv (fprop / data gradient) against cuDNN on the same box.  python tools/time_conv64.py [N H W]"""
+import sys
+import torch
+import torch.nn.functional as F
+sys.path.insert(0, ".")
+from rcf_unsupvideoseg_b200 import conv64 as c64  # noqa: E402
+
+
+def timeit(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+def main():
+    shapes = [(4, 480, 854), (16, 96, 96), (16, 48, 48)] if len(sys.argv) < 4 else [tuple(int(a) for a in sys.argv[1:4])]
+    for N, H, W in shapes:
+        x = torch.randn(N, 64, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+        w = torch.randn(64, 64, 3, 3, device="cuda") / 24
+        wp = c64.pack_weights(w, False)
+        flops = 2 * N * H * W * 64 * 64 * 9
+        row = [f"{N}x64x{H}x{W}"]
+        for nprod in (1, 2, 3):
+            t = timeit(lambda: c64.conv64_raw(x, wp, nprod))
+            row.append(f"nprod{nprod} {t:8.1f} us ({flops / t / 1e6:6.1f} TFLOP/s)")
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            t = timeit(lambda: F.conv2d(x, w, None, 1, 1))
+            row.append(f"cudnn {'tf32' if tf32 else 'fp32'} {t:8.1f} us")
+        t = timeit(lambda: c64.pack_weights(w, False))
+        row.append(f"pack {t:5.1f} us")
+        print(" | ".join(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()
