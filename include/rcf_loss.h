@@ -192,17 +192,32 @@ RCF_API int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstr
                               float* dw, float* db, void* ws, void* stream);
 
 /* ---- second layer of flow_feat_before_agg (reference :89-91): Conv2d(64 -> 64, 3x3, padding 1, no bias here) on the
- * 5th-generation tensor cores (tcgen05.mma, bf16 operands, fp32 accumulation in tensor memory; csrc/rcf_conv64.cu).
- * Replaces the cuDNN kernels ATen picks for nn.Conv2d.forward / its data gradient.  in / out: channels-last
- * [nimg, H, W, 64] fp32, dense, 16-byte aligned.  wpack: RCF_CONV64_WPACK_BYTES device bytes filled by
- * rcf_conv64_pack_weights from the [64,64,3,3] fp32 weight; transpose_flip = 1 packs the operator of the DATA GRADIENT
- * (din = conv(dout, W^T flipped)), so rcf_conv64_forward computes it with the same kernel.
- * nprod: bf16 products per fp32 product: 3 = fp32-grade (x = hi + lo split of both operands, ~1e-5), 2 = weights split,
- * activations rounded to bf16 (TF32 class), 1 = plain bf16 (autocast class). */
+ * 5th-generation tensor cores (TMA tiled loads -> tcgen05.mma with bf16 operands -> fp32 accumulation in tensor memory;
+ * csrc/rcf_conv64.cu).  Replaces the cuDNN kernels ATen picks for nn.Conv2d.forward / its data gradient.
+ * Activations are passed as TWO channels-last bf16 tensors [nimg, H, W, 64], x ~ in_hi + in_lo (what rcf_split_bf16 and
+ * the library's own producers write); out: channels-last fp32 [nimg, H, W, 64]; all dense, 16-byte aligned.
+ * wpack: RCF_CONV64_WPACK_BYTES device bytes filled by rcf_conv64_pack_weights from the [64,64,3,3] fp32 weight;
+ * transpose_flip = 1 packs the operator of the DATA GRADIENT (din = conv(dout, W^T flipped)), so rcf_conv64_forward
+ * computes it with the same kernel.
+ * nprod: bf16 products per fp32 product: 3 = fp32-grade (hi + lo of both operands, ~1e-5), 2 = weights hi + lo,
+ * activations in_hi only (TF32 class), 1 = in_hi x w_hi (autocast class).  in_lo may be NULL unless nprod == 3. */
 #define RCF_CONV64_WPACK_BYTES (9 * 16384)
 RCF_API int rcf_conv64_pack_weights(const float* w, void* wpack, int transpose_flip, void* stream);
-RCF_API int rcf_conv64_forward(const float* in, const void* wpack, float* out, int nimg, int H, int W, int nprod,
-                               void* stream);
+RCF_API int rcf_conv64_forward(const void* in_hi, const void* in_lo, const void* wpack, float* out, int nimg, int H, int W,
+                               int nprod, void* stream);
+/* Weight gradient of the same convolution (replaces cuDNN's wgrad kernel): dw [64,64,3,3] fp32 from the layer input
+ * x ~ x_hi + x_lo and the output gradient g ~ g_hi + g_lo, all channels-last bf16 [nimg, H, W, 64]
+ * (csrc/rcf_conv64_wgrad.cu: TMA row-segment tiles, tcgen05.mma with the pixel axis as K, six taps per MMA).
+ * nprod 3: x_hi*g_hi + x_lo*g_hi + x_hi*g_lo (fp32-grade); 2: x_hi*(g_hi + g_lo) (x_lo may be NULL); 1: x_hi*g_hi.
+ * ws: rcf_conv64_wgrad_workspace_bytes() device bytes (per-CTA partials, summed in a fixed order: bit-reproducible). */
+RCF_API int rcf_conv64_wgrad_workspace_bytes(int nimg, int H, int W, size_t* bytes);
+RCF_API int rcf_conv64_wgrad(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, float* dw, void* ws,
+                             int nimg, int H, int W, int nprod, void* stream);
+/* x (n fp32 values, n % 4 == 0) -> hi = bf16(x), lo = bf16(x - hi) (lo may be NULL). */
+RCF_API int rcf_split_bf16(const float* x, void* hi, void* lo, size_t n, void* stream);
+/* Measurement hook: device buffer of 64 x 8 int64 filled by CTA 0 of the following conv launches with clock64 stamps
+ * (NULL switches it off). */
+RCF_API int rcf_debug_conv64_trace(void* buf);
 /* Test hook (synchronises the device): 1 if a tcgen05 kernel of this process reported a barrier time-out since the
  * previous call (a protocol bug: results of that launch are invalid), 0 otherwise. */
 RCF_API int rcf_debug_conv64_status(void);
@@ -274,6 +289,7 @@ RCF_API int rcf_debug_time_kernel(int which, void* start_event, void* stop_event
 #define RCF_OPT_L2_HINTS 3       /* evict-first streaming loads of flow/residual in pass 2 (default 1) */
 #define RCF_OPT_SINGLE_PASS 4    /* theta_mode 0 with D == 0: skip pass 1, S_k is accumulated inside pass 2 (default 1) */
 #define RCF_OPT_PDL 5            /* programmatic dependent launch between the library's consecutive kernels (default 1) */
+#define RCF_OPT_CONV64_DEBUG 6   /* measurement only, INVALID results: bit 0 no epilogue stores, bit 1 no producer loads, bit 2 no MMAs */
 RCF_API int rcf_debug_set_option(int option, int value);
 
 #ifdef __cplusplus

@@ -66,7 +66,8 @@ EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "r
                     "rcf_debug_set_option", "rcf_stem_forward", "rcf_stem_workspace_bytes", "rcf_stem_backward",
                     "rcf_resize_bilinear_forward", "rcf_resize_bilinear_backward", "rcf_flow_stage_hwc",
                     "rcf_mask_prep_workspace_floats", "rcf_mask_losses_forward", "rcf_mask_losses_backward",
-                    "rcf_conv64_pack_weights", "rcf_conv64_forward", "rcf_debug_conv64_status")
+                    "rcf_conv64_pack_weights", "rcf_conv64_forward", "rcf_split_bf16", "rcf_debug_conv64_status", "rcf_conv64_wgrad_workspace_bytes", "rcf_conv64_wgrad",
+                    "rcf_debug_conv64_trace")
 
 _lib = None
 _lock = threading.Lock()
@@ -146,7 +147,17 @@ def load_library(build_if_missing: bool = True):
         lib.rcf_conv64_pack_weights.restype = C.c_int
         lib.rcf_conv64_pack_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.rcf_conv64_forward.restype = C.c_int
-        lib.rcf_conv64_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.rcf_conv64_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p]
+        lib.rcf_conv64_wgrad_workspace_bytes.restype = C.c_int
+        lib.rcf_conv64_wgrad_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        lib.rcf_conv64_wgrad.restype = C.c_int
+        lib.rcf_conv64_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_void_p]
+        lib.rcf_split_bf16.restype = C.c_int
+        lib.rcf_split_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.rcf_debug_conv64_trace.restype = C.c_int
+        lib.rcf_debug_conv64_trace.argtypes = [C.c_void_p]
         lib.rcf_debug_conv64_status.restype = C.c_int
         lib.rcf_debug_conv64_status.argtypes = []
         lib.rcf_debug_set_option.restype = C.c_int

@@ -40,20 +40,76 @@ def pack_weights(w: torch.Tensor, transpose_flip: bool) -> torch.Tensor:
     return out
 
 
-def conv64_raw(x: torch.Tensor, wpack: torch.Tensor, nprod: int) -> torch.Tensor:
-    """x: [N,64,H,W] fp32 in channels-last memory format; returns the same shape / format."""
+def split_bf16(x: torch.Tensor, want_lo: bool = True):
+    """fp32 tensor (any dense layout, numel % 4 == 0) -> (hi, lo) bf16 tensors of the same shape / strides, x ~ hi + lo."""
     lib = _lib.load_library()
+    hi = torch.empty_like(x, dtype=torch.bfloat16)
+    lo = torch.empty_like(x, dtype=torch.bfloat16) if want_lo else None
+    with _lib.device_guard(x.device):
+        _lib.check(lib.rcf_split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr() if want_lo else None, x.numel(),
+                                      torch.cuda.current_stream(x.device).cuda_stream), "rcf_split_bf16")
+    return hi, lo
+
+
+def conv64_pair(x_hi: torch.Tensor, x_lo, wpack: torch.Tensor, nprod: int) -> torch.Tensor:
+    """x_hi / x_lo: [N,64,H,W] bf16, channels-last memory format (x ~ hi + lo); returns fp32 channels-last."""
+    lib = _lib.load_library()
+    if not x_hi.is_cuda:
+        raise RuntimeError("conv64: CUDA tensors required (no CPU fallback)")
+    N, C, H, W = x_hi.shape
+    assert C == 64 and x_hi.dtype == torch.bfloat16 and x_hi.is_contiguous(memory_format=torch.channels_last)
+    assert nprod < 3 or (x_lo is not None and x_lo.shape == x_hi.shape and x_lo.is_contiguous(memory_format=torch.channels_last))
+    out = torch.empty((N, 64, H, W), dtype=torch.float32, device=x_hi.device, memory_format=torch.channels_last)
+    with _lib.device_guard(x_hi.device):
+        _lib.check(lib.rcf_conv64_forward(x_hi.data_ptr(), x_lo.data_ptr() if x_lo is not None else None, wpack.data_ptr(),
+                                          out.data_ptr(), N, H, W, int(nprod),
+                                          torch.cuda.current_stream(x_hi.device).cuda_stream), "rcf_conv64_forward")
+    return out
+
+
+def conv64_raw(x: torch.Tensor, wpack: torch.Tensor, nprod: int) -> torch.Tensor:
+    """x: [N,64,H,W] fp32 (made channels-last if it is not); returns the same shape, channels-last."""
     if not x.is_cuda:
         raise RuntimeError("conv64: CUDA tensors required (no CPU fallback)")
-    N, C, H, W = x.shape
-    assert C == 64
     if x.dtype != torch.float32 or not x.is_contiguous(memory_format=torch.channels_last):
         x = x.float().contiguous(memory_format=torch.channels_last)
-    out = torch.empty((N, 64, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-    with _lib.device_guard(x.device):
-        _lib.check(lib.rcf_conv64_forward(x.data_ptr(), wpack.data_ptr(), out.data_ptr(), N, H, W, int(nprod),
-                                          torch.cuda.current_stream(x.device).cuda_stream), "rcf_conv64_forward")
-    return out
+    hi, lo = split_bf16(x, want_lo=(nprod == 3))
+    return conv64_pair(hi, lo, wpack, nprod)
+
+
+_WS_BYTES = {}
+
+
+def conv64_wgrad_pair(x_hi, x_lo, g_hi, g_lo, nprod: int) -> torch.Tensor:
+    """dW [64,64,3,3] fp32 from the layer input x ~ x_hi + x_lo and the output gradient g ~ g_hi + g_lo (bf16 channels-last)."""
+    lib = _lib.load_library()
+    N, C, H, W = x_hi.shape
+    assert C == 64 and g_hi.shape == x_hi.shape
+    for t in (x_hi, x_lo, g_hi, g_lo):
+        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=torch.channels_last))
+    dev = x_hi.device
+    key = (dev.index, N, H, W)
+    if key not in _WS_BYTES:
+        import ctypes as C_
+        nbytes = C_.c_size_t()
+        _lib.check(lib.rcf_conv64_wgrad_workspace_bytes(N, H, W, C_.byref(nbytes)), "rcf_conv64_wgrad_workspace_bytes")
+        _WS_BYTES[key] = nbytes.value
+    ws = torch.empty(_WS_BYTES[key], dtype=torch.uint8, device=dev)
+    dw = torch.empty(64, 64, 3, 3, dtype=torch.float32, device=dev)
+    with _lib.device_guard(dev):
+        _lib.check(lib.rcf_conv64_wgrad(x_hi.data_ptr(), x_lo.data_ptr() if x_lo is not None else None, g_hi.data_ptr(),
+                                        g_lo.data_ptr() if g_lo is not None else None, dw.data_ptr(), ws.data_ptr(), N, H, W,
+                                        int(nprod), torch.cuda.current_stream(dev).cuda_stream), "rcf_conv64_wgrad")
+    return dw
+
+
+def conv64_wgrad_raw(x: torch.Tensor, g: torch.Tensor, nprod: int) -> torch.Tensor:
+    """fp32 convenience wrapper (splits both operands first)."""
+    x = x.float().contiguous(memory_format=torch.channels_last)
+    g = g.float().contiguous(memory_format=torch.channels_last)
+    x_hi, x_lo = split_bf16(x, want_lo=(nprod == 3))
+    g_hi, g_lo = split_bf16(g, want_lo=(nprod >= 2))
+    return conv64_wgrad_pair(x_hi, x_lo, g_hi, g_lo, nprod)
 
 
 class _Conv64Fn(torch.autograd.Function):
@@ -71,9 +127,7 @@ class _Conv64Fn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = conv64_raw(g, pack_weights(w, True), ctx.nprod)
         if ctx.needs_input_grad[1]:
-            g_cl = g.contiguous(memory_format=torch.channels_last)
-            dw = torch.ops.aten.convolution_backward(g_cl, x, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1,
-                                                     (False, True, False))[1]
+            dw = conv64_wgrad_raw(x, g, 3 if ctx.nprod >= 2 else 1)
         return dx, dw, None
 
 

@@ -2,42 +2,46 @@
 // flow_feat_before_agg (reference models/flow_aggregation_head_with_residual.py:89-91) and its gradients.
 //
 // Tile geometry ("linear padded tile").  A CTA tile is TR x TW output pixels.  Its input window (TR+2) x Wp, Wp = TW+2,
-// is staged in shared memory as rows of 64 bf16 channels (128 B, 128-byte swizzle) indexed by the LINEAR position
+// is brought into shared memory by ONE TMA tiled load (out-of-image elements arrive as zeros = the padding) as rows of
+// 64 bf16 channels (128 B, 128-byte swizzle) indexed by the LINEAR position
 // q = r * Wp + x.  An M-tile of the GEMM is 128 CONSECUTIVE positions starting at q = Wp + 1 (the first output pixel),
 // so the A operand of tap (ty, tx) is the same tile read from a start address shifted by (ty * Wp + tx) rows: no im2col
-// copy.  Rows of an M-tile that fall on halo columns are computed and dropped (2 / Wp of the work).
+// copy.  Rows of an M-tile that fall on halo columns are computed and dropped (2 / Wp of the work).  One M-tile per CTA
+// tile ((TR-1) * Wp + TW <= 128): tiles are small (<= 27 KB) so three of them fit beside the 144 KB of weights and the
+// TMA latency hides behind the MMAs of the two tiles in front.
 #pragma once
 #include <stdint.h>
 
-#define C64_THREADS 384          /* warps 0-3 epilogue (TMEM lane quarters), warp 4 MMA issue + weights, warps 5-11 producers */
-#define C64_EPI_WARPS 4
-#define C64_MMA_WARP 4
-#define C64_PROD_WARP0 5
-#define C64_PROD_WARPS 7
-#define C64_PROD_THREADS (C64_PROD_WARPS * 32)
+#define C64_THREADS 320          /* warps 0-7 epilogue (TMEM lane quarter x column half), warp 8 MMA issue + weights, warp 9 TMA */
+#define C64_EPI_WARPS 8
+#define C64_MMA_WARP 8
+#define C64_TMA_WARP 9
 #define C64_TAP_BYTES 16384      /* one tap of packed weights: 128 rows (hi of co 0..63, lo of co 0..63) x 64 k, bf16 */
 #define C64_W_BYTES (9 * C64_TAP_BYTES)
-#define C64_MAX_POS 328          /* positions per staged tile buffer */
+#define C64_MAX_POS 216          /* positions per staged tile buffer (27 KB) */
 #define C64_ABUF_BYTES (C64_MAX_POS * 128)
-#define C64_SMEM_BYTES (C64_W_BYTES + 2 * C64_ABUF_BYTES + 128)
+#define C64_NA 3                 /* A-tile ring stages (a TMA tile load takes longer than the MMAs of one tile) */
+#define C64_NT 4                 /* accumulator stages in tensor memory: 4 x 128 columns */
+#define C64_SMEM_BYTES (C64_W_BYTES + C64_NA * C64_ABUF_BYTES + 256)
 
 struct Conv64Geom {
     int nimg, H, W;
     int TW, TR, Wp;              // tile of TR x TW outputs; padded row Wp = TW + 2
     int tiles_x, tiles_y, ntiles;
-    int nmt;                     // M-tiles (128 positions) per tile: 1 or 2
+    int nmt;                     // M-tiles (128 positions) per tile: always 1 (one accumulator stage per tile)
     int npos;                    // (TR + 2) * Wp staged positions
+    uint32_t wp_magic;           // ceil(2^32 / Wp): q / Wp == __umulhi(q, wp_magic) for q < 2^16
 };
 
 // Picks the tile that minimises the number of MMA rows (then staged positions) for an H x W image.
 static inline Conv64Geom conv64_make_geom(int nimg, int H, int W) {
     Conv64Geom best = {};
     long long best_rows = -1, best_pos = 0;
-    for (int TW = 4; TW <= 97; ++TW) {
+    for (int TW = 4; TW <= 64; ++TW) {
         const int Wp = TW + 2;
         for (int TR = 1; TR <= 64; ++TR) {
             const int npos = (TR + 2) * Wp, span = (TR - 1) * Wp + TW;
-            if (span > 256) break;
+            if (span > 128) break;
             const int nmt = (span + 127) / 128;
             if (npos > C64_MAX_POS || 2 * Wp + 2 + 128 * nmt > C64_MAX_POS) continue;
             const int tx = (W + TW - 1) / TW, ty = (H + TR - 1) / TR;
@@ -50,5 +54,6 @@ static inline Conv64Geom conv64_make_geom(int nimg, int H, int W) {
     }
     best.nimg = nimg; best.H = H; best.W = W;
     best.ntiles = nimg * best.tiles_x * best.tiles_y;
+    best.wp_magic = (uint32_t)((0x100000000ull + best.Wp - 1) / best.Wp);
     return best;
 }

@@ -1,14 +1,12 @@
 // sm_100a primitives for the tensor-core feature branch: tcgen05 (MMA, TMEM alloc / load, commit), mbarrier,
 // bulk async copies and the shared-memory matrix / instruction descriptors.  Inline PTX only; no CUTLASS.
 //
-// Operand layout used throughout (no swizzle, "interleaved" canonical layout of the tcgen05 matrix descriptor):
-// a tile is a set of PLANES; plane c holds the 16-byte chunk c (8 bf16 channels) of every position, positions at a
-// 16-byte pitch:    addr(chunk c, position q) = base + c * plane_stride + q * 16.
-//  * read K-major  (rows = positions, K = channels):   8-row groups 128 B apart (SBO), K chunks a plane apart (LBO).
-//    A row shift (a convolution tap) is a change of the start address by a multiple of 16 B.
-//  * read MN-major (rows = channels,  K = positions):  row chunks a plane apart (SBO), 8-position groups 128 B apart (LBO).
-// The same physical tile therefore feeds the forward / data-gradient GEMMs (K-major) and the weight-gradient GEMM
-// (MN-major) without a transpose.
+// Operand layout used by the kernels: rows of 64 bf16 channels (128 B) per pixel position with the 128-byte swizzle --
+// exactly what a TMA tiled load of a channels-last bf16 tensor produces.
+//  * read K-major  (rows = positions, K = channels): forward / data-gradient GEMMs; a convolution tap is a change of the
+//    start address by whole rows (the swizzle is a function of the absolute address, so no re-layout is needed);
+//  * read MN-major (rows = channels,  K = positions): weight-gradient GEMM, same tile, no transpose.
+// (The no-swizzle "plane" layout of make_desc() was the first candidate; tools/microbench/umma_probe*.cu compare them.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -131,6 +129,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- TMA: 4-D tiled tensor load global -> shared (box described by a CUtensorMap), completion in bytes on an mbarrier.
+// Coordinates are signed, innermost first; elements outside the tensor arrive as zeros (= the convolution's zero padding).
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
 // ---- bf16 split: x = hi + lo (+ ~2^-17 |x|) ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t bf16_rn_bits(float x) {             // round-to-nearest-even bf16, as the upper 16 bits
     uint32_t u = __float_as_uint(x);
@@ -140,6 +149,17 @@ __device__ __forceinline__ uint32_t bf16_rn_bits(float x) {             // round
 __device__ __forceinline__ void split_bf16(float x, uint32_t& hi_bits, uint32_t& lo_bits) {
     hi_bits = bf16_rn_bits(x);
     lo_bits = bf16_rn_bits(x - __uint_as_float(hi_bits));
+}
+// Hardware conversion of two floats to one packed bf16x2 word (round to nearest even): `a` lands in the LOW half.
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+// hi = bf16x2(a, b); lo = bf16x2(a - float(hi.a), b - float(hi.b))
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = cvt_bf16x2(a, b);
+    lo = cvt_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
 }
 // pack two bf16 (given as fp32 bit patterns whose low halves are zero) into one 32-bit word: e0 in the low half
 __device__ __forceinline__ uint32_t pack_bf16(uint32_t e0_bits, uint32_t e1_bits) { return (e0_bits >> 16) | e1_bits; }
