@@ -44,7 +44,7 @@ extern "C" {
 #define RCF_API
 #endif
 
-#define RCF_ABI_VERSION 2
+#define RCF_ABI_VERSION 3
 #define RCF_MAX_K 8          /* mask_layer supported by the compiled kernels */
 #define RCF_MAX_CF 256       /* num_flow_feat_channels supported by the segment kernels */
 
@@ -133,6 +133,11 @@ typedef struct RcfGrads {
     float* dw2;        /* [2,Cf] */
     float* db2;        /* [2] */
     float* dfeat_bias; /* [Cf] gradient of RcfInputs.feat_bias (sum over pixels of dfeat), or NULL */
+    /* ABI 3, channels-last feat only: dfeat written as the bf16 pair dfeat ~ hi + lo (same element strides as dfeat,
+       dfeat_bstride % 8 == 0) -- the operand format of rcf_conv64_forward / rcf_conv64_wgrad; dfeat_lo may be NULL.
+       Independent of `dfeat` (either, both or none may be requested). */
+    void* dfeat_hi[2];
+    void* dfeat_lo[2];
 } RcfGrads;
 
 /* ABI version of the loaded library (== RCF_ABI_VERSION of the header it was built from). */
@@ -181,6 +186,11 @@ RCF_API int rcf_corresponding_map(const float* coords, float* out, void* scratch
 RCF_API int rcf_stem_forward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W, int Cf,
                              int ks, const float* w, const float* b, float clamp_t, float slope, float* act,
                              uint32_t* sign, void* stream);
+/* The same layer with the activation written as the bf16 pair act ~ act_hi + act_lo (channels-last [ndir*B, H, W, 64]
+ * bf16 each; act_lo may be NULL) instead of fp32: the operand format of rcf_conv64_forward.  Cf = 64 only. */
+RCF_API int rcf_stem_forward_bf16(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W,
+                                  int ks, const float* w, const float* b, float clamp_t, float slope, void* act_hi,
+                                  void* act_lo, uint32_t* sign, void* stream);
 RCF_API int rcf_stem_workspace_bytes(int ndir, int B, int H, int W, int Cf, int ks, size_t* bytes);
 /* dw [Cf,2,ks,ks], db [Cf] from dact (gradient w.r.t. act) and EITHER the forward output act OR the sign bits the forward
  * wrote; ws from rcf_stem_workspace_bytes.

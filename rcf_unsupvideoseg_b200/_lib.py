@@ -12,7 +12,7 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "librcf_loss.so")
 
-RCF_ABI_VERSION = 2
+RCF_ABI_VERSION = 3
 RCF_MAX_K = 8
 RCF_MAX_CF = 256
 
@@ -58,6 +58,7 @@ class RcfGrads(C.Structure):
     _fields_ = [
         ("dmask", _ptr2), ("dresid", _ptr2), ("dfeat", _ptr2), ("dtheta", _ptr2),
         ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p), ("dfeat_bias", C.c_void_p),
+        ("dfeat_hi", _ptr2), ("dfeat_lo", _ptr2),
     ]
 
 
@@ -66,7 +67,7 @@ EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "r
                     "rcf_debug_set_option", "rcf_stem_forward", "rcf_stem_workspace_bytes", "rcf_stem_backward",
                     "rcf_resize_bilinear_forward", "rcf_resize_bilinear_backward", "rcf_flow_stage_hwc",
                     "rcf_mask_prep_workspace_floats", "rcf_mask_losses_forward", "rcf_mask_losses_backward",
-                    "rcf_conv64_pack_weights", "rcf_conv64_forward", "rcf_split_bf16", "rcf_debug_conv64_status", "rcf_conv64_wgrad_workspace_bytes", "rcf_conv64_wgrad",
+                    "rcf_conv64_pack_weights", "rcf_conv64_forward", "rcf_split_bf16", "rcf_debug_conv64_status", "rcf_stem_forward_bf16", "rcf_conv64_wgrad_workspace_bytes", "rcf_conv64_wgrad",
                     "rcf_debug_conv64_trace")
 
 _lib = None
@@ -123,6 +124,10 @@ def load_library(build_if_missing: bool = True):
         lib.rcf_stem_forward.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
                                          C.c_void_p]
+        lib.rcf_stem_forward_bf16.restype = C.c_int
+        lib.rcf_stem_forward_bf16.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
         lib.rcf_stem_workspace_bytes.restype = C.c_int
         lib.rcf_stem_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         lib.rcf_stem_backward.restype = C.c_int

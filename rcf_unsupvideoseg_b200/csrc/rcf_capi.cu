@@ -226,6 +226,11 @@ extern "C" int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const floa
     for (int i = 0; i < desc->ndir; ++i) {
         a.dmask[i] = grads->dmask[i]; a.dresid[i] = grads->dresid[i];
         a.dfeat[i] = desc->theta_mode == 1 ? grads->dfeat[i] : nullptr;
+        a.dfeat_hi[i] = (desc->theta_mode == 1 && desc->feat_nhwc) ? static_cast<uint32_t*>(grads->dfeat_hi[i]) : nullptr;
+        a.dfeat_lo[i] = a.dfeat_hi[i] ? static_cast<uint32_t*>(grads->dfeat_lo[i]) : nullptr;
+        if (a.dfeat_hi[i] && (!aligned16(a.dfeat_hi[i]) || (a.dfeat_lo[i] && !aligned16(a.dfeat_lo[i])) || desc->dfeat_bstride[i] % 8))
+            return RCF_ERR_ALIGN;
+        if (a.dfeat_hi[i]) any_dfeat = true;
         a.dtheta[i] = desc->theta_mode == 0 ? grads->dtheta[i] : nullptr;
         a.dmask_bs[i] = desc->dmask_bstride[i]; a.dresid_bs[i] = desc->dresid_bstride[i];
         a.dfeat_bs[i] = desc->dfeat_bstride[i];

@@ -162,6 +162,7 @@ struct RcfK {
     const float* grad_loss;
     int grad_total;           // grad_loss is one float (gradient of the total), not one per direction
     float* dmask[2]; float* dresid[2]; float* dfeat[2]; float* dtheta[2];
+    uint32_t* dfeat_hi[2]; uint32_t* dfeat_lo[2];   // channels-last dfeat as bf16 pairs (hi word, lo word) instead of fp32
     long long dmask_bs[2], dresid_bs[2], dfeat_bs[2];
     float *dw1, *db1, *dw2, *db2;
     float* dfeat_bias;        // [Cf] or null

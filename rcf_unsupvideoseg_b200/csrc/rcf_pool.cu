@@ -9,6 +9,7 @@
 // Thread-per-pixel-pack mapping: G is read once, dG written once, the dM term is accumulated in registers
 // on top of what the streaming backward (k_bwd, launched before) already stored.
 #include "rcf_common.cuh"
+#include "rcf_umma.cuh"
 
 // blockIdx.z splits the feature channels (more CTAs for small frames: 96x96 training shapes would otherwise
 // launch only 80 CTAs on 148 SMs).  A warp handles FB feature channels at once so that one shared-memory read of
@@ -280,6 +281,16 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
     const int iters = (TP + groups - 1) / groups;      // uniform trip count: shuffles below stay convergent
     const float4* __restrict__ gp = reinterpret_cast<const float4*>(feat + (long long)p0 * Cf) + c4;
     float4* __restrict__ dgp = dfeat ? reinterpret_cast<float4*>(dfeat + (long long)p0 * Cf) + c4 : nullptr;
+    // bf16 (hi, lo) pair output (what the tcgen05 conv kernels load by TMA): 4 channels = one uint2 per word tensor
+    uint2* __restrict__ dgh = a.dfeat_hi[dir] ? reinterpret_cast<uint2*>(a.dfeat_hi[dir] + ((long long)b * a.dfeat_bs[dir] + (long long)p0 * Cf) / 2) + c4 : nullptr;
+    uint2* __restrict__ dgl = a.dfeat_lo[dir] ? reinterpret_cast<uint2*>(a.dfeat_lo[dir] + ((long long)b * a.dfeat_bs[dir] + (long long)p0 * Cf) / 2) + c4 : nullptr;
+    auto store_pair = [&](int p, const float (&dg)[4]) {
+        uint32_t h0, h1, l0, l1;
+        umma::split_bf16x2(dg[0], dg[1], h0, l0);
+        umma::split_bf16x2(dg[2], dg[3], h1, l1);
+        dgh[(long long)p * nf4] = make_uint2(h0, h1);
+        if (dgl) dgl[(long long)p * nf4] = make_uint2(l0, l1);
+    };
     // fast reduction when 16 lanes share a pixel and K == 4 (Cf = 64, the reference default): recursive halving
     // (2 + 1 shuffles) then two butterflies, instead of 4 x 4 butterflies
     const bool fast = (K == 4) && (nf4 == 16);
@@ -328,6 +339,7 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
                         dbias[j] += live ? dg[j] : 0.0f;
                     }
                     if (live && dgp) dgp[(long long)p * nf4] = make_float4(dg[0], dg[1], dg[2], dg[3]);
+                    if (live && dgh) store_pair(p, dg);
                     const float s0 = up8 ? part[0] : part[2], s1 = up8 ? part[1] : part[3];
                     const float k0 = up8 ? part[2] : part[0], k1 = up8 ? part[3] : part[1];
                     const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
@@ -378,6 +390,7 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
                 dbias[j] += dg[j];
             }
             if (dgp) dgp[(long long)p * nf4] = make_float4(dg[0], dg[1], dg[2], dg[3]);
+            if (dgh) store_pair(p, dg);
         }
 #pragma unroll
         for (int k = 0; k < K; ++k)

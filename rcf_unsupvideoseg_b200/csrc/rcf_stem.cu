@@ -10,6 +10,7 @@
 //                 accumulators, fixed-order combination inside the CTA, per-CTA partials reduced by k_stem_bwd_final
 //                 in fp64 => bit-reproducible.  No input gradient: the RAFT flow carries no grad.
 #include "rcf_common.cuh"
+#include "rcf_umma.cuh"
 
 namespace {
 
@@ -21,6 +22,8 @@ struct StemK {
     const float* w;      // [Cf][2][KS][KS]
     const float* b;      // [Cf]
     float* act;          // [N][P][Cf]
+    uint32_t* act_hi;    // tensor-core path, optional: the activation as bf16 pairs [N][P][Cf/2] (hi word; lo word = act - hi)
+    uint32_t* act_lo;    //   instead of the fp32 map: what the tcgen05 conv (rcf_conv64.cu) loads by TMA
     const float* act_in; // backward: forward output (sign of the pre-activation) -- CUDA-core path
     uint32_t* sign_out;  // tensor-core path: [N][P][Cf/32] bit f%32 of word f/32 set <=> pre-activation of channel f is <= 0
     const uint32_t* sign_in;
@@ -396,12 +399,26 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
                 word |= __shfl_xor_sync(0xffffffffu, word, 1);
                 word |= __shfl_xor_sync(0xffffffffu, word, 2);
                 if (x + 8 * h < a.W) {
-                    float* dst = img + (long long)(pofs + 8 * h) * Cf;
                     const float sl = a.slope;                    // 0 <= slope <= 1 (checked by the launcher): lrelu = max(v, slope*v)
-                    *reinterpret_cast<float4*>(dst) = make_float4(fmaxf(v[0], sl * v[0]), fmaxf(v[1], sl * v[1]),
-                                                                  fmaxf(v[2], sl * v[2]), fmaxf(v[3], sl * v[3]));
-                    *reinterpret_cast<float4*>(dst + 16) = make_float4(fmaxf(v[4], sl * v[4]), fmaxf(v[5], sl * v[5]),
-                                                                       fmaxf(v[6], sl * v[6]), fmaxf(v[7], sl * v[7]));
+                    float o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e], sl * v[e]);
+                    if (a.act_hi) {                              // bf16 (hi, lo) pair: 4 channels = 2 words, +16 channels = +8 words
+                        const long long wofs = ((long long)n * a.P + pofs + 8 * h) * (Cf / 2) + half * 16 + 2 * t;
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) umma::split_bf16x2(o[2 * e], o[2 * e + 1], hw[e], lw[e]);
+                        *reinterpret_cast<uint2*>(a.act_hi + wofs) = make_uint2(hw[0], hw[1]);
+                        *reinterpret_cast<uint2*>(a.act_hi + wofs + 8) = make_uint2(hw[2], hw[3]);
+                        if (a.act_lo) {
+                            *reinterpret_cast<uint2*>(a.act_lo + wofs) = make_uint2(lw[0], lw[1]);
+                            *reinterpret_cast<uint2*>(a.act_lo + wofs + 8) = make_uint2(lw[2], lw[3]);
+                        }
+                    } else {
+                        float* dst = img + (long long)(pofs + 8 * h) * Cf;
+                        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<float4*>(dst + 16) = make_float4(o[4], o[5], o[6], o[7]);
+                    }
                     if (t == 0 && simg) simg[(long long)(pofs + 8 * h) * 2] = word;
                 }
             }
@@ -604,6 +621,30 @@ extern "C" int rcf_stem_forward(const float* const* flow, const int64_t* flow_bs
         case 1: k_stem_fwd<1><<<grid, RCF_BLOCK, 0, s>>>(a); break;
         case 3: k_stem_fwd<3><<<grid, RCF_BLOCK, 0, s>>>(a); break;
         case 5: k_stem_fwd<5><<<grid, RCF_BLOCK, 0, s>>>(a); break;
+    }
+    RCF_CUDA(cudaGetLastError());
+    return RCF_OK;
+}
+
+// Same layer, output as the bf16 (hi, lo) pair the tcgen05 conv consumes (Cf = 64 only; act_lo may be NULL).
+extern "C" int rcf_stem_forward_bf16(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W,
+                                     int ks, const float* w, const float* b, float clamp_t, float slope, void* act_hi,
+                                     void* act_lo, uint32_t* sign, void* stream) {
+    const int v = stem_check(ndir, B, H, W, STEM_MMA_CF, ks);
+    if (v != RCF_OK) return v;
+    if (!flow || !flow_bstride || !flow[0] || (ndir > 1 && !flow[1]) || !w || !b || !act_hi) return RCF_ERR_NULL;
+    if ((reinterpret_cast<uintptr_t>(act_hi) | reinterpret_cast<uintptr_t>(act_lo)) & 15u) return RCF_ERR_ALIGN;
+    if (!(slope >= 0.0f && slope <= 1.0f)) return RCF_ERR_UNSUPPORTED;
+    StemK a{};
+    fill(a, flow, flow_bstride, ndir, B, H, W, STEM_MMA_CF, clamp_t, slope);
+    a.w = w; a.b = b; a.act = nullptr; a.sign_out = sign;
+    a.act_hi = static_cast<uint32_t*>(act_hi); a.act_lo = static_cast<uint32_t*>(act_lo);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int g = stem_grid_bwd(a.ntiles);
+    switch (ks) {
+        case 1: k_stem_fwd_mma<1><<<g, RCF_BLOCK, 0, s>>>(a); break;
+        case 3: k_stem_fwd_mma<3><<<g, RCF_BLOCK, 0, s>>>(a); break;
+        case 5: k_stem_fwd_mma<5><<<g, RCF_BLOCK, 0, s>>>(a); break;
     }
     RCF_CUDA(cudaGetLastError());
     return RCF_OK;

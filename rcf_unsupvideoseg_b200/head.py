@@ -7,9 +7,12 @@ constructor keywords and defaults, parameter names (``flow_feat_before_agg.{0,2}
 module globals of models/rcf_model.py (:75); see INTEGRATION.md for the one-line rebinding.
 
 What runs where:
-  * ``flow_feat_before_agg`` (two small convs, reference :84-93) -> cuDNN through torch (library GEMM work);
-  * everything else (mask normalisation, masked pooling, segment MLP, affine / quadratic fit,
-    residual, reconstruction, loss, and the whole backward) -> librcf_loss.so (sm_100a kernels).
+  * default head shape (64 feature channels, 3x3 kernels -- every shipped config): EVERYTHING runs in librcf_loss.so as one
+    autograd node (fused_head.RcfHeadFn): conv stem (mma.sync 3xTF32), second conv + its data and weight gradients on
+    tcgen05 / TMA / tensor memory (csrc/rcf_conv64*.cu), pooling, segment MLP, fit, loss and the whole backward;
+  * other head shapes: the second conv of ``flow_feat_before_agg`` (reference :89-91) goes through torch (cuDNN), the
+    rest (mask normalisation, masked pooling, segment MLP, affine / quadratic fit, residual, reconstruction, loss, and
+    the whole backward) through librcf_loss.so (sm_100a kernels).
 There is no PyTorch implementation of the loss in this package: without the CUDA library (or on CPU
 tensors) ``forward`` raises.
 
@@ -30,9 +33,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .function import LossSpec, rcf_motion_loss
-from .conv_overlap import conv2d_dual_stream
+from .fused_head import RcfHeadFn
+from .conv64 import conv64_supported, default_nprod
 from .resize import resize_bilinear_multi
-from .stem import flow_stem, flow_stem_conv, stem_supported
+from .stem import flow_stem, stem_supported
 
 logger = logging.getLogger("main")
 
@@ -143,12 +147,12 @@ class FlowAggregationHeadWithResidual(nn.Module):
         self.channels_last_features = True
         #   handwritten_stem=False sends the first conv + LeakyReLU through cuDNN/ATen instead of csrc/rcf_stem.cu.
         self.handwritten_stem = True
-        #   overlap_conv_backward=True (experiment, off): stem + second conv become one autograd node whose backward issues the
-        #   conv's weight gradient on a side stream beside its data gradient + the stem's gradients (stem.py::_StemConvFn,
-        #   conv_overlap.py).  Measured on B200 at the training shapes: -1..-2 % inside a CUDA graph (the cuDNN kernels
-        #   already occupy every SM, there is little left to overlap) and +15-20 % host time per eager step (stream
-        #   switches), so the default stays the plain single-stream backward.
-        self.overlap_conv_backward = False
+        #   tensor_core_conv=False sends the second conv through cuDNN/ATen instead of csrc/rcf_conv64*.cu (tcgen05).
+        #   conv_precision: bf16 products per fp32 product of the tcgen05 convs; None = what the reference's own convs would
+        #   do under the caller's torch settings: 3 (fp32-grade) when torch.backends.cudnn.allow_tf32 is False, 2 (weights
+        #   hi+lo, activations bf16: TF32 class) at torch's default, 1 (plain bf16) inside torch.autocast.
+        self.tensor_core_conv = True
+        self.conv_precision = None
 
     # ------------------------------------------------------------------------------------------
     @property
@@ -188,14 +192,8 @@ class FlowAggregationHeadWithResidual(nn.Module):
         if self._use_channels_last() and stem_flows is not None and self.handwritten_stem \
                 and stem_supported(self.num_flow_feat_channels, seq[0].kernel_size[0]) and seq[0].bias is not None:
             c2 = seq[2]
-            if self.overlap_conv_backward and torch.is_grad_enabled() and c2.weight.requires_grad \
-                    and (seq[0].weight.requires_grad or seq[0].bias.requires_grad):
-                # stem + conv2 as one autograd node whose backward runs conv2's wgrad beside dgrad + stem gradients
-                feat = flow_stem_conv(stem_flows, seq[0].weight, seq[0].bias, stem_clamp, seq[1].negative_slope,
-                                      c2.weight, c2.stride, c2.padding, c2.dilation, c2.groups)
-            else:
-                act1 = flow_stem(stem_flows, seq[0].weight, seq[0].bias, stem_clamp, seq[1].negative_slope)
-                feat = self._conv2(act1, c2)
+            act1 = flow_stem(stem_flows, seq[0].weight, seq[0].bias, stem_clamp, seq[1].negative_slope)
+            feat = self._conv2(act1, c2)
             if c2.bias is None:
                 return feat, None
             if feat.is_contiguous(memory_format=torch.channels_last):
@@ -219,10 +217,9 @@ class FlowAggregationHeadWithResidual(nn.Module):
             return feat + c2.bias.view(1, -1, 1, 1), None       # cuDNN answered in NCHW: plain bias add
         return seq[2](seq[1](seq[0](flow))), None
 
-    def _conv2(self, x, c2):
-        """bias-free second conv; with overlap_conv_backward its data- and weight-gradient kernels run on two streams."""
-        if self.overlap_conv_backward and x.is_cuda and torch.is_grad_enabled() and (x.requires_grad or c2.weight.requires_grad):
-            return conv2d_dual_stream(x, c2.weight, c2.stride, c2.padding, c2.dilation, c2.groups)
+    @staticmethod
+    def _conv2(x, c2):
+        """bias-free second conv (general head shapes: ATen / cuDNN)."""
         return F.conv2d(x, c2.weight, None, c2.stride, c2.padding, c2.dilation, c2.groups)
 
     @staticmethod
@@ -270,12 +267,35 @@ class FlowAggregationHeadWithResidual(nn.Module):
         l0, l2 = self.flow_feat_after_agg[0], self.flow_feat_after_agg[2]
         return l0.weight, l0.bias, l2.weight, l2.bias
 
+    def _tc_head_supported(self) -> bool:
+        """Default head shape: the whole head runs as one autograd node on the library's own kernels (fused_head.py)."""
+        seq = self.flow_feat_before_agg
+        c1, c2 = seq[0], seq[2]
+        return bool(self.tensor_core_conv and self.handwritten_stem and self.channels_last_features
+                    and self.num_flow_feat_channels == 64 and self._fused_clamp()
+                    and c1.bias is not None and c2.bias is not None and conv64_supported(c2)
+                    and c1.kernel_size[0] in (1, 3, 5) and c1.kernel_size[0] == c1.kernel_size[1]
+                    and tuple(c1.padding) == ((c1.kernel_size[0] - 1) // 2,) * 2 and tuple(c1.stride) == (1, 1)
+                    and 0.0 <= seq[1].negative_slope <= 1.0)
+
     def _run(self, masks5, flows, resids, *, want_vis, vis_norm, inv_n=0.0):
         """masks5 [B,ndir,K,H,W]; flows / resids: per-direction lists."""
         self._check_residual_mode()
         if not masks5.is_cuda:
             raise RuntimeError("FlowAggregationHeadWithResidual (B200) needs CUDA tensors; there is no CPU fallback")
         B, ndir, K, H, W = masks5.shape
+        in_autocast = torch.is_autocast_enabled()
+        if self._tc_head_supported():
+            with torch.autocast(device_type="cuda", enabled=False):
+                resids = self._resize_residuals([r.float() for r in resids])
+                for r in resids:
+                    assert r.shape[-2:] == (H, W), f"residual spatial size {tuple(r.shape[-2:])} != mask size {(H, W)}"
+                spec = self._spec(K, H, W, want_vis=want_vis, vis_norm=vis_norm, inv_n=inv_n, clamp_fused=True)
+                nprod = self.conv_precision if self.conv_precision is not None else default_nprod(in_autocast)
+                seq = self.flow_feat_before_agg
+                out = RcfHeadFn.apply(spec, int(nprod), float(seq[1].negative_slope), masks5.float(), seq[0].weight, seq[0].bias,
+                                      seq[2].weight, seq[2].bias, *self._mlp_params(), *[f.float() for f in flows], *resids)
+            return out[0], out[1], tuple(out[2:])
         with torch.autocast(device_type="cuda", enabled=False):
             masks5 = masks5.float()
             k_flows, c_flows, rs = [], [], []

@@ -58,7 +58,7 @@ int main(void) {
   F(RcfDesc,vis_bstride); F(RcfDesc,vis_dstride); F(RcfDesc,vis_scale); F(RcfDesc,feat_lrelu_slope); F(RcfDesc,feat_nhwc);
   F(RcfInputs,mask); F(RcfInputs,flow); F(RcfInputs,resid); F(RcfInputs,feat); F(RcfInputs,theta); F(RcfInputs,w1); F(RcfInputs,b1); F(RcfInputs,w2); F(RcfInputs,b2); F(RcfInputs,feat_bias);
   F(RcfVisOut,gt); F(RcfVisOut,pred); F(RcfVisOut,agg); F(RcfVisOut,res); F(RcfVisOut,aff);
-  F(RcfGrads,dmask); F(RcfGrads,dresid); F(RcfGrads,dfeat); F(RcfGrads,dtheta); F(RcfGrads,dw1); F(RcfGrads,db1); F(RcfGrads,dw2); F(RcfGrads,db2); F(RcfGrads,dfeat_bias);
+  F(RcfGrads,dmask); F(RcfGrads,dresid); F(RcfGrads,dfeat); F(RcfGrads,dtheta); F(RcfGrads,dw1); F(RcfGrads,db1); F(RcfGrads,dw2); F(RcfGrads,db2); F(RcfGrads,dfeat_bias); F(RcfGrads,dfeat_hi); F(RcfGrads,dfeat_lo);
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as td:

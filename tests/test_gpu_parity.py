@@ -515,18 +515,3 @@ def test_programmatic_dependent_launch_is_bit_identical(rcf):
     torch.cuda.synchronize()
     for l_, g_ in outs:
         assert torch.equal(l_, ref_loss) and torch.equal(g_, ref_g)
-
-
-def test_overlapped_conv_backward_matches_default(rcf):
-    """head.overlap_conv_backward (stem + conv2 as one autograd node, wgrad on a side stream) only reschedules kernels."""
-    g = Golden("free_l1")
-    res = []
-    for ov in (False, True):
-        head = build_head(rcf, g)
-        head.overlap_conv_backward = ov
-        flows, loss, grads = run_head(head, g.inputs, g.gbar)
-        torch.cuda.synchronize()
-        res.append((float(loss["seg"]), grads["d_masks"].clone(), {n: p.grad.clone() for n, p in head.named_parameters()}))
-    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])
-    for n in res[0][2]:
-        assert rel_l2(res[1][2][n].cpu().numpy(), res[0][2][n].cpu().numpy()) < 1e-5, n

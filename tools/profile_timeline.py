@@ -23,6 +23,8 @@ ap.add_argument("--H", type=int, default=96); ap.add_argument("--W", type=int, d
 ap.add_argument("--Cf", type=int, default=64); ap.add_argument("--ks", type=int, default=3)
 ap.add_argument("--affine", action="store_true"); ap.add_argument("--resize", action="store_true")
 ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--nprod", type=int, default=0, help="conv_precision of the tcgen05 convs (0 = follow torch settings)")
+ap.add_argument("--no-tc", action="store_true", help="second conv through cuDNN (round-1 path)")
 ap.add_argument("--cudnn-benchmark", action="store_true", help="torch.backends.cudnn.benchmark = True (algorithm search)")
 a = ap.parse_args()
 torch.backends.cudnn.benchmark = bool(a.cudnn_benchmark)
@@ -34,6 +36,8 @@ head = pkg.FlowAggregationHeadWithResidual(args=None, create_flownet=True, mask_
                                            num_flow_feat_channels=a.Cf, flow_feat_before_agg_kernel_size=a.ks,
                                            allow_residual_resize=a.resize, **kw).to(dev)
 head.return_flows = False
+head.tensor_core_conv = not a.no_tc
+head.conv_precision = a.nprod or None
 g = torch.Generator(device=dev).manual_seed(0)
 masks = torch.softmax(torch.randn(B, 2, K, H, W, device=dev, generator=g) * 2, dim=2).requires_grad_(True)
 fw = torch.randn(B, 1, 2, H, W, device=dev, generator=g) * 8
