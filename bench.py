@@ -12,13 +12,17 @@ all-reduce of 2 floats per step (issued asynchronously, off the critical path).
 
   value  : device-resident loss core (theta supplied = SURVEY 8(d) "Scope L"): rcf_forward + rcf_backward
            through the C ABI, samples/s over all ranks, CUDA-event timed, max over ranks.
-  e2e    : the drop-in nn.Module call (FlowAggregationHeadWithResidual with the loss-core proxy feature
-           branch Cf=2,k=1 of SURVEY 8(d)) fed from PINNED HOST buffers every step: H2D of masks/flows/
-           residuals, fwd+bwd, D2H of the loss scalars and of the mask/residual gradients.
+  e2e    : the drop-in nn.Module call (FlowAggregationHeadWithResidual with the reference's DEFAULT constructor:
+           64 feature channels, 3x3 convs -- conv stem, tcgen05 convs, pooling, MLP, loss, all in librcf_loss.so) fed
+           from PINNED HOST buffers every step: H2D of masks/flows/residuals, fwd+bwd, D2H of the loss scalars and
+           of the mask/residual gradients.
   roofline: dominant kernel k_bwd (streaming backward): algorithmic bytes per launch / mean CUDA-event
            duration of that kernel inside the timed region (library timing hook), vs MEASURED_PEAKS.json.
   cpu_baseline: oracle/torch_port.py (op-for-op PyTorch CPU port of the reference head, pinned to the
-           reference's outputs by tests) on the host cores, bounded sample (B=2), rank 0, N=1 only.
+           reference's outputs by tests; same default constructor) on the host cores, bounded sample (B=2), rank 0, N=1.
+  extras : the rest of BASELINE.json's configs in the same record: loss-core sweep (C2 affine, C4 K=2/4/8, C5, FBMS),
+           C3 as written (global B=64 split over the ranks, free + affine), the drop-in module device-resident
+           (value_module), the tcgen05 conv kernels next to cuDNN, training shapes, PyTorch-eager port on the same GPU.
 --impl reference times that CPU port alone on the same config (the reference itself is Python under
 /root/reference, which does not exist on the GPU box).
 """
@@ -37,15 +41,29 @@ if ROOT not in sys.path:
 METRIC = "RCF loss fwd+bwd frames/sec and % HBM roofline at 1/2/4/8 B200 vs host-CPU ref"
 UNIT = "samples/s"
 B_PER_GPU, K, H, W = 16, 4, 480, 854
-HEAD_KW = dict(mask_layer=K, mask_size=(H, W), free_residual=True, clamp_flow_t=20.0,
-               num_flow_feat_channels=2, flow_feat_before_agg_kernel_size=1)
+HEAD_KW = dict(mask_layer=K, mask_size=(H, W), free_residual=True, clamp_flow_t=20.0)     # default head: Cf=64, 3x3 convs
+NBLOCKS = 5          # timed blocks of `steps` steps each; the median block is reported
+
+
+def synthetic_inputs(B, K_, H_, W_, seed, device=None):
+    """SURVEY.md 8(d) synthetic inputs from torch's CPU generator (bit-reproducible on any machine)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    masks = torch.softmax(torch.randn(B, 2, K_, H_, W_, generator=g) * 2.0, dim=2)
+    fw = torch.randn(B, 1, 2, H_, W_, generator=g) * 8.0
+    bw = torch.randn(B, 1, 2, H_, W_, generator=g) * 8.0
+    rfw = torch.randn(B, 2 * K_, H_, W_, generator=g) * 5.0
+    rbw = torch.randn(B, 2 * K_, H_, W_, generator=g) * 5.0
+    out = (masks, fw, bw, rfw, rbw)
+    return tuple(t.to(device) for t in out) if device is not None else out
 
 
 def workload_config(n_gpus):
     return {
         "workload": f"C2: RCF loss fwd+bwd, B={B_PER_GPU}/GPU, K={K}, {H}x{W}, free_residual+L1+clamp20 (stage-1 DAVIS flags)",
         "value_path": "loss core, theta supplied (SURVEY 8d Scope L), C ABI rcf_forward+rcf_backward, device-resident",
-        "e2e_path": "drop-in head, proxy feature branch Cf=2 k=1, pinned host buffers in, loss+grads out",
+        "e2e_path": "drop-in head, default constructor (Cf=64, 3x3 convs: stem + tcgen05 convs + pooling + MLP + loss), "
+                    "pinned host buffers in, loss+grads out",
         "global_batch": B_PER_GPU * n_gpus, "parallelism": f"batch-sharded x{n_gpus}",
         "l2_policy": "inputs (735 MB/GPU) larger than L2 (126 MB); no flush needed",
         "algorithmic_bytes_per_sample": 2 * H * W * (36 * K + 16),
@@ -137,7 +155,7 @@ def cpu_port_time(steps, warmup, budget_s=150.0):
     """Times oracle/torch_port.py (the reference's op sequence in PyTorch CPU) on a bounded sample."""
     import torch
 
-    from oracle.torch_port import PortedHead, synthetic_inputs
+    from oracle.torch_port import PortedHead
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     Bs = 2
@@ -163,7 +181,7 @@ def cpu_port_time(steps, warmup, budget_s=150.0):
         t0 = time.perf_counter(); step(); times.append(time.perf_counter() - t0)
     mean = sum(times) / len(times)
     return {"value": Bs / mean, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"B={Bs} of the C2 workload ({K=}, {H}x{W}, proxy head Cf=2 k=1), {len(times)} timed steps, "
+            "sample": f"B={Bs} of the C2 workload ({K=}, {H}x{W}, default head Cf=64 3x3), {len(times)} timed steps, "
                       f"mean {mean * 1e3:.1f} ms/step, best {min(times) * 1e3:.1f} ms; torch {torch.__version__} CPU, "
                       f"{cores} threads"}, mean, steps
 
@@ -206,7 +224,6 @@ def run_ours(args):
     B = B_PER_GPU
     P = H * W
     inv_n = 1.0 / (B * world * 2 * P)
-    from oracle.torch_port import synthetic_inputs   # input generator only (torch CPU generator)
     masks_h, fw_h, bw_h, rfw_h, rbw_h = synthetic_inputs(B, K, H, W, seed=rank)
     masks = masks_h.to(dev).requires_grad_(True)
     fw, bw = fw_h.to(dev), bw_h.to(dev)
@@ -287,20 +304,27 @@ def run_ours(args):
         for _ in range(3):
             g_.replay()
         barrier()
-        gs_, ge_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        gs_.record()
-        for _ in range(args.steps):
-            g_.replay()
-            if world > 1:      # the per-step loss all-reduce stays outside the graph, asynchronous
-                lr = loss_g.detach().clone()
-                pending.append((dist.all_reduce(lr, async_op=True), lr))
-        ge_.record()
-        clocks.poll_until(ge_)
-        barrier()
-        for w, _ in pending:
-            w.wait()
-        pending.clear()
-        graph_ms = gs_.elapsed_time(ge_) / args.steps
+        block_ms = []
+        for _blk in range(NBLOCKS):          # NBLOCKS regions of exactly `steps` steps, each bracketed by barrier + sync
+            barrier()
+            gs_, ge_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            gs_.record()
+            for _ in range(args.steps):
+                g_.replay()
+                if world > 1:      # the per-step loss all-reduce stays outside the graph, asynchronous
+                    lr = loss_g.detach().clone()
+                    pending.append((dist.all_reduce(lr, async_op=True), lr))
+            ge_.record()
+            clocks.poll_until(ge_)
+            barrier()
+            for w, _ in pending:
+                w.wait()
+            pending.clear()
+            tb = torch.tensor([gs_.elapsed_time(ge_) / args.steps], device=dev)
+            if world > 1:
+                dist.all_reduce(tb, op=dist.ReduceOp.MAX)      # max over ranks, per block
+            block_ms.append(float(tb))
+        graph_ms = sorted(block_ms)[len(block_ms) // 2]
         lfin = loss_g.detach().clone()
         if world > 1:
             dist.all_reduce(lfin)
@@ -309,11 +333,13 @@ def run_ours(args):
         print(f"[bench] CUDA graph capture unavailable ({type(ex).__name__}: {str(ex)[:300]}); using eager timing",
               file=sys.stderr)
         torch.cuda.synchronize()
-    best_ms = eager_ms if graph_ms is None else min(graph_ms, eager_ms)
-    t = torch.tensor([best_ms, eager_ms, graph_ms if graph_ms is not None else -1.0], device=dev)
+    t = torch.tensor([eager_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, eager_ms, graph_ms = float(t[0]), float(t[1]), float(t[2])
+    eager_ms = float(t[0])
+    if graph_ms is None:
+        block_ms, graph_ms = [], -1.0
+    ms_step = eager_ms if graph_ms <= 0 else min(graph_ms, eager_ms)
     value = B * world / (ms_step * 1e-3)
     kb_ms = sorted(a.elapsed_time(b) for a, b in ev_pairs)
     kb_mean = sum(kb_ms) / len(kb_ms)
@@ -405,8 +431,12 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "pcie_gbs_each_way": [h2d / e2e_ms / 1e6, d2h / e2e_ms / 1e6],
-                    "note": "PCIe-bound; copies of neighbouring steps overlap compute on 3 streams"},
-            "gpu_launches": 5 * args.steps,   # k_loss, k_finalize, k_loss_sum | k_segment_bwd, k_bwd (single-pass forward)
+                    "note": "PCIe-bound; copies of neighbouring steps overlap compute on 3 streams",
+                    "conv_precision": "follows torch.backends.cudnn.allow_tf32 (torch default True -> 2 bf16 products, "
+                                      "weights hi+lo; False -> 3 products, fp32-grade)"},
+            # value region: k_loss, k_finalize, k_loss_sum | k_segment_bwd, k_bwd per step (single-pass forward), NBLOCKS blocks;
+            # e2e region: the 23 kernels of the default head per step (profiles/r02_timeline_c1_np2.md)
+            "gpu_launches": 5 * args.steps * NBLOCKS + 23 * e2e_steps,
             "roofline": {"bound": "hbm", "kernel": "k_bwd<K=4,D=0,PX=4> (streaming backward)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": read_traffic("k_bwd<4, 0, 4>"),
                          "peak_source": peak_src, "kernel_ms": kb_mean, "kernel_ms_min": kb_ms[0],
@@ -414,14 +444,20 @@ def run_ours(args):
             "step_roofline": {"algorithmic_gbs": step_gbs, "frac": step_gbs / peak,
                               "frame_directions_per_s": 2 * value},
             "timing": {"eager_ms_per_step": eager_ms, "cuda_graph_ms_per_step": (graph_ms if graph_ms > 0 else None),
+                       "cuda_graph_block_ms": block_ms, "blocks": f"{NBLOCKS} x {args.steps} steps, median block reported",
                        "cpu_enqueue_ms_per_step": cpu_enqueue_ms,
                        "value_from": "cuda_graph" if (graph_ms > 0 and graph_ms <= eager_ms) else "eager"},
             "loss": loss_val,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"], _, _ = cpu_port_time(20, 2, budget_s=25.0)
-            if not args.no_extras:
-                line["extras"] = extras(pkg, dev)
+            line["cpu_baseline"], _, _ = cpu_port_time(8, 1, budget_s=25.0)
+        line["extras"] = {}
+    c3 = None if args.no_extras else c3_strong_scaling(pkg, dev, world, rank)
+    if rank == 0:
+        if c3 is not None:
+            line["extras"]["c3_strong_scaling_global_B64"] = c3
+        if world == 1 and not args.no_extras:
+            line["extras"].update(extras(pkg, dev))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -441,21 +477,212 @@ def _time_cuda(fn, steps, warmup=3):
     return s.elapsed_time(e) / steps
 
 
+
+def _graph_time(step, steps, blocks=3, sync=None):
+    """Captures `step` (a fwd+bwd closure) into one CUDA graph and times `blocks` x `steps` replays; median block, ms/step."""
+    import gc
+
+    import torch
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    gc.collect()
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        out = step()
+    for _ in range(3):
+        gr.replay()
+    res = []
+    for _ in range(blocks):
+        if sync is not None:
+            sync()
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(steps):
+            gr.replay()
+        e_.record()
+        torch.cuda.synchronize()
+        res.append(s_.elapsed_time(e_) / steps)
+    del out, gr
+    torch.cuda.empty_cache()
+    return sorted(res)[len(res) // 2]
+
+
+def _core_step(pkg, dev, B, K_, H_, W_, D, robust=False, inv_n=0.0, seed=0):
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    masks = torch.softmax(torch.randn(B, 2, K_, H_, W_, device=dev, generator=g) * 2, dim=2).requires_grad_(True)
+    flows = [torch.randn(B, 2, H_, W_, device=dev, generator=g) * 8 for _ in range(2)]
+    resids = [(torch.randn(B, 2 * K_, H_, W_, device=dev, generator=g) * 5).requires_grad_(True) for _ in range(2)]
+    thetas = [torch.randn(B, 2, K_, device=dev, generator=g).requires_grad_(True) for _ in range(2)]
+    spec = pkg.LossSpec(K=K_, H=H_, W=W_, D=D, Cf=0, clamp_t=20.0, robust=robust, inv_n=inv_n)
+    gl = torch.ones(2, device=dev)
+
+    def step():
+        loss, _ = pkg.rcf_motion_loss(spec, masks, flows, resids, thetas=thetas)
+        return loss, torch.autograd.grad(loss, [masks, *resids, *thetas], grad_outputs=gl)
+    return step
+
+
+def _module_step(pkg, dev, B, K_, H_, W_, kw, inv_n=0.0, nprod=None, seed=0):
+    import torch
+    torch.manual_seed(1)
+    head = pkg.FlowAggregationHeadWithResidual(args=None, create_flownet=True, mask_layer=K_, mask_size=(H_, W_), **kw).to(dev)
+    head.return_flows = False
+    head.loss_inv_n = inv_n
+    head.conv_precision = nprod
+    ins = synthetic_inputs(B, K_, H_, W_, seed=seed, device=dev)
+    m = ins[0].requires_grad_(True)
+    r1 = ins[3].requires_grad_(True)
+    r2 = ins[4].requires_grad_(True)
+    imgs = torch.zeros(B, 2, 3, 8, 8)
+    params = list(head.parameters())
+
+    def step():
+        _, l = head(imgs, m, ins[1], ins[2], r1, r2)
+        return torch.autograd.grad(l["seg"], [m, r1, r2, *params])
+    return step
+
+
+def loss_core_sweep(pkg, dev):
+    """BASELINE.json configs C2 (affine), C4 (K = 2/4/8, B = 32), C5 (three resolutions) and the FBMS K = 3 affine flags
+    through the loss core (theta supplied), CUDA-graph replay; `frac` = SURVEY 8(d) algorithmic bytes (36K+16 B/px/dir)
+    / time / measured HBM copy rate.  Affine rows need pass 1 (4K+8 B/px/dir more traffic: ceiling 160/184 = 87 % at K=4)."""
+    peak, _ = read_peaks()
+    rows = [("C2_free", 16, 4, 480, 854, 0), ("C2_affine", 16, 4, 480, 854, 2), ("C4_K2_free", 32, 2, 480, 854, 0),
+            ("C4_K4_free", 32, 4, 480, 854, 0), ("C4_K8_free", 32, 8, 480, 854, 0), ("C4_K8_affine", 32, 8, 480, 854, 2),
+            ("FBMS_K3_affine", 16, 3, 480, 854, 2), ("C5_240x427_free", 16, 4, 240, 427, 0),
+            ("C5_480x854_free", 16, 4, 480, 854, 0), ("C5_1080x1920_free", 16, 4, 1080, 1920, 0),
+            ("DAVIS_train_96x96_B8_free", 8, 4, 96, 96, 0), ("STv2_train_48x48_B8_affine", 8, 4, 48, 48, 2)]
+    out = {}
+    for name, B, K_, H_, W_, D in rows:
+        ms = _graph_time(_core_step(pkg, dev, B, K_, H_, W_, D), 20)
+        alg = B * 2 * H_ * W_ * (36 * K_ + 16)
+        out[name] = {"B": B, "K": K_, "HxW": f"{H_}x{W_}", "mode": {0: "free", 2: "affine"}[D], "ms_per_step": ms,
+                     "samples_per_s": B / ms * 1e3, "algorithmic_gbs": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak}
+    return out
+
+
+def module_throughput(pkg, dev):
+    """The drop-in nn.Module (default head: Cf = 64, 3x3 convs) device-resident at C2 (B = 16) and C1 (B = 2), fwd + bwd
+    incl. all 8 parameter gradients, CUDA-graph replay, for each conv precision."""
+    out = {}
+    for name, B in (("C2_B16", 16), ("C1_B2", 2)):
+        for nprod in (2, 3, 1):
+            ms = _graph_time(_module_step(pkg, dev, B, K, H, W, dict(free_residual=True, clamp_flow_t=20.0), nprod=nprod), 5)
+            out[f"{name}_nprod{nprod}"] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3}
+    out["note"] = ("nprod = bf16 products per fp32 product in the tcgen05 convs: 3 fp32-grade (torch.backends.cudnn.allow_tf32 = "
+                   "False), 2 weights hi+lo x bf16 activations (torch default), 1 plain bf16 (autocast)")
+    return out
+
+
+def conv_kernels(pkg, dev):
+    """The three tcgen05 conv kernels against the cuDNN kernels they replace, same tensors (4 x 64 x 480 x 854 = C1)."""
+    import torch
+    import torch.nn.functional as F
+
+    from rcf_unsupvideoseg_b200 import conv64 as c64
+    N_ = 4
+    x = torch.randn(N_, 64, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(N_, 64, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(64, 64, 3, 3, device=dev) / 24
+    wp, wpt = c64.pack_weights(w, False), c64.pack_weights(w, True)
+    hi, lo = c64.split_bf16(x)
+    g_hi, g_lo = c64.split_bf16(gy)
+    flops = 2.0 * N_ * H * W * 64 * 64 * 9
+    out = {"gflop_per_kernel": flops / 1e9}
+    for nprod in (1, 2, 3):
+        t_f = _time_cuda(lambda: c64.conv64_pair(hi, lo, wp, nprod), 10) * 1e3
+        t_d = _time_cuda(lambda: c64.conv64_pair(g_hi, g_lo, wpt, nprod), 10) * 1e3
+        t_w = _time_cuda(lambda: c64.conv64_wgrad_pair(hi, lo, g_hi, g_lo, nprod), 10) * 1e3
+        out[f"tcgen05_nprod{nprod}_us"] = {"fprop": t_f, "dgrad": t_d, "wgrad": t_w, "fprop_tflops": flops / t_f / 1e6}
+    old = torch.backends.cudnn.allow_tf32
+    for tf32 in (True, False):
+        torch.backends.cudnn.allow_tf32 = tf32
+        cb = lambda mask: torch.ops.aten.convolution_backward(gy, x, w, None, (1, 1), (1, 1), (1, 1), False, (0, 0), 1, mask)  # noqa: E731
+        out[f"cudnn_{'tf32' if tf32 else 'fp32'}_us"] = {
+            "fprop": _time_cuda(lambda: F.conv2d(x, w, None, 1, 1), 5) * 1e3,
+            "dgrad": _time_cuda(lambda: cb((True, False, False)), 5) * 1e3,
+            "wgrad": _time_cuda(lambda: cb((False, True, False)), 5) * 1e3}
+    torch.backends.cudnn.allow_tf32 = old
+    return out
+
+
+def c3_strong_scaling(pkg, dev, world, rank):
+    """BASELINE.json config C3 as written: global batch 64 at K = 4, 480x854, split over the ranks (64 / N per GPU:
+    strong scaling), free_residual and free_residual_with_affine, loss core and drop-in module.  The mean's normaliser is
+    the global element count, so per-rank losses sum to the global loss (one 2-float NCCL all-reduce per step, outside
+    the timed graph).  Times are the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    GB = 64
+    if GB % world:
+        return None
+    Bl = GB // world
+    inv_n = 1.0 / (GB * 2 * H * W)
+    peak, _ = read_peaks()
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+
+    out = {"global_batch": GB, "per_gpu_batch": Bl, "n_gpus": world, "scaling": "strong"}
+    for name, mk in (("loss_core_free", lambda: _core_step(pkg, dev, Bl, K, H, W, 0, inv_n=inv_n, seed=rank)),
+                     ("loss_core_affine", lambda: _core_step(pkg, dev, Bl, K, H, W, 2, inv_n=inv_n, seed=rank)),
+                     ("module_free_default_head", lambda: _module_step(pkg, dev, Bl, K, H, W, dict(free_residual=True, clamp_flow_t=20.0),
+                                                                       inv_n=inv_n, seed=rank)),
+                     ("module_affine_default_head", lambda: _module_step(pkg, dev, Bl, K, H, W,
+                                                                         dict(free_residual_with_affine=True, clamp_flow_t=20.0),
+                                                                         inv_n=inv_n, seed=rank))):
+        try:
+            ms = _graph_time(mk(), 10 if "core" in name else 3, sync=sync)
+        except Exception as ex:  # noqa: BLE001
+            ms = float("nan")
+            print(f"[bench] c3 {name}: {type(ex).__name__}: {str(ex)[:200]}", file=sys.stderr)
+            torch.cuda.empty_cache()
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+        rec = {"ms_per_step": ms, "samples_per_s": GB / ms * 1e3}
+        if "core" in name:
+            rec["frac_of_hbm_peak_per_gpu"] = Bl * 2 * H * W * (36 * K + 16) / ms / 1e6 / peak
+        out[name] = rec
+    return out
+
+
 def extras(pkg, dev):
     """Add-on measurements reported beside the headline (SURVEY.md 8(d) 'report separately'):
     the same workloads through (a) the drop-in head and (b) the op-for-op PyTorch port of the reference
     running EAGER ON THE SAME GPU (the GPU baseline the reference user has today)."""
     import torch
 
-    from oracle.torch_port import PortedHead, synthetic_inputs
+    from oracle.torch_port import PortedHead       # baseline arm only: the reference's op sequence, eager on this GPU
     out = {}
+    try:
+        out["loss_core_sweep"] = loss_core_sweep(pkg, dev)
+    except Exception as ex:  # noqa: BLE001
+        out["loss_core_sweep"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+        torch.cuda.empty_cache()
+    try:
+        out["value_module"] = module_throughput(pkg, dev)
+    except Exception as ex:  # noqa: BLE001
+        out["value_module"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+        torch.cuda.empty_cache()
+    try:
+        out["conv64_kernels_vs_cudnn_4x64x480x854"] = conv_kernels(pkg, dev)
+    except Exception as ex:  # noqa: BLE001
+        out["conv64_kernels_vs_cudnn_4x64x480x854"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+        torch.cuda.empty_cache()
     cases = {
         "c2_proxy_head_B16_480x854": (16, 4, 480, 854, dict(free_residual=True, clamp_flow_t=20.0, num_flow_feat_channels=2,
                                                              flow_feat_before_agg_kernel_size=1), 10),
-        "c2_affine_proxy_head_B16_480x854": (16, 4, 480, 854, dict(free_residual_with_affine=True, clamp_flow_t=20.0,
-                                                                   num_flow_feat_channels=2,
-                                                                   flow_feat_before_agg_kernel_size=1), 10),
-        "c1_full_head_B2_480x854": (2, 4, 480, 854, dict(free_residual=True, clamp_flow_t=20.0), 5),
+        "c1_full_head_B2_480x854": (2, 4, 480, 854, dict(free_residual=True, clamp_flow_t=20.0), 10),
         "davis_stage1_train_B8_96x96_full_head": (8, 4, 96, 96, dict(free_residual=True, clamp_flow_t=20.0), 50),
         "stv2_stage1_train_B8_48x48_affine_full_head": (8, 4, 48, 48, dict(free_residual_with_affine=True, clamp_flow_t=20.0), 50),
     }

@@ -158,6 +158,108 @@ def test_full_size_c1_against_reference_scalars(rcf, case):
             assert abs(a - b) <= 1e-3 * scale + 1e-4 * abs(b), (name, a, b)
 
 
+def _r2_cases():
+    path = os.path.join(GOLDEN_DIR, "full_size_scalars_r2.json")
+    if not os.path.exists(path):
+        return []
+    with open(path) as f:
+        return sorted(json.load(f).keys())
+
+
+@pytest.mark.parametrize("case", _r2_cases())
+def test_full_size_baseline_shapes_against_reference_scalars(rcf, case):
+    """The remaining BASELINE.json shapes at FULL size against the unmodified reference (fp32, CPU; fixtures made by
+    tests/golden/make_full_size.py): C4 K = 2 / 8 at 480x854 (K = 8: the 64-bit mask packs), C5 240x427 and 1080x1920
+    (2 M pixels per plane: index arithmetic), and the affine fit at K = 3 (FBMS) and K = 8."""
+    with open(os.path.join(GOLDEN_DIR, "full_size_scalars_r2.json")) as f:
+        ref = json.load(f)[case]
+    s = ref["shape"]
+    torch.manual_seed(ref["param_seed"])
+    head = rcf.FlowAggregationHeadWithResidual(args=None, create_flownet=True, mask_layer=s["K"],
+                                               mask_size=(s["H"], s["W"]), **ref["kwargs"]).cuda()
+    masks, fw, bw, rfw, rbw = _torch_inputs(s["B"], s["K"], s["H"], s["W"], ref["seed"])
+    masks.requires_grad_(True); rfw.requires_grad_(True); rbw.requires_grad_(True)
+    imgs = torch.zeros(s["B"], 2, 3, 8, 8, device="cuda")
+    flows, loss = head(imgs, masks, fw, bw, rfw, rbw)
+    loss["seg"].backward()
+    torch.cuda.synchronize()
+    for k in ("seg_fw", "seg_bw", "seg"):
+        assert abs(float(loss[k]) - ref["loss"][k]) <= LOSS_RTOL * abs(ref["loss"][k]), k
+    for name, t in (("d_masks", masks.grad), ("d_resid_fw", rfw.grad), ("d_resid_bw", rbw.grad),
+                    ("pred_flow", flows["pred_flow"][0])):
+        cs = _checksum(t)
+        assert abs(cs["l2"] - ref[name]["l2"]) <= GRAD_RTOL * ref[name]["l2"], name
+        assert abs(cs["abs_sum"] - ref[name]["abs_sum"]) <= GRAD_RTOL * ref[name]["abs_sum"], name
+        scale = ref[name]["l2"] / np.sqrt(t.numel())
+        for a, b in zip(cs["sample"], ref[name]["sample"]):
+            assert abs(a - b) <= 1e-3 * scale + 1e-4 * abs(b), (name, a, b)
+
+
+@pytest.mark.parametrize("case", ["c1_free_l1_full_head", "c1_affine_l1_proxy_head"])
+def test_c2_batch16_against_tiled_c1_reference(rcf, case):
+    """BASELINE.json's headline shape C2 (B = 16, K = 4, 480x854) against the reference: the batch is the C1 fixture's
+    batch (B = 2) repeated 8 times, so the loss is C1's and every gradient is C1's divided by 8 (mean over 8x the
+    elements): l2 over the tiled tensor = l2_C1 / sqrt(8), abs_sum = abs_sum_C1, and the parameter gradients are C1's."""
+    with open(os.path.join(GOLDEN_DIR, "full_size_scalars.json")) as f:
+        ref = json.load(f)[case]
+    s = ref["shape"]
+    R = 8
+    torch.manual_seed(ref["param_seed"])
+    head = rcf.FlowAggregationHeadWithResidual(args=None, create_flownet=True, mask_layer=s["K"],
+                                               mask_size=(s["H"], s["W"]), **ref["kwargs"]).cuda()
+    head.return_flows = False
+    base = _torch_inputs(s["B"], s["K"], s["H"], s["W"], ref["seed"])
+    masks, fw, bw, rfw, rbw = [t.repeat(R, *([1] * (t.dim() - 1))) for t in base]
+    masks.requires_grad_(True); rfw.requires_grad_(True); rbw.requires_grad_(True)
+    imgs = torch.zeros(s["B"] * R, 2, 3, 8, 8, device="cuda")
+    _, loss = head(imgs, masks, fw, bw, rfw, rbw)
+    loss["seg"].backward()
+    torch.cuda.synchronize()
+    for k in ("seg_fw", "seg_bw", "seg"):
+        assert abs(float(loss[k]) - ref["loss"][k]) <= LOSS_RTOL * abs(ref["loss"][k]), k
+    for name, t in (("d_masks", masks.grad), ("d_resid_fw", rfw.grad), ("d_resid_bw", rbw.grad)):
+        cs = dict(l2=float(t.double().norm()), abs_sum=float(t.double().abs().sum()))
+        assert abs(cs["l2"] * np.sqrt(R) - ref[name]["l2"]) <= GRAD_RTOL * ref[name]["l2"], name
+        assert abs(cs["abs_sum"] - ref[name]["abs_sum"]) <= GRAD_RTOL * ref[name]["abs_sum"], name
+        first = _checksum(t[:s["B"]] * R)                    # the first copy, rescaled, is C1's gradient
+        scale = ref[name]["l2"] / np.sqrt(t[:s["B"]].numel())
+        for a, b in zip(first["sample"], ref[name]["sample"]):
+            assert abs(a - b) <= 1e-3 * scale + 1e-4 * abs(b), (name, a, b)
+    for k, p in head.named_parameters():
+        cs = _checksum(p.grad)
+        assert abs(cs["l2"] - ref["dparams"][k]["l2"]) <= 3e-4 * ref["dparams"][k]["l2"], k
+
+
+def test_head_at_torch_default_tf32_bounds_parameter_gradient_error(rcf):
+    """torch's DEFAULT settings allow TF32 convolutions (what the reference's convs then run in).  The tcgen05 convs follow
+    that switch: allow_tf32 = False -> 3 bf16 products per fp32 product (fp32-grade), True -> 2 products (weights hi+lo,
+    activations rounded to bf16: 8 instead of TF32's 10 mantissa bits on the activation side, full fp32 on the weight side).
+    Against the reference's fp64 results on a 12x14-pixel golden case (no averaging over pixels: the worst case for
+    rounding noise): loss 1e-5 and mask / residual gradients 1e-4 in BOTH modes; parameter gradients 2e-4 fp32-grade,
+    3e-2 in the 2-product mode -- printed next to what the cuDNN TF32 kernels give on the same inputs."""
+    g = Golden("free_l1")
+    errs = {}
+    for mode, allow, tc in (("tcgen05, 2 products (allow_tf32)", True, True), ("tcgen05, 3 products", False, True),
+                            ("cuDNN TF32 (round-1 path)", True, False)):
+        torch.backends.cudnn.allow_tf32 = allow
+        try:
+            head = build_head(rcf, g)
+            head.tensor_core_conv = tc
+            assert head._tc_head_supported() == tc
+            _, loss, grads = run_head(head, g.inputs, g.gbar)
+        finally:
+            torch.backends.cudnn.allow_tf32 = False
+        ref = float(g.ref("f64", "loss.seg"))
+        assert abs(float(loss["seg"]) - ref) <= LOSS_RTOL * abs(ref), mode
+        for k in ("d_masks", "d_resid_fw", "d_resid_bw"):
+            assert rel_l2(grads[k].cpu().numpy(), g.ref("f64", k)) <= GRAD_RTOL, (mode, k)
+        errs[mode] = {k.replace("flow_feat_", ""): rel_l2(p.grad.cpu().numpy(), g.ref("f64", "dparam." + k))
+                      for k, p in head.named_parameters()}
+        print(f"parameter-gradient rel-L2 errors, {mode}: " + ", ".join(f"{k} {v:.1e}" for k, v in errs[mode].items()))
+    assert max(errs["tcgen05, 3 products"].values()) <= 2e-4
+    assert max(errs["tcgen05, 2 products (allow_tf32)"].values()) <= 3e-2
+
+
 def test_full_size_properties(rcf):
     """Size-independent properties at C2-like shapes: determinism, linearity in the upstream gradient,
     batch-shard consistency and direction symmetry."""
