@@ -211,7 +211,7 @@ RCF_API int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstr
  * computes it with the same kernel.
  * nprod: bf16 products per fp32 product: 3 = fp32-grade (hi + lo of both operands, ~1e-5), 2 = weights hi + lo,
  * activations in_hi only (TF32 class), 1 = in_hi x w_hi (autocast class).  in_lo may be NULL unless nprod == 3. */
-#define RCF_CONV64_WPACK_BYTES (9 * 16384)
+#define RCF_CONV64_WPACK_BYTES (9 * 16384 + 2 * (9 * 8192 + 9 * 4096))   /* one-CTA image + the two CTA-pair images */
 RCF_API int rcf_conv64_pack_weights(const float* w, void* wpack, int transpose_flip, void* stream);
 RCF_API int rcf_conv64_forward(const void* in_hi, const void* in_lo, const void* wpack, float* out, int nimg, int H, int W,
                                int nprod, void* stream);
@@ -299,6 +299,7 @@ RCF_API int rcf_debug_time_kernel(int which, void* start_event, void* stop_event
 #define RCF_OPT_L2_HINTS 3       /* evict-first streaming loads of flow/residual in pass 2 (default 1) */
 #define RCF_OPT_SINGLE_PASS 4    /* theta_mode 0 with D == 0: skip pass 1, S_k is accumulated inside pass 2 (default 1) */
 #define RCF_OPT_PDL 5            /* programmatic dependent launch between the library's consecutive kernels (default 1) */
+#define RCF_OPT_CONV64_PAIR 7    /* 1 (default): conv fprop / data gradient on CTA pairs (cta_group::2); 0: one-CTA kernel */
 #define RCF_OPT_CONV64_DEBUG 6   /* measurement only, INVALID results: bit 0 no epilogue stores, bit 1 no producer loads, bit 2 no MMAs */
 RCF_API int rcf_debug_set_option(int option, int value);
 

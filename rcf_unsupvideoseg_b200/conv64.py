@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 
-WPACK_BYTES = 9 * 16384
+WPACK_BYTES = 9 * 16384 + 2 * (9 * 8192 + 9 * 4096)      # RCF_CONV64_WPACK_BYTES
 
 
 def default_nprod(autocast: bool = False) -> int:

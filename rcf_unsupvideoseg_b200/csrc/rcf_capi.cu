@@ -130,8 +130,10 @@ extern "C" int rcf_debug_time_kernel(int which, void* start_event, void* stop_ev
 }
 
 extern "C" void rcf_conv64_set_debug(int v);
+extern "C" void rcf_conv64_set_pair(int v);
 extern "C" int rcf_debug_set_option(int option, int value) {
     if (option == RCF_OPT_CONV64_DEBUG) { rcf_conv64_set_debug(value); return RCF_OK; }
+    if (option == RCF_OPT_CONV64_PAIR) { rcf_conv64_set_pair(value); return RCF_OK; }
     if (option == RCF_OPT_FUSED_FORWARD) { g_fused_forward = value ? 1 : 0; return RCF_OK; }
     if (option == RCF_OPT_FUSED_LAG && value >= 1 && value <= 64) { g_fused_lag = value; return RCF_OK; }
     if (option == RCF_OPT_L2_HINTS) { g_l2_hints = value ? 1 : 0; return RCF_OK; }

@@ -70,6 +70,14 @@ __global__ void k_conv64_pack(const float* __restrict__ w, uint8_t* __restrict__
     uint8_t* base = out + tap * C64_TAP_BYTES + chunk + (k & 7) * 2;
     *reinterpret_cast<uint16_t*>(base + n * 128) = (uint16_t)(hi >> 16);
     *reinterpret_cast<uint16_t*>(base + (64 + n) * 128) = (uint16_t)(lo >> 16);
+    // CTA-pair images (rcf_conv64_pair.cu): rank 0 region Y = hi rows, rank 1 region Y = lo rows; region Z of rank n / 32 =
+    // hi rows of output channels [32 rank, +32)
+    uint8_t* pair = out + C64_W_BYTES;
+    const int inrow = chunk + (k & 7) * 2;
+    *reinterpret_cast<uint16_t*>(pair + tap * 8192 + n * 128 + inrow) = (uint16_t)(hi >> 16);
+    *reinterpret_cast<uint16_t*>(pair + C64_PAIR_IMAGE_BYTES + tap * 8192 + n * 128 + inrow) = (uint16_t)(lo >> 16);
+    *reinterpret_cast<uint16_t*>(pair + (n >> 5) * C64_PAIR_IMAGE_BYTES + C64_PAIR_Y_BYTES + tap * 4096 + (n & 31) * 128 + inrow) =
+        (uint16_t)(hi >> 16);
 }
 
 // fp32 channels-last -> (hi, lo) bf16 channels-last; the library's own producers write the pair directly, this is for
@@ -249,6 +257,7 @@ k_conv64(const Conv64Args a, const __grid_constant__ CUtensorMap tm_hi, const __
 
 int g_conv64_attr_done = 0;
 int g_conv64_debug = 0;
+int g_conv64_pair = 1;          // CTA-pair kernel (rcf_conv64_pair.cu) instead of the one-CTA kernel
 long long* g_conv64_trace = nullptr;
 __device__ int g_conv64_status;
 
@@ -282,6 +291,9 @@ int rcf_make_tmap_nhwc64(CUtensorMap* tm, const void* base, int nimg, int H, int
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? RCF_OK : (int)cudaErrorInvalidValue;
 }
+
+int rcf_conv64_pair_launch(const void* in_hi, const void* in_lo, const void* wpack_pair, float* out, int nimg, int H, int W,
+                           int nprod, cudaStream_t s);
 
 int* rcf_conv64_status_addr() {
     static int* addr = nullptr;          // resolved once (outside any stream capture of later calls)
@@ -321,6 +333,8 @@ RCF_API int rcf_conv64_forward(const void* in_hi, const void* in_lo, const void*
         if (e != cudaSuccess) return (int)e;
         g_conv64_attr_done = 1;
     }
+    if (g_conv64_pair)
+        return rcf_conv64_pair_launch(in_hi, in_lo, (const uint8_t*)wpack + C64_W_BYTES, out, nimg, H, W, nprod, (cudaStream_t)stream);
     Conv64Args a;
     a.g = conv64_make_geom(nimg, H, W);
     a.out = out; a.wpack = (const uint8_t*)wpack; a.debug = g_conv64_debug; a.trace = g_conv64_trace;
@@ -343,6 +357,7 @@ RCF_API int rcf_conv64_forward(const void* in_hi, const void* in_lo, const void*
 }
 
 void rcf_conv64_set_debug(int v) { g_conv64_debug = v; }
+void rcf_conv64_set_pair(int v) { g_conv64_pair = v ? 1 : 0; }
 // Measurement hook: device buffer of 64 x 8 int64 that CTA 0 of the following conv launches fills with clock64 stamps
 // (per tile: 0 tile landed, 1 TMEM stage free, 2 MMAs issued, 3 A buffer free, 4 accumulators complete, 5 epilogue done).
 RCF_API int rcf_debug_conv64_trace(void* buf) { g_conv64_trace = (long long*)buf; return RCF_OK; }

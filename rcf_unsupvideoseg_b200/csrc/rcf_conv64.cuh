@@ -24,6 +24,12 @@
 #define C64_NT 4                 /* accumulator stages in tensor memory: 4 x 128 columns */
 #define C64_SMEM_BYTES (C64_W_BYTES + C64_NA * C64_ABUF_BYTES + 256)
 
+/* CTA-pair kernel (rcf_conv64_pair.cu): per-CTA weight image = region Y (9 taps x 64 rows) + region Z (9 taps x 32 rows) */
+#define C64_PAIR_Y_BYTES (9 * 8192)
+#define C64_PAIR_Z_BYTES (9 * 4096)
+#define C64_PAIR_IMAGE_BYTES (C64_PAIR_Y_BYTES + C64_PAIR_Z_BYTES)
+#define C64_WPACK_TOTAL_BYTES (C64_W_BYTES + 2 * C64_PAIR_IMAGE_BYTES)   /* == RCF_CONV64_WPACK_BYTES */
+
 struct Conv64Geom {
     int nimg, H, W;
     int TW, TR, Wp;              // tile of TR x TW outputs; padded row Wp = TW + 2

@@ -22,6 +22,10 @@ KEYS = [
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active %"),
+    ("sm__inst_executed_pipe_tensor.sum", "tensor pipe instructions"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts (LSU)"),
+    ("smsp__inst_executed_pipe_uniform.sum", "uniform-pipe instructions"),
     ("launch__registers_per_thread", "registers/thread"),
     ("launch__occupancy_limit_registers", "CTAs/SM (register limit)"),
     ("launch__grid_size", "grid"),

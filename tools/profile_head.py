@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--resize", action="store_true", help="residual at half resolution + allow_residual_resize")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--nprod", type=int, default=0, help="conv_precision of the tcgen05 convs (0 = follow torch settings)")
     a = ap.parse_args()
     dev = torch.device("cuda")
     B, K, H, W = a.B, a.K, a.H, a.W
@@ -33,6 +34,7 @@ def main():
                                                clamp_flow_t=20.0, num_flow_feat_channels=a.Cf,
                                                flow_feat_before_agg_kernel_size=a.ks,
                                                allow_residual_resize=a.resize, **kw).to(dev)
+    head.conv_precision = a.nprod or None
     g = torch.Generator(device=dev).manual_seed(0)
     masks = torch.softmax(torch.randn(B, 2, K, H, W, device=dev, generator=g) * 2, dim=2).requires_grad_(True)
     fw = torch.randn(B, 1, 2, H, W, device=dev, generator=g) * 8

@@ -27,10 +27,14 @@ def main():
         wp = c64.pack_weights(w, False)
         flops = 2 * N * H * W * 64 * 64 * 9
         row = [f"{N}x64x{H}x{W}"]
-        for nprod in (1, 2, 3):
-            hi, lo = c64.split_bf16(x)
-            t = timeit(lambda: c64.conv64_pair(hi, lo, wp, nprod))
-            row.append(f"nprod{nprod} {t:8.1f} us ({flops / t / 1e6:6.1f} TFLOP/s)")
+        from rcf_unsupvideoseg_b200 import _lib as _l
+        for pair in (1, 0):
+            _l.load_library().rcf_debug_set_option(7, pair)
+            for nprod in (1, 2, 3):
+                hi, lo = c64.split_bf16(x)
+                t = timeit(lambda: c64.conv64_pair(hi, lo, wp, nprod))
+                row.append(f"{'pair' if pair else 'one-CTA'} nprod{nprod} {t:8.1f} us ({flops / t / 1e6:6.1f} TFLOP/s)")
+        _l.load_library().rcf_debug_set_option(7, 1)
         if "--debug" in sys.argv:
             from rcf_unsupvideoseg_b200 import _lib
             lib = _lib.load_library()
