@@ -215,7 +215,18 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_note = None
     if world > 1:
+        # e2e is host-memory / PCIe bound: bind this rank to the CPUs of its GPU's NUMA node BEFORE the pinned staging
+        # buffers are allocated (first touch puts their pages next to the GPU's root port)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h_ = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            pynvml.nvmlDeviceSetCpuAffinity(h_)
+            numa_note = f"rank bound to the {len(os.sched_getaffinity(0))} CPUs NVML reports as local to GPU {local_rank}"
+        except Exception as ex:  # noqa: BLE001
+            numa_note = f"NUMA binding unavailable ({type(ex).__name__})"
         # keep stdout clean for the one JSON line: NCCL's banner / debug output goes to a file
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/rcf_bench_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
@@ -431,7 +442,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "pcie_gbs_each_way": [h2d / e2e_ms / 1e6, d2h / e2e_ms / 1e6],
-                    "note": "PCIe-bound; copies of neighbouring steps overlap compute on 3 streams",
+                    "note": "PCIe-bound; copies of neighbouring steps overlap compute on 3 streams", "host_numa": numa_note,
                     "conv_precision": "follows torch.backends.cudnn.allow_tf32 (torch default True -> 2 bf16 products, "
                                       "weights hi+lo; False -> 3 products, fp32-grade)"},
             # value region: k_loss, k_finalize, k_loss_sum | k_segment_bwd, k_bwd per step (single-pass forward), NBLOCKS blocks;

@@ -92,6 +92,9 @@ int validate_inputs(const RcfDesc& d, const RcfInputs& in) {
     }
     if (d.theta_mode == 1 && (!in.w1 || !in.b1 || !in.w2 || !in.b2)) return RCF_ERR_NULL;
     if (in.feat_bias && !d.feat_nhwc) return RCF_ERR_MODE;
+    if (d.theta_mode == 1 && d.feat_nhwc)      // the channels-last pooling kernels use 128-bit accesses unconditionally
+        for (int i = 0; i < d.ndir; ++i)
+            if (!aligned16(in.feat[i]) || d.feat_bstride[i] % 4) return RCF_ERR_ALIGN;
     return RCF_OK;
 }
 
@@ -238,7 +241,10 @@ extern "C" int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const floa
         a.dfeat_bs[i] = desc->dfeat_bstride[i];
         if (a.dmask[i] && (!aligned16(a.dmask[i]) || a.dmask_bs[i] % 4)) { vec = false; vec_pool = false; }
         if (a.dresid[i] && (!aligned16(a.dresid[i]) || a.dresid_bs[i] % 4)) vec = false;
-        if (a.dfeat[i] && (!aligned16(a.dfeat[i]) || a.dfeat_bs[i] % 4)) vec_pool = false;
+        if (a.dfeat[i] && (!aligned16(a.dfeat[i]) || a.dfeat_bs[i] % 4)) {
+            if (desc->feat_nhwc) return RCF_ERR_ALIGN;      // channels-last dfeat is always written with 128-bit stores
+            vec_pool = false;
+        }
         if (a.dmask[i] && !aligned4(a.dmask[i])) return RCF_ERR_ALIGN;
         if (a.dresid[i] && !aligned4(a.dresid[i])) return RCF_ERR_ALIGN;
         if (a.dfeat[i]) any_dfeat = true;

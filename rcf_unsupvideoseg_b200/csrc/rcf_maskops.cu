@@ -378,6 +378,12 @@ extern "C" int rcf_mask_losses_forward(const RcfMaskCfg* cfg, const float* logit
     if (v != RCF_OK) return v;
     if (!logits || !masks || !losses || !ws) return RCF_ERR_NULL;
     MaskK a{};
+    // a channel index outside [0, K) is an error (only -1 means "this loss is off"): a mistyped config must not turn into
+    // a silently zero loss
+    if (cfg->compact_channel < -1 || cfg->compact_channel >= cfg->K || cfg->pl_channel < -1 || cfg->pl_channel >= cfg->K ||
+        (cfg->sharpen_mode == 2 && (cfg->sharpen_channel < 0 || cfg->sharpen_channel >= cfg->K)) || cfg->sharpen_mode < 0 ||
+        cfg->sharpen_mode > 2)
+        return RCF_ERR_SHAPE;
     fill_cfg(a, *cfg);
     if (a.compact_ch >= 0 && !frame_stats) return RCF_ERR_NULL;
     a.logits = logits; a.masks = masks; a.losses = losses; a.part = ws; a.fstats = frame_stats;

@@ -20,7 +20,7 @@ class _LossOnly(nn.Module):
     def __init__(self, head, imgs_shape):
         super().__init__()
         self.head = head
-        self._imgs = torch.zeros(imgs_shape)      # only .shape is read by forward (reference :322-324)
+        self._imgs = torch.empty(imgs_shape, device="meta")      # only .shape is read by forward (reference :322-324)
 
     def forward(self, masks, gt_fw, gt_bw, res_fw, res_bw):
         prev = self.head.return_flows

@@ -81,7 +81,8 @@ def mask_losses(logits: torch.Tensor, *, compact_channel: Optional[int] = None, 
                 ) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
     """logits [B, I, K, H, W] -> (masks, {'entropy', 'compactness', 'pl', 'sharpen'}).
 
-    compact_channel: channel of CompactnessHead (None: loss not computed, entry is 0).
+    compact_channel: channel of CompactnessHead (None: loss not computed, entry is 0; -1: the object channel, as in
+    models/compactness_head.py:19-27 -- object_channel must then be given).  Channel indices outside [0, K) raise.
     pl_masks [B, I, H, W] + object_channel: PL (or CRF) target and the object channel; pl_mask_pos_th = -1 uses the target
     as it is, any other value binarises it (`pl_masks > th`), exactly as get_pl_loss / get_crf_loss do.
     sharpen: None | 'kl' (get_sharpen_loss with object_aware_sharpening=False: KL to utils.sharpen(masks, t_sharpen)) |
@@ -91,6 +92,14 @@ def mask_losses(logits: torch.Tensor, *, compact_channel: Optional[int] = None, 
     smode = {None: 0, 'kl': 1, 'object_hinge': 2}[sharpen]
     if smode == 2:
         assert object_channel is not None, "sharpen='object_hinge' needs object_channel"
+    if compact_channel is not None and int(compact_channel) == -1:
+        if object_channel is None:
+            raise ValueError("compact_channel=-1 means 'the object channel' (compactness_head.py:19-27): pass object_channel")
+        compact_channel = object_channel
+    K = logits.shape[2]
+    for name, ch in (("compact_channel", compact_channel), ("object_channel", object_channel)):
+        if ch is not None and not 0 <= int(ch) < K:
+            raise ValueError(f"{name}={ch} is outside [0, {K})")
     use_pl = pl_masks is not None and object_channel is not None
     masks, losses, _ = _MaskLossesFn.apply(logits, pl_masks if use_pl else None,
                                            -1 if compact_channel is None else int(compact_channel),

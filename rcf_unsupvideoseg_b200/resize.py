@@ -68,7 +68,8 @@ def resize_bilinear_multi(xs: Sequence[torch.Tensor], size, align_corners: bool 
 
 def resize_bilinear(x: torch.Tensor, size, align_corners: bool = False) -> torch.Tensor:
     """Drop-in for F.interpolate(x, size, mode='bilinear', align_corners=align_corners) on fp32 CUDA tensors."""
-    return resize_bilinear_multi([x], size, align_corners)[0]
+    out = resize_bilinear_multi([x], size, align_corners)[0]
+    return out if out.dtype == x.dtype else out.to(x.dtype)      # F.interpolate preserves the input dtype
 
 
 def stage_flow_hwc(flow_hwc: torch.Tensor, size, align_corners: bool = False, channel_scale=None) -> torch.Tensor:

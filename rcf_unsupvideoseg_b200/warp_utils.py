@@ -73,7 +73,8 @@ def flow_warp(x, flow12, pad='border', mode='bilinear'):
         raise NotImplementedError(f"flow_warp mode={mode!r}: only 'bilinear' is implemented (the only mode the reference uses)")
     if pad not in ('border', 'zeros'):
         raise NotImplementedError(f"flow_warp pad={pad!r}: only 'border' and 'zeros' are implemented")
-    return _FlowWarpFn.apply(x, flow12, pad == 'border')
+    out = _FlowWarpFn.apply(x, flow12, pad == 'border')
+    return out if out.dtype == x.dtype else out.to(x.dtype)      # grid_sample preserves the input dtype (fp16 under AMP)
 
 
 def get_corresponding_map(data):
