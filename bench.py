@@ -606,12 +606,28 @@ def conv_kernels(pkg, dev):
     hi, lo = c64.split_bf16(x)
     g_hi, g_lo = c64.split_bf16(gy)
     flops = 2.0 * N_ * H * W * 64 * 64 * 9
-    out = {"gflop_per_kernel": flops / 1e9}
+    burst, sustained = 1630.8, 1391.4
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+            burst, sustained = float(pk["bf16_tflops"]), float(pk["bf16_tflops_sustained"])
+    except Exception:  # noqa: BLE001
+        pass
+    out = {"gflop_per_kernel": flops / 1e9,
+           "tensor_roofline": {"bound": "tensor", "peak_burst_tflops": burst, "peak_sustained_tflops": sustained, "unit": "TFLOP/s",
+                               "definition": "bf16 FLOPs the kernel issues to the tensor cores (nprod products per fp32 product; the weight "
+                                             "gradient also computes the centre tap row twice: x 12/9) / CUDA-event time / the measured "
+                                             "cuBLAS bf16 rate (MEASURED_PEAKS.json); halo rows (4-5 %) not counted"}}
     for nprod in (1, 2, 3):
         t_f = _time_cuda(lambda: c64.conv64_pair(hi, lo, wp, nprod), 10) * 1e3
         t_d = _time_cuda(lambda: c64.conv64_pair(g_hi, g_lo, wpt, nprod), 10) * 1e3
         t_w = _time_cuda(lambda: c64.conv64_wgrad_pair(hi, lo, g_hi, g_lo, nprod), 10) * 1e3
-        out[f"tcgen05_nprod{nprod}_us"] = {"fprop": t_f, "dgrad": t_d, "wgrad": t_w, "fprop_tflops": flops / t_f / 1e6}
+        ex_f, ex_w = nprod * flops / t_f / 1e6, nprod * (12.0 / 9.0) * flops / t_w / 1e6
+        out[f"tcgen05_nprod{nprod}_us"] = {"fprop": t_f, "dgrad": t_d, "wgrad": t_w, "fprop_useful_fp32_tflops": flops / t_f / 1e6,
+                                           "fprop_executed_bf16_tflops": ex_f, "fprop_frac_of_burst_peak": ex_f / burst,
+                                           "fprop_frac_of_sustained_peak": ex_f / sustained,
+                                           "wgrad_executed_bf16_tflops": ex_w, "wgrad_frac_of_burst_peak": ex_w / burst,
+                                           "wgrad_frac_of_sustained_peak": ex_w / sustained}
     old = torch.backends.cudnn.allow_tf32
     for tf32 in (True, False):
         torch.backends.cudnn.allow_tf32 = tf32
