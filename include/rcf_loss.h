@@ -291,11 +291,7 @@ RCF_API int rcf_mask_losses_backward(const RcfMaskCfg* cfg, const float* masks, 
 RCF_API int rcf_debug_time_kernel(int which, void* start_event, void* stop_event);
 
 /* Implementation switches for A/B measurements (process-wide; results are bit-identical either way).
- * RCF_OPT_FUSED_FORWARD (default 0): theta_mode 0 on the vector path runs pass 1, the per-segment solve and pass 2 as
- * one persistent, ticket-ordered launch so that pass 2 re-reads the masks from L2 (DRAM traffic -18 % in forward,
- * but measured ~6 % slower on B200 at 2 CTAs/SM: kept as an experiment); 0 = three separate launches. */
-#define RCF_OPT_FUSED_FORWARD 1
-#define RCF_OPT_FUSED_LAG 2      /* slots between pass 1 and pass 2 of a frame-direction (1..64) */
+ * (options 1 and 2 belonged to a single-launch forward experiment that was measured slower and removed) */
 #define RCF_OPT_L2_HINTS 3       /* evict-first streaming loads of flow/residual in pass 2 (default 1) */
 #define RCF_OPT_SINGLE_PASS 4    /* theta_mode 0 with D == 0: skip pass 1, S_k is accumulated inside pass 2 (default 1) */
 #define RCF_OPT_PDL 5            /* programmatic dependent launch between the library's consecutive kernels (default 1) */

@@ -8,8 +8,6 @@
 
 namespace {
 
-int g_fused_forward = 0;   // rcf_debug_set_option(RCF_OPT_FUSED_FORWARD, 0/1); off: measured slower, see DESIGN.md
-int g_fused_lag = 4;       // RCF_OPT_FUSED_LAG
 int g_l2_hints = 1;        // RCF_OPT_L2_HINTS
 int g_single_pass = 1;     // RCF_OPT_SINGLE_PASS
 int g_pdl = 1;             // RCF_OPT_PDL
@@ -71,14 +69,12 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.poolbar = reinterpret_cast<float*>(w + L.w_poolbar);
     a.dh = reinterpret_cast<double*>(w + L.w_dh);
     a.thbar = reinterpret_cast<double*>(w + L.w_thbar);
-    a.sync = reinterpret_cast<int*>(w + L.w_sync);
     a.dbpart = reinterpret_cast<float*>(w + L.w_dbpart);
     a.dbfd = reinterpret_cast<double*>(w + L.w_dbfd);
     a.poolsum = reinterpret_cast<double*>(w + L.w_poolsum);
     a.nblkpb = L.nblkpb; a.poolchunk = L.poolchunk; a.pooltp = L.pooltp;
     a.mlp_smem = (d.theta_mode == 1 && d.Cf % 4 == 0 && d.Cf <= 128 && aligned16(in.w1)) ? 1 : 0;
     a.pdl = g_pdl;
-    a.lag = g_fused_lag;
     a.l2_hints = g_l2_hints;   // pass 2 streams flow/residual evict-first so the masks of pass 1 survive in L2
     a.nchunk1 = L.nchunk1; a.nchunk2 = L.nchunk2; a.nchunkb = L.nchunkb; a.nchunkp = L.nchunkp;
 }
@@ -137,8 +133,6 @@ extern "C" void rcf_conv64_set_pair(int v);
 extern "C" int rcf_debug_set_option(int option, int value) {
     if (option == RCF_OPT_CONV64_DEBUG) { rcf_conv64_set_debug(value); return RCF_OK; }
     if (option == RCF_OPT_CONV64_PAIR) { rcf_conv64_set_pair(value); return RCF_OK; }
-    if (option == RCF_OPT_FUSED_FORWARD) { g_fused_forward = value ? 1 : 0; return RCF_OK; }
-    if (option == RCF_OPT_FUSED_LAG && value >= 1 && value <= 64) { g_fused_lag = value; return RCF_OK; }
     if (option == RCF_OPT_L2_HINTS) { g_l2_hints = value ? 1 : 0; return RCF_OK; }
     if (option == RCF_OPT_SINGLE_PASS) { g_single_pass = value ? 1 : 0; return RCF_OK; }
     if (option == RCF_OPT_PDL) { g_pdl = value ? 1 : 0; return RCF_OK; }
@@ -198,10 +192,6 @@ extern "C" int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss
         // theta supplied, no affine fit: nothing in pass 2 depends on pass 1, so the forward reads every input once; the
         // coefficient pack is just theta, which k_loss / k_bwd read directly (no k_segment_fwd launch either)
         { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_loss(a, vec, s)); }
-    } else if (desc->theta_mode == 0 && vec && g_fused_forward) {
-        // one launch: pass 1, per-segment solve and pass 2, ordered for L2 reuse of the masks (rcf_forward_fused.cu)
-        RCF_CUDA(cudaMemsetAsync(a.sync, 0, (size_t)(1 + 2 * L.nfd) * sizeof(int), s));
-        { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_forward_fused(a, s)); }
     } else {
         { ScopedTime t(RCF_TIME_MOMENTS, s); RCF_CUDA(rcf_launch_moments(a, vec, s)); }
         if (desc->theta_mode == 1) { ScopedTime t(RCF_TIME_POOL, s); RCF_CUDA(rcf_launch_pool(a, vec_ok_inputs(*desc, *in, true), s)); }

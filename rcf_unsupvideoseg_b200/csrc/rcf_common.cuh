@@ -63,7 +63,7 @@ struct RcfLayout {
     // ctx (bytes offsets)
     size_t c_segd, c_coef, c_mlp, c_gm, c_bytes;
     // ws
-    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_sync, w_dbpart, w_dbfd, w_poolsum, w_bytes;
+    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_dbpart, w_dbfd, w_poolsum, w_bytes;
     int nblkpb;   // CTAs per frame-direction of the channels-last pooling backward (pooltp pixels each)
     int poolchunk, pooltp;
 };
@@ -100,7 +100,6 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.w_poolbar = o; o = rcf_align256(o + nseg * d.Cf * sizeof(float));
     L.w_dh = o;      o = rcf_align256(o + nseg * d.Cf * sizeof(double));
     L.w_thbar = o;   o = rcf_align256(o + nseg * 2 * sizeof(double));
-    L.w_sync = o;    o = rcf_align256(o + (size_t)(1 + 2 * L.nfd) * sizeof(int));   // ticket, pass-1 counters, ready flags
     L.pooltp = rcf_pool_tp_nhwc(L.P, L.nfd);
     L.poolchunk = pc;
     L.nblkpb = (L.P + L.pooltp - 1) / L.pooltp;
@@ -147,8 +146,6 @@ struct RcfK {
     double* dh;
     double* thbar;
     int nchunk1, nchunk2, nchunkb, nchunkp;
-    int* sync;     // fused forward: [0] ticket, [1..nfd] pass-1 arrival counters, [1+nfd..] ready flags
-    int lag;       // fused forward: pass 2 of frame-direction t is scheduled LAG slots after its pass 1
     int l2_hints;  // pass 2 streams flow/residual with an L2 evict-first policy (keeps the masks resident)
     int pdl;          // launch with programmatic stream serialization (kernels call rcf_pdl_prologue() first)
     int mlp_smem;     // segment kernels stage the MLP weights in shared memory (Cf % 4 == 0 and Cf <= 128)
@@ -375,7 +372,6 @@ int rcf_pdl_enabled();   // RCF_OPT_PDL (rcf_capi.cu)
 
 // launchers (one translation unit each)
 cudaError_t rcf_launch_moments(const RcfK& a, bool vec, cudaStream_t s);
-cudaError_t rcf_launch_forward_fused(const RcfK& a, cudaStream_t s);
 cudaError_t rcf_launch_pool(const RcfK& a, bool vec, cudaStream_t s);
 cudaError_t rcf_launch_segment_fwd(const RcfK& a, cudaStream_t s);
 cudaError_t rcf_launch_loss(const RcfK& a, bool vec, cudaStream_t s);

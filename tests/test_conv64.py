@@ -75,6 +75,26 @@ def test_conv64_autograd_function(c64):
     assert _rel(dw, dwd) <= WTOL[3]
 
 
+def test_conv64_one_cta_and_cta_pair_kernels_agree(c64):
+    """RCF_OPT_CONV64_PAIR = 0 selects the one-CTA kernel (same MMA sequence per tile, other pipeline): identical results."""
+    from rcf_unsupvideoseg_b200 import _lib
+    lib = _lib.load_library()
+    x = torch.randn(3, 64, 37, 61, device="cuda").contiguous(memory_format=torch.channels_last)
+    w = torch.randn(64, 64, 3, 3, device="cuda") / 24
+    wp = c64.pack_weights(w, False)
+    try:
+        for nprod in (1, 2, 3):
+            lib.rcf_debug_set_option(7, 1)
+            a = c64.conv64_raw(x, wp, nprod)
+            lib.rcf_debug_set_option(7, 0)
+            b = c64.conv64_raw(x, wp, nprod)
+            torch.cuda.synchronize()
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-6), nprod      # fp32 accumulation order inside the MMAs may differ between M = 128 and M = 256
+    finally:
+        lib.rcf_debug_set_option(7, 1)
+    assert lib.rcf_debug_conv64_status() == 0
+
+
 def test_conv64_is_bit_reproducible(c64):
     x = torch.randn(2, 64, 40, 52, device="cuda").contiguous(memory_format=torch.channels_last)
     w = torch.randn(64, 64, 3, 3, device="cuda") / 24
