@@ -11,7 +11,7 @@
 #include "rcf_moments_dev.cuh"
 
 template <int K, int D, int PX>
-__global__ void __launch_bounds__(RCF_BLOCK, (D == 2 && K <= 4) ? 3 : 1) k_moments(const RcfK a) {
+__global__ void __launch_bounds__(RCF_BLOCK, (D == 2) ? 2 : 1) k_moments(const RcfK a) {
     rcf_pdl_prologue();
     __shared__ float red[RCF_WARPS][K * rcf_ns(D)];
     moments_tile<K, D, PX>(a, blockIdx.y, blockIdx.x, red);

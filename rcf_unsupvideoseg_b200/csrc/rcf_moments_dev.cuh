@@ -27,6 +27,87 @@ __device__ __forceinline__ void moments_tile(const RcfK& a, int fd, int chunk, f
         float acc[KG * NS];
 #pragma unroll
         for (int i = 0; i < KG * NS; ++i) acc[i] = 0.0f;
+        if constexpr (D == 2) {
+            // Affine fit.  The K x 12 outer-product accumulation is issue-bound as scalar FFMAs (measured: 44 M warp
+            // instructions, issue active 57 %, 4.2 TB/s), so the 12 sums of a segment are kept as 6 packed pairs and
+            // updated with FFMA2 (two round-to-nearest FMAs per issue slot, the mask value as the broadcast operand):
+            //   P0 = (F0, F1)   P1 = (u0, u1)   P2 = F0*P1   P3 = F1*P1   P4 = u0*P1   P5 = (u1*u1, 1)
+            // Every pair is produced in place (no register moves); same products and the same summation order per
+            // accumulator as the scalar chain, so the results are bit-identical to it.
+            f32x2 acc2[KG * 6];
+#pragma unroll
+            for (int i = 0; i < KG * 6; ++i) acc2[i] = 0ull;
+            // Software pipeline: the loads of tile it+1 (KG mask packs + 2 flow packs per thread) are issued before tile
+            // it is consumed.  Without it a warp alternates "issue loads / wait ~1 us / compute", and the 16-24 resident
+            // warps do not cover the HBM latency (measured 4.2 TB/s whatever the instruction count).  Out-of-range
+            // pixels load zeros: their products vanish, no branch around the arithmetic.
+            auto load = [&](int it, float (&m)[KG][PX], float (&f0)[PX], float (&f1)[PX]) {
+                const int p = p0 + (it * RCF_BLOCK + tid) * PX;
+                const bool in = p < P;
+#pragma unroll
+                for (int k = 0; k < KG; ++k) {
+                    if (in && k0 + k < K) Pack<PX>::ld(m[k], mask + (long long)(k0 + k) * P + p);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) m[k][j] = 0.0f;
+                    }
+                }
+                if (in) {
+                    Pack<PX>::ld(f0, flow + p);
+                    Pack<PX>::ld(f1, flow + P + p);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) f0[j] = f1[j] = 0.0f;
+                }
+            };
+            float mc[KG][PX], f0c[PX], f1c[PX];
+            load(0, mc, f0c, f1c);
+#pragma unroll
+            for (int it = 0; it < ITER; ++it) {
+                float mn[KG][PX], f0n[PX], f1n[PX];
+                if (it + 1 < ITER) load(it + 1, mn, f0n, f1n);
+                float y[PX], x[PX];
+                px_coords<PX>(p0 + (it * RCF_BLOCK + tid) * PX, a, y, x);
+#pragma unroll
+                for (int j = 0; j < PX; ++j) {
+                    float u[2];
+                    px_feats<2>(y[j], x[j], u);
+                    const float F0 = clamp_flow(f0c[j], a.clamp_t), F1 = clamp_flow(f1c[j], a.clamp_t);
+                    f32x2 zp[6];
+                    zp[0] = pack2(F0, F1);
+                    zp[1] = pack2(u[0], u[1]);
+                    zp[2] = mul2(pack2(F0, F0), zp[1]);
+                    zp[3] = mul2(pack2(F1, F1), zp[1]);
+                    zp[4] = mul2(pack2(u[0], u[0]), zp[1]);
+                    zp[5] = pack2(u[1] * u[1], 1.0f);
+#pragma unroll
+                    for (int k = 0; k < KG; ++k) {
+                        const f32x2 mm = pack2(mc[k][j], mc[k][j]);
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) acc2[k * 6 + i] = fma2(mm, zp[i], acc2[k * 6 + i]);
+                    }
+                }
+                if (it + 1 < ITER) {
+#pragma unroll
+                    for (int j = 0; j < PX; ++j) {
+#pragma unroll
+                        for (int k = 0; k < KG; ++k) mc[k][j] = mn[k][j];
+                        f0c[j] = f0n[j];
+                        f1c[j] = f1n[j];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < KG; ++k) {
+                float* o = acc + k * NS;       // (1, F0, F1, u0, u1, F0u0, F0u1, F1u0, F1u1, u0u0, u0u1, u1u1)
+                unpack2(acc2[k * 6 + 0], o[1], o[2]);
+                unpack2(acc2[k * 6 + 1], o[3], o[4]);
+                unpack2(acc2[k * 6 + 2], o[5], o[6]);
+                unpack2(acc2[k * 6 + 3], o[7], o[8]);
+                unpack2(acc2[k * 6 + 4], o[9], o[10]);
+                unpack2(acc2[k * 6 + 5], o[11], o[0]);
+            }
+        } else
         if constexpr (D == 0) {
             // mask sums only: issue every load of the tile (ITER*K 128-bit loads per thread) before the first add,
             // so the tile runs at full memory-level parallelism even at 2 CTAs/SM inside the fused forward kernel
