@@ -59,6 +59,112 @@ __global__ void __launch_bounds__(RCF_BLOCK, (D <= 2) ? 2 : 1) k_bwd(const RcfK 
             float y[PX], x[PX];
             if constexpr (D > 0) px_coords<PX>(p, a, y, x);
 
+            if constexpr (D == 2 && PX % 2 == 0) {
+                // Affine fit: every quantity is per pixel, so the whole body runs on PIXEL pairs (the halves of a
+                // 128-bit load are register neighbours) with FFMA2 / FMUL2 / FADD2 and broadcast coefficients: the
+                // scalar form is 130 M warp instructions (issue active 54 %) for a kernel that should wait on HBM only.
+                // Same operations in the same order per pixel as the scalar code below.
+                constexpr int PP = PX / 2;
+                const f32x2 one2 = pack2(1.0f, 1.0f), mtwo2 = pack2(-2.0f, -2.0f), sc2 = pack2(a.scale, a.scale);
+                const f32x2 es2 = pack2(a.ex2_scale, a.ex2_scale), ds2 = pack2(a.dres_scale, a.dres_scale);
+                f32x2 up[2][PP], gp[2][PP], tp[2][K][PP], fp[2][PP];
+#pragma unroll
+                for (int h = 0; h < PP; ++h) {
+                    up[0][h] = pack2(y[2 * h], y[2 * h + 1]);
+                    up[1][h] = pack2(x[2 * h], x[2 * h + 1]);
+                    gp[0][h] = gp[1][h] = 0ull;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float ck[CF];
+#pragma unroll
+                    for (int i = 0; i < CF; ++i) ck[i] = cf[k * CF + i];
+                    const f32x2 nmu0 = pack2(-ck[6], -ck[6]), nmu1 = pack2(-ck[7], -ck[7]);
+#pragma unroll
+                    for (int h = 0; h < PP; ++h) {
+                        const f32x2 v0 = add2(up[0][h], nmu0), v1 = add2(up[1][h], nmu1);
+                        const f32x2 mp = pack2(m[k][2 * h], m[k][2 * h + 1]);
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            f32x2 t = pack2(r[c][k][2 * h], r[c][k][2 * h + 1]);
+                            if (!a.unbounded) {
+                                float e0, e1, q0, q1;
+                                unpack2(mul2(t, es2), e0, e1);
+                                unpack2(add2(pack2(fast_ex2(e0), fast_ex2(e1)), one2), q0, q1);
+                                t = fma2(mtwo2, pack2(fast_rcp(q0), fast_rcp(q1)), one2);
+                            }
+                            tp[c][k][h] = t;
+                            f32x2 q = fma2(sc2, t, pack2(ck[c], ck[c]));
+                            q = fma2(pack2(ck[2 + c * 2], ck[2 + c * 2]), v0, q);
+                            q = fma2(pack2(ck[3 + c * 2], ck[3 + c * 2]), v1, q);
+                            gp[c][h] = fma2(mp, q, gp[c][h]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int h = 0; h < PP; ++h) {
+                        float pr[2], fc[2], gw[2];
+                        unpack2(gp[c][h], pr[0], pr[1]);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            fc[e] = clamp_flow(f[c][2 * h + e], a.clamp_t);
+                            float phi, w;
+                            loss_terms(fc[e] - pr[e], a, phi, w);
+                            gw[e] = gs * w;
+                        }
+                        fp[c][h] = pack2(fc[0], fc[1]);
+                        gp[c][h] = pack2(gw[0], gw[1]);
+                    }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float ck[CF], bk[CB];
+#pragma unroll
+                    for (int i = 0; i < CF; ++i) ck[i] = cf[k * CF + i];
+#pragma unroll
+                    for (int i = 0; i < CB; ++i) bk[i] = cb[k * CB + i];
+                    // bk: muF[2], B[2][2], Csym[3], mubar[2], c0
+                    const f32x2 nmu0 = pack2(-ck[6], -ck[6]), nmu1 = pack2(-ck[7], -ck[7]);
+                    const f32x2 nb0 = pack2(-bk[0], -bk[0]), nb1 = pack2(-bk[1], -bk[1]);
+                    float dm[PX], dr0[PX], dr1[PX];
+#pragma unroll
+                    for (int h = 0; h < PP; ++h) {
+                        const f32x2 mp = pack2(m[k][2 * h], m[k][2 * h + 1]);
+                        const f32x2 t0 = tp[0][k][h], t1 = tp[1][k][h];
+                        const f32x2 v0 = add2(up[0][h], nmu0), v1 = add2(up[1][h], nmu1);
+                        f32x2 q0 = fma2(sc2, t0, pack2(ck[0], ck[0])), q1 = fma2(sc2, t1, pack2(ck[1], ck[1]));
+                        q0 = fma2(pack2(ck[2], ck[2]), v0, q0);
+                        q1 = fma2(pack2(ck[4], ck[4]), v0, q1);
+                        q0 = fma2(pack2(ck[3], ck[3]), v1, q0);
+                        q1 = fma2(pack2(ck[5], ck[5]), v1, q1);
+                        const f32x2 ff0 = add2(fp[0][h], nb0), ff1 = add2(fp[1][h], nb1);
+                        f32x2 acc = pack2(bk[CB - 1], bk[CB - 1]);
+                        f32x2 lin = fma2(ff0, pack2(bk[2], bk[2]), fma2(ff1, pack2(bk[4], bk[4]), pack2(bk[9], bk[9])));
+                        lin = fma2(pack2(bk[6], bk[6]), v0, lin);
+                        lin = fma2(pack2(bk[7], bk[7]), v1, lin);
+                        acc = fma2(lin, v0, acc);
+                        lin = fma2(ff0, pack2(bk[3], bk[3]), fma2(ff1, pack2(bk[5], bk[5]), pack2(bk[10], bk[10])));
+                        lin = fma2(pack2(bk[8], bk[8]), v1, lin);
+                        acc = fma2(lin, v1, acc);
+                        unpack2(fma2(gp[0][h], q0, fma2(gp[1][h], q1, acc)), dm[2 * h], dm[2 * h + 1]);
+                        if (a.unbounded) {
+                            unpack2(mul2(gp[0][h], mp), dr0[2 * h], dr0[2 * h + 1]);
+                            unpack2(mul2(gp[1][h], mp), dr1[2 * h], dr1[2 * h + 1]);
+                        } else {
+                            const f32x2 nt0 = mul2(t0, pack2(-1.0f, -1.0f)), nt1 = mul2(t1, pack2(-1.0f, -1.0f));
+                            unpack2(mul2(mul2(mul2(gp[0][h], ds2), fma2(nt0, t0, one2)), mp), dr0[2 * h], dr0[2 * h + 1]);
+                            unpack2(mul2(mul2(mul2(gp[1][h], ds2), fma2(nt1, t1, one2)), mp), dr1[2 * h], dr1[2 * h + 1]);
+                        }
+                    }
+                    if (dmask) Pack<PX>::st(dmask + (long long)k * P + p, dm);
+                    if (dresid) {
+                        Pack<PX>::st(dresid + (long long)k * P + p, dr0);
+                        Pack<PX>::st(dresid + (long long)(K + k) * P + p, dr1);
+                    }
+                }
+                continue;
+            }
             // ---- phase 1: recompute T (kept in r) and pred, segment-outer ------------------------
             float g[2][PX];
 #pragma unroll

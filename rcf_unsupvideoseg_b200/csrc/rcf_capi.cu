@@ -77,6 +77,7 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.pdl = g_pdl;
     a.l2_hints = g_l2_hints;   // pass 2 streams flow/residual evict-first so the masks of pass 1 survive in L2
     a.nchunk1 = L.nchunk1; a.nchunk2 = L.nchunk2; a.nchunkb = L.nchunkb; a.nchunkp = L.nchunkp;
+    a.chunk2 = L.chunk2;
 }
 
 int validate_inputs(const RcfDesc& d, const RcfInputs& in) {
@@ -96,7 +97,7 @@ int validate_inputs(const RcfDesc& d, const RcfInputs& in) {
 
 // 128-bit path: every plane start must be 16-byte aligned
 bool vec_ok_inputs(const RcfDesc& d, const RcfInputs& in, bool with_feat) {
-    if (((long long)d.H * d.W) % 4 != 0) return false;
+    if (((long long)d.H * d.W) % 4 != 0 || d.W < 4) return false;     // a pack crosses at most one line end (px_coords_rc)
     for (int i = 0; i < d.ndir; ++i) {
         if (!aligned16(in.mask[i]) || !aligned16(in.flow[i]) || !aligned16(in.resid[i])) return false;
         if (d.mask_bstride[i] % 4 || d.flow_bstride[i] % 4 || d.resid_bstride[i] % 4) return false;

@@ -27,6 +27,11 @@
 // twice the pixels per CTA halves that overhead: C2 affine 0.459 -> 0.443 ms, FBMS K=3 0.388 -> 0.373 ms; K = 8 (64-bit
 // packs, two segment groups) got slower with it (1.68 -> 1.81 ms) and keeps 4096
 RCF_HD constexpr int rcf_chunk_mom(int D, int K) { return (D == 2 && K <= 4) ? 2 * RCF_CHUNK_MOM : RCF_CHUNK_MOM; }
+// Pass 2 with the affine fit carries 1 + 2K + 4K accumulators through a warp/CTA reduction per chunk: large frames take
+// 4x longer chunks (K <= 4: the wider kernels have no registers for the loop state) so that epilogue (and the coefficient prologue) amortise; the training shapes keep the short one.
+RCF_HD int rcf_chunk_loss(int D, int K, int P, int nfd) {
+    return (D == 2 && K <= 4 && (long long)((P + 8191) / 8192) * nfd >= 4 * 148) ? 8192 : RCF_CHUNK_LOSS;
+}
 RCF_HD constexpr int rcf_ns(int D) { return D == 0 ? 1 : 3 + 3 * D + D * (D + 1) / 2; }
 // pass-2 gradient moments per fd: [0] sum phi, [1 + c*K + k] sum w_c m_k,
 //   D > 0: [1 + 2K + (k*2+c)*D + d] sum w_c m_k (u_d - mu_kd)
@@ -60,6 +65,7 @@ RCF_HD int rcf_pool_chunk(int K, int nhwc, int P, int nfd) { return nhwc ? rcf_p
 struct RcfLayout {
     int nfd, P, ns, gm, cf, cb, segd;
     int nchunk1, nchunk2, nchunkb, nchunkp;
+    int chunk2;   // pixels per CTA of pass 2
     // ctx (bytes offsets)
     size_t c_segd, c_coef, c_mlp, c_gm, c_bytes;
     // ws
@@ -80,7 +86,8 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.cb = rcf_cb(d.D);
     L.segd = rcf_segd(d.D);
     L.nchunk1 = (L.P + rcf_chunk_mom(d.D, d.K) - 1) / rcf_chunk_mom(d.D, d.K);
-    L.nchunk2 = (L.P + RCF_CHUNK_LOSS - 1) / RCF_CHUNK_LOSS;
+    L.chunk2 = rcf_chunk_loss(d.D, d.K, L.P, L.nfd);
+    L.nchunk2 = (L.P + L.chunk2 - 1) / L.chunk2;
     L.nchunkb = (L.P + RCF_CHUNK_BWD - 1) / RCF_CHUNK_BWD;
     const int pc = rcf_pool_chunk(d.K, d.feat_nhwc, L.P, L.nfd);
     L.nchunkp = (L.P + pc - 1) / pc;
@@ -146,6 +153,7 @@ struct RcfK {
     double* dh;
     double* thbar;
     int nchunk1, nchunk2, nchunkb, nchunkp;
+    int chunk2;    // pixels per CTA of pass 2 (a multiple of RCF_CHUNK_LOSS)
     int l2_hints;  // pass 2 streams flow/residual with an L2 evict-first policy (keeps the masks resident)
     int pdl;          // launch with programmatic stream serialization (kernels call rcf_pdl_prologue() first)
     int mlp_smem;     // segment kernels stage the MLP weights in shared memory (Cf % 4 == 0 and Cf <= 128)
@@ -325,6 +333,11 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     f32x2 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
@@ -355,17 +368,28 @@ __device__ __forceinline__ float clamp_flow(float f, float t) {
     return t >= 0.0f ? fminf(fmaxf(f, -t), t) : f;
 }
 
-// coordinates of PX consecutive flat pixels starting at p
+// coordinates of PX consecutive flat pixels starting at (row, col): y = (row - cy) * sy, x = (col - cx) * sx, the row
+// advancing where the pack crosses the end of a line.  col - cx is formed as (col - cx) + j [- W]: every term is a
+// multiple of 0.5 far below 2^24, so the sum is exact and the result equals ((float)(col + j) - cx) * sx bit for bit,
+// at 4-5 instructions per pixel instead of two int->float conversions plus the wrap bookkeeping.
 template <int PX>
-__device__ __forceinline__ void px_coords(int p, const RcfK& a, float (&y)[PX], float (&x)[PX]) {
-    int row = p / a.W;
-    int col = p - row * a.W;
+__device__ __forceinline__ void px_coords_rc(int row, int col, const RcfK& a, float (&y)[PX], float (&x)[PX]) {
+    const float y0 = ((float)row - a.cy) * a.sy, y1 = ((float)(row + 1) - a.cy) * a.sy;
+    const float base = (float)col - a.cx, wf = (float)a.W;
 #pragma unroll
     for (int j = 0; j < PX; ++j) {
-        y[j] = ((float)row - a.cy) * a.sy;
-        x[j] = ((float)col - a.cx) * a.sx;
-        if (++col == a.W) { col = 0; ++row; }
+        const bool wrap = col + j >= a.W;            // PX <= W on every path that uses packs
+        float c = base + (float)j;
+        if (wrap) c -= wf;
+        y[j] = wrap ? y1 : y0;
+        x[j] = c * a.sx;
     }
+}
+// ... starting at flat pixel p
+template <int PX>
+__device__ __forceinline__ void px_coords(int p, const RcfK& a, float (&y)[PX], float (&x)[PX]) {
+    const int row = p / a.W;
+    px_coords_rc<PX>(row, p - row * a.W, a, y, x);
 }
 template <int D>
 __device__ __forceinline__ void px_feats(float y, float x, float (&u)[D > 0 ? D : 1]) {

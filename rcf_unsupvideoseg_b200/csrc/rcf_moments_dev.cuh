@@ -1,5 +1,6 @@
 // rcf_moments_dev.cuh -- pass-1 tile body (shared by k_moments and the fused forward kernel).
 #pragma once
+#include <type_traits>
 #include "rcf_common.cuh"
 
 // Segments are processed in groups of KG (as many as keep KG*NS accumulators in registers); inside a
@@ -38,65 +39,74 @@ __device__ __forceinline__ void moments_tile(const RcfK& a, int fd, int chunk, f
 #pragma unroll
             for (int i = 0; i < KG * 6; ++i) acc2[i] = 0ull;
             // Software pipeline: the loads of tile it+1 (KG mask packs + 2 flow packs per thread) are issued before tile
-            // it is consumed.  Without it a warp alternates "issue loads / wait ~1 us / compute", and the 16-24 resident
-            // warps do not cover the HBM latency (measured 4.2 TB/s whatever the instruction count).  Out-of-range
-            // pixels load zeros: their products vanish, no branch around the arithmetic.
-            auto load = [&](int it, float (&m)[KG][PX], float (&f0)[PX], float (&f1)[PX]) {
-                const int p = p0 + (it * RCF_BLOCK + tid) * PX;
-                const bool in = p < P;
-#pragma unroll
-                for (int k = 0; k < KG; ++k) {
-                    if (in && k0 + k < K) Pack<PX>::ld(m[k], mask + (long long)(k0 + k) * P + p);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < PX; ++j) m[k][j] = 0.0f;
-                    }
-                }
-                if (in) {
-                    Pack<PX>::ld(f0, flow + p);
-                    Pack<PX>::ld(f1, flow + P + p);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < PX; ++j) f0[j] = f1[j] = 0.0f;
-                }
-            };
-            float mc[KG][PX], f0c[PX], f1c[PX];
-            load(0, mc, f0c, f1c);
-#pragma unroll
-            for (int it = 0; it < ITER; ++it) {
-                float mn[KG][PX], f0n[PX], f1n[PX];
-                if (it + 1 < ITER) load(it + 1, mn, f0n, f1n);
-                float y[PX], x[PX];
-                px_coords<PX>(p0 + (it * RCF_BLOCK + tid) * PX, a, y, x);
-#pragma unroll
-                for (int j = 0; j < PX; ++j) {
-                    float u[2];
-                    px_feats<2>(y[j], x[j], u);
-                    const float F0 = clamp_flow(f0c[j], a.clamp_t), F1 = clamp_flow(f1c[j], a.clamp_t);
-                    f32x2 zp[6];
-                    zp[0] = pack2(F0, F1);
-                    zp[1] = pack2(u[0], u[1]);
-                    zp[2] = mul2(pack2(F0, F0), zp[1]);
-                    zp[3] = mul2(pack2(F1, F1), zp[1]);
-                    zp[4] = mul2(pack2(u[0], u[0]), zp[1]);
-                    zp[5] = pack2(u[1] * u[1], 1.0f);
+            // it is consumed.  Without it a warp alternates "issue loads / wait ~1 us / compute", and the 16 resident
+            // warps do not cover the HBM latency.  Chunks that lie entirely inside the frame (all but the last one) run
+            // without any bounds logic; the last chunk loads zeros for out-of-range pixels (their products vanish).
+            // (row, col) of the thread's pack advance incrementally: one integer division per thread, not per pack.
+            constexpr int STEP = RCF_BLOCK * PX;
+            const int drow = STEP / a.W, dcol = STEP - drow * a.W;
+            auto sweep = [&](auto guard_tag) {
+                constexpr bool GUARD = decltype(guard_tag)::value;
+                auto load = [&](int it, float (&m)[KG][PX], float (&f0)[PX], float (&f1)[PX]) {
+                    const int p = p0 + it * STEP + tid * PX;
+                    const bool in = !GUARD || p < P;
 #pragma unroll
                     for (int k = 0; k < KG; ++k) {
-                        const f32x2 mm = pack2(mc[k][j], mc[k][j]);
+                        if (in && k0 + k < K) Pack<PX>::ld(m[k], mask + (long long)(k0 + k) * P + p);
+                        else {
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) acc2[k * 6 + i] = fma2(mm, zp[i], acc2[k * 6 + i]);
+                            for (int j = 0; j < PX; ++j) m[k][j] = 0.0f;
+                        }
                     }
-                }
-                if (it + 1 < ITER) {
+                    if (in) {
+                        Pack<PX>::ld(f0, flow + p);
+                        Pack<PX>::ld(f1, flow + P + p);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) f0[j] = f1[j] = 0.0f;
+                    }
+                };
+                int row = (p0 + tid * PX) / a.W, col = (p0 + tid * PX) - row * a.W;
+                float mc[KG][PX], f0c[PX], f1c[PX];
+                load(0, mc, f0c, f1c);
+#pragma unroll
+                for (int it = 0; it < ITER; ++it) {
+                    float mn[KG][PX], f0n[PX], f1n[PX];
+                    if (it + 1 < ITER) load(it + 1, mn, f0n, f1n);
+                    float y[PX], x[PX];
+                    px_coords_rc<PX>(row, col, a, y, x);
+                    row += drow; col += dcol;
+                    if (col >= a.W) { col -= a.W; ++row; }
 #pragma unroll
                     for (int j = 0; j < PX; ++j) {
+                        const float F0 = clamp_flow(f0c[j], a.clamp_t), F1 = clamp_flow(f1c[j], a.clamp_t);
+                        f32x2 zp[6];
+                        zp[0] = pack2(F0, F1);
+                        zp[1] = pack2(y[j], x[j]);
+                        zp[2] = mul2(pack2(F0, F0), zp[1]);
+                        zp[3] = mul2(pack2(F1, F1), zp[1]);
+                        zp[4] = mul2(pack2(y[j], y[j]), zp[1]);
+                        zp[5] = pack2(x[j] * x[j], 1.0f);
 #pragma unroll
-                        for (int k = 0; k < KG; ++k) mc[k][j] = mn[k][j];
-                        f0c[j] = f0n[j];
-                        f1c[j] = f1n[j];
+                        for (int k = 0; k < KG; ++k) {
+                            const f32x2 mm = pack2(mc[k][j], mc[k][j]);
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) acc2[k * 6 + i] = fma2(mm, zp[i], acc2[k * 6 + i]);
+                        }
+                    }
+                    if (it + 1 < ITER) {
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) {
+#pragma unroll
+                            for (int k = 0; k < KG; ++k) mc[k][j] = mn[k][j];
+                            f0c[j] = f0n[j];
+                            f1c[j] = f1n[j];
+                        }
                     }
                 }
-            }
+            };
+            if (p0 + CHUNK <= P) sweep(std::false_type{});
+            else sweep(std::true_type{});
 #pragma unroll
             for (int k = 0; k < KG; ++k) {
                 float* o = acc + k * NS;       // (1, F0, F1, u0, u1, F0u0, F0u1, F1u0, F1u1, u0u0, u0u1, u1u1)
