@@ -44,7 +44,7 @@ extern "C" {
 #define RCF_API
 #endif
 
-#define RCF_ABI_VERSION 3
+#define RCF_ABI_VERSION 4
 #define RCF_MAX_K 8          /* mask_layer supported by the compiled kernels */
 #define RCF_MAX_CF 256       /* num_flow_feat_channels supported by the segment kernels */
 
@@ -187,10 +187,13 @@ RCF_API int rcf_stem_forward(const float* const* flow, const int64_t* flow_bstri
                              int ks, const float* w, const float* b, float clamp_t, float slope, float* act,
                              uint32_t* sign, void* stream);
 /* The same layer with the activation written as the bf16 pair act ~ act_hi + act_lo (channels-last [ndir*B, H, W, 64]
- * bf16 each; act_lo may be NULL) instead of fp32: the operand format of rcf_conv64_forward.  Cf = 64 only. */
+ * bf16 each; act_lo may be NULL) instead of fp32: the operand format of rcf_conv64_forward.  Cf = 64 only.
+ * nprod (here and in rcf_stem_backward): TF32 products per fp32 product on the tensor-core path -- >= 3: hi*hi + hi*lo +
+ * lo*hi (fp32-grade, what torch.backends.cudnn.allow_tf32 = False asks for); 1 or 2: one product of round-to-nearest TF32
+ * operands (what cuDNN runs for this layer under allow_tf32 = True / autocast; a third of the MMAs). */
 RCF_API int rcf_stem_forward_bf16(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W,
                                   int ks, const float* w, const float* b, float clamp_t, float slope, void* act_hi,
-                                  void* act_lo, uint32_t* sign, void* stream);
+                                  void* act_lo, uint32_t* sign, int nprod, void* stream);
 RCF_API int rcf_stem_workspace_bytes(int ndir, int B, int H, int W, int Cf, int ks, size_t* bytes);
 /* dw [Cf,2,ks,ks], db [Cf] from dact (gradient w.r.t. act) and EITHER the forward output act OR the sign bits the forward
  * wrote; ws from rcf_stem_workspace_bytes.
@@ -199,7 +202,7 @@ RCF_API int rcf_stem_workspace_bytes(int ndir, int B, int H, int W, int Cf, int 
  * and the backward reads these 8 B/px instead of the 256 B/px activation map. */
 RCF_API int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W, int Cf,
                               int ks, float clamp_t, float slope, const float* act, const uint32_t* sign, const float* dact,
-                              float* dw, float* db, void* ws, void* stream);
+                              float* dw, float* db, void* ws, int nprod, void* stream);
 
 /* ---- second layer of flow_feat_before_agg (reference :89-91): Conv2d(64 -> 64, 3x3, padding 1, no bias here) on the
  * 5th-generation tensor cores (TMA tiled loads -> tcgen05.mma with bf16 operands -> fp32 accumulation in tensor memory;

@@ -12,7 +12,7 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "librcf_loss.so")
 
-RCF_ABI_VERSION = 3
+RCF_ABI_VERSION = 4
 RCF_MAX_K = 8
 RCF_MAX_CF = 256
 
@@ -127,13 +127,13 @@ def load_library(build_if_missing: bool = True):
         lib.rcf_stem_forward_bf16.restype = C.c_int
         lib.rcf_stem_forward_bf16.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
-                                              C.c_void_p, C.c_void_p]
+                                              C.c_void_p, C.c_int, C.c_void_p]
         lib.rcf_stem_workspace_bytes.restype = C.c_int
         lib.rcf_stem_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         lib.rcf_stem_backward.restype = C.c_int
         lib.rcf_stem_backward.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
-                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         for fn in (lib.rcf_resize_bilinear_forward, lib.rcf_resize_bilinear_backward):
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

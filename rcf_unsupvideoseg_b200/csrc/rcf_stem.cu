@@ -276,11 +276,15 @@ struct StemTile {
             pre[e] = v;
         }
     }
+    template <int NP>
     __device__ __forceinline__ void commit(const StemK& a, uint32_t* Thi, uint32_t* Tlo) const {
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             const int i = threadIdx.x + e * RCF_BLOCK;
-            if (i < TSZ) split_tf32(clamp_flow(pre[e], a.clamp_t), Thi[i], Tlo[i]);
+            if (i < TSZ) {
+                if constexpr (NP == 1) Thi[i] = to_tf32(clamp_flow(pre[e], a.clamp_t));
+                else split_tf32(clamp_flow(pre[e], a.clamp_t), Thi[i], Tlo[i]);
+            }
         }
     }
 };
@@ -308,7 +312,9 @@ __device__ __forceinline__ uint32_t nonpos4(float v0, float v1, float v2, float 
 // K = taps + 1 (bias column): full k8 steps plus one k4 step for a remainder <= 4 (3x3: 19 = 8 + 8 + 3).
 // The scheduler's issue slots are shared by the MMAs and everything else (measured: MMA time + other-instruction time
 // add up), so the epilogue is kept short: LeakyReLU as max(v, slope*v), sign bits by byte permutes, one address per tile.
-template <int KS>
+// NP = TF32 products per fp32 product: 3 (hi*hi + hi*lo + lo*hi, fp32-grade) or 1 (plain TF32 with round-to-nearest
+// operands -- what cuDNN runs for this layer under torch.backends.cudnn.allow_tf32; a third of the MMAs, half the LDS).
+template <int KS, int NP>
 __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(const StemK a) {
     using TL = StemTile<KS>;
     constexpr int NT = 2 * KS * KS, NK = NT + 1, SW = TL::SW, TSZ = TL::TSZ;
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
     for (; tl < a.ntiles; tl += gridDim.x) {
         n = nn; y0 = ny0; x0 = nx0;
         __syncthreads();                               // previous tile fully consumed
-        st.commit(a, Thi, Tlo);
+        st.template commit<NP>(a, Thi, Tlo);
         __syncthreads();
         if (tl + (int)gridDim.x < a.ntiles) {          // next tile's loads in flight while this tile is computed
             dec(tl + gridDim.x, nn, ny0, nx0);
@@ -374,18 +380,29 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
                 const int i0 = offA[s][0] + pix0 * mulA[s][0], i1 = offA[s][0] + pix1 * mulA[s][0];
                 const int i2 = offA[s][1] + pix0 * mulA[s][1], i3 = offA[s][1] + pix1 * mulA[s][1];
                 const uint32_t ah[4] = {Thi[i0], Thi[i1], Thi[i2], Thi[i3]};
-                const uint32_t al[4] = {Tlo[i0], Tlo[i1], Tlo[i2], Tlo[i3]};
+                if constexpr (NP == 1) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) mma_3xtf32(c[j], ah, al, bh[j][s], bl[j][s]);
+                    for (int j = 0; j < 4; ++j) mma_tf32(c[j], ah, bh[j][s][0], bh[j][s][1]);
+                } else {
+                    const uint32_t al[4] = {Tlo[i0], Tlo[i1], Tlo[i2], Tlo[i3]};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mma_3xtf32(c[j], ah, al, bh[j][s], bl[j][s]);
+                }
             }
             if (K4) {
                 const int i0 = off4 + pix0 * mul4, i1 = off4 + pix1 * mul4;
-                const uint32_t ah0 = Thi[i0], ah1 = Thi[i1], al0 = Tlo[i0], al1 = Tlo[i1];
+                const uint32_t ah0 = Thi[i0], ah1 = Thi[i1];
+                if constexpr (NP == 1) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    mma_tf32_k4(c[j], al0, al1, b4h[j]);
-                    mma_tf32_k4(c[j], ah0, ah1, b4l[j]);
-                    mma_tf32_k4(c[j], ah0, ah1, b4h[j]);
+                    for (int j = 0; j < 4; ++j) mma_tf32_k4(c[j], ah0, ah1, b4h[j]);
+                } else {
+                    const uint32_t al0 = Tlo[i0], al1 = Tlo[i1];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        mma_tf32_k4(c[j], al0, al1, b4h[j]);
+                        mma_tf32_k4(c[j], ah0, ah1, b4l[j]);
+                        mma_tf32_k4(c[j], ah0, ah1, b4h[j]);
+                    }
                 }
             }
             const int x = x0 + lx0 + g;
@@ -431,7 +448,7 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
 // r = g + 8h of M-tile m is channel 32*half + 4g + 2m + h: a lane needs channels 4g..4g+3 of the pixels t and t+4 of the
 // group = one 128-bit load each, and the 8 lanes of a pixel read 128 contiguous bytes.  The loads of four groups
 // (8 x LDG.128 + 8 sign words per lane) are issued before the first group is consumed.
-template <int KS>
+template <int KS, int NP>
 __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_bwd_mma(const StemK a) {
     rcf_pdl_prologue();
     using TL = StemTile<KS>;
@@ -464,7 +481,7 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_bwd_mma(c
     for (; tl < a.ntiles; tl += gridDim.x) {      // fixed tile -> CTA assignment (reproducible)
         n = nn; y0 = ny0; x0 = nx0;
         __syncthreads();
-        st.commit(a, Thi, Tlo);
+        st.template commit<NP>(a, Thi, Tlo);
         __syncthreads();
         if (tl + (int)gridDim.x < a.ntiles) {
             dec(tl + gridDim.x, nn, ny0, nx0);
@@ -509,18 +526,24 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_bwd_mma(c
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     const int j0 = offB[j] + pA * mulB[j], j1 = offB[j] + (pA + 4) * mulB[j];
-                    bh[j][0] = Thi[j0]; bl[j][0] = Tlo[j0];
-                    bh[j][1] = Thi[j1]; bl[j][1] = Tlo[j1];
+                    bh[j][0] = Thi[j0]; bh[j][1] = Thi[j1];
+                    if constexpr (NP != 1) { bl[j][0] = Tlo[j0]; bl[j][1] = Tlo[j1]; }
                 }
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
-                    uint32_t ah[4], al[4];
-                    split_tf32_fast(v[0][2 * m], ah[0], al[0]);
-                    split_tf32_fast(v[0][2 * m + 1], ah[1], al[1]);
-                    split_tf32_fast(v[1][2 * m], ah[2], al[2]);
-                    split_tf32_fast(v[1][2 * m + 1], ah[3], al[3]);
+                    if constexpr (NP == 1) {
+                        const uint32_t ah[4] = {to_tf32(v[0][2 * m]), to_tf32(v[0][2 * m + 1]), to_tf32(v[1][2 * m]), to_tf32(v[1][2 * m + 1])};
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j) mma_3xtf32(acc[m][j], ah, al, bh[j], bl[j]);
+                        for (int j = 0; j < NJ; ++j) mma_tf32(acc[m][j], ah, bh[j][0], bh[j][1]);
+                    } else {
+                        uint32_t ah[4], al[4];
+                        split_tf32_fast(v[0][2 * m], ah[0], al[0]);
+                        split_tf32_fast(v[0][2 * m + 1], ah[1], al[1]);
+                        split_tf32_fast(v[1][2 * m], ah[2], al[2]);
+                        split_tf32_fast(v[1][2 * m + 1], ah[3], al[3]);
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) mma_3xtf32(acc[m][j], ah, al, bh[j], bl[j]);
+                    }
                 }
             }
         }
@@ -609,9 +632,9 @@ extern "C" int rcf_stem_forward(const float* const* flow, const int64_t* flow_bs
     if (Cf == STEM_MMA_CF && slope >= 0.0f && slope <= 1.0f) {            // tensor-core path, persistent CTAs (weights split once per CTA)
         const int g = stem_grid_bwd(a.ntiles);
         switch (ks) {
-            case 1: k_stem_fwd_mma<1><<<g, RCF_BLOCK, 0, s>>>(a); break;
-            case 3: k_stem_fwd_mma<3><<<g, RCF_BLOCK, 0, s>>>(a); break;
-            case 5: k_stem_fwd_mma<5><<<g, RCF_BLOCK, 0, s>>>(a); break;
+            case 1: k_stem_fwd_mma<1, 3><<<g, RCF_BLOCK, 0, s>>>(a); break;
+            case 3: k_stem_fwd_mma<3, 3><<<g, RCF_BLOCK, 0, s>>>(a); break;
+            case 5: k_stem_fwd_mma<5, 3><<<g, RCF_BLOCK, 0, s>>>(a); break;
         }
         RCF_CUDA(cudaGetLastError());
         return RCF_OK;
@@ -629,7 +652,7 @@ extern "C" int rcf_stem_forward(const float* const* flow, const int64_t* flow_bs
 // Same layer, output as the bf16 (hi, lo) pair the tcgen05 conv consumes (Cf = 64 only; act_lo may be NULL).
 extern "C" int rcf_stem_forward_bf16(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W,
                                      int ks, const float* w, const float* b, float clamp_t, float slope, void* act_hi,
-                                     void* act_lo, uint32_t* sign, void* stream) {
+                                     void* act_lo, uint32_t* sign, int nprod, void* stream) {
     const int v = stem_check(ndir, B, H, W, STEM_MMA_CF, ks);
     if (v != RCF_OK) return v;
     if (!flow || !flow_bstride || !flow[0] || (ndir > 1 && !flow[1]) || !w || !b || !act_hi) return RCF_ERR_NULL;
@@ -641,26 +664,34 @@ extern "C" int rcf_stem_forward_bf16(const float* const* flow, const int64_t* fl
     a.act_hi = static_cast<uint32_t*>(act_hi); a.act_lo = static_cast<uint32_t*>(act_lo);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int g = stem_grid_bwd(a.ntiles);
-    switch (ks) {
-        case 1: k_stem_fwd_mma<1><<<g, RCF_BLOCK, 0, s>>>(a); break;
-        case 3: k_stem_fwd_mma<3><<<g, RCF_BLOCK, 0, s>>>(a); break;
-        case 5: k_stem_fwd_mma<5><<<g, RCF_BLOCK, 0, s>>>(a); break;
+    if (nprod >= 3) {
+        switch (ks) {
+            case 1: k_stem_fwd_mma<1, 3><<<g, RCF_BLOCK, 0, s>>>(a); break;
+            case 3: k_stem_fwd_mma<3, 3><<<g, RCF_BLOCK, 0, s>>>(a); break;
+            case 5: k_stem_fwd_mma<5, 3><<<g, RCF_BLOCK, 0, s>>>(a); break;
+        }
+    } else {
+        switch (ks) {
+            case 1: k_stem_fwd_mma<1, 1><<<g, RCF_BLOCK, 0, s>>>(a); break;
+            case 3: k_stem_fwd_mma<3, 1><<<g, RCF_BLOCK, 0, s>>>(a); break;
+            case 5: k_stem_fwd_mma<5, 1><<<g, RCF_BLOCK, 0, s>>>(a); break;
+        }
     }
     RCF_CUDA(cudaGetLastError());
     return RCF_OK;
 }
 
-template <int KS>
+template <int KS, int NP>
 static int launch_stem_bwd_mma(const StemK& a, int g, cudaStream_t s) {
     constexpr int NJ = (2 * KS * KS + 1 + 7) / 8;
     const size_t smem = (size_t)RCF_WARPS * 32 * NJ * 8 * sizeof(float);
-    RCF_CUDA(cudaFuncSetAttribute(k_stem_bwd_mma<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return (int)rcf_launch(k_stem_bwd_mma<KS>, g, RCF_BLOCK, smem, s, rcf_pdl_enabled(), a);
+    RCF_CUDA(cudaFuncSetAttribute(k_stem_bwd_mma<KS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return (int)rcf_launch(k_stem_bwd_mma<KS, NP>, g, RCF_BLOCK, smem, s, rcf_pdl_enabled(), a);
 }
 
 extern "C" int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W,
                                  int Cf, int ks, float clamp_t, float slope, const float* act, const uint32_t* sign,
-                                 const float* dact, float* dw, float* db, void* ws, void* stream) {
+                                 const float* dact, float* dw, float* db, void* ws, int nprod, void* stream) {
     const int v = stem_check(ndir, B, H, W, Cf, ks);
     if (v != RCF_OK) return v;
     if (!flow || !flow_bstride || !flow[0] || (ndir > 1 && !flow[1]) || (!act && !sign) || !dact || !dw || !db || !ws)
@@ -675,10 +706,18 @@ extern "C" int rcf_stem_backward(const float* const* flow, const int64_t* flow_b
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (sign) {                         // tensor-core path (sign bits written by rcf_stem_forward)
         int e = RCF_OK;
-        switch (ks) {
-            case 1: e = launch_stem_bwd_mma<1>(a, g, s); break;
-            case 3: e = launch_stem_bwd_mma<3>(a, g, s); break;
-            case 5: e = launch_stem_bwd_mma<5>(a, g, s); break;
+        if (nprod >= 3) {
+            switch (ks) {
+                case 1: e = launch_stem_bwd_mma<1, 3>(a, g, s); break;
+                case 3: e = launch_stem_bwd_mma<3, 3>(a, g, s); break;
+                case 5: e = launch_stem_bwd_mma<5, 3>(a, g, s); break;
+            }
+        } else {
+            switch (ks) {
+                case 1: e = launch_stem_bwd_mma<1, 1>(a, g, s); break;
+                case 3: e = launch_stem_bwd_mma<3, 1>(a, g, s); break;
+                case 5: e = launch_stem_bwd_mma<5, 1>(a, g, s); break;
+            }
         }
         if (e != RCF_OK) return e;
     } else {

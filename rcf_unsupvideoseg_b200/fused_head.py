@@ -26,8 +26,9 @@ from .function import LossSpec, _as_dir_view, _inner_dense, _make_desc, _sizes
 from .stem import _views, stem_backward_raw
 
 
-def stem_forward_pair(fl, w, b, clamp_t: float, slope: float, want_lo: bool):
-    """First conv + LeakyReLU; returns (act_hi, act_lo or None, sign): bf16 channels-last [ndir*B,64,H,W] and the sign bits."""
+def stem_forward_pair(fl, w, b, clamp_t: float, slope: float, want_lo: bool, nprod: int = 3):
+    """First conv + LeakyReLU; returns (act_hi, act_lo or None, sign): bf16 channels-last [ndir*B,64,H,W] and the sign bits.
+    nprod >= 3: 3xTF32 (fp32-grade); below: one TF32 product, like cuDNN under allow_tf32."""
     lib = _lib.load_library()
     ndir = len(fl)
     B, _, H, W = fl[0].shape
@@ -41,7 +42,7 @@ def stem_forward_pair(fl, w, b, clamp_t: float, slope: float, want_lo: bool):
     with _lib.device_guard(dev):
         _lib.check(lib.rcf_stem_forward_bf16(ptrs, strides, ndir, B, H, W, ks, w.data_ptr(), b.data_ptr(), float(clamp_t),
                                              float(slope), hi.data_ptr(), lo.data_ptr() if lo is not None else None,
-                                             sign.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                                             sign.data_ptr(), int(nprod), torch.cuda.current_stream(dev).cuda_stream),
                    "rcf_stem_forward_bf16")
     return hi, lo, sign
 
@@ -69,7 +70,7 @@ class RcfHeadFn(torch.autograd.Function):
 
         # conv branch: stem (bf16 pair out) -> tcgen05 conv (fp32 pre-activation, channels-last, bias applied by the pooling kernels)
         clamp = -1.0 if spec.clamp_t is None else float(spec.clamp_t)
-        a_hi, a_lo, sign = stem_forward_pair(flows_v, cw1c, cb1c, clamp, stem_slope, want_lo=(nprod == 3))
+        a_hi, a_lo, sign = stem_forward_pair(flows_v, cw1c, cb1c, clamp, stem_slope, want_lo=(nprod == 3), nprod=nprod)
         feat = c64.conv64_pair(a_hi, a_lo, c64.pack_weights(cw2c, False), nprod)          # [ndir*B,64,H,W] channels-last
 
         desc = _make_desc(spec, B, ndir)
@@ -187,5 +188,5 @@ class RcfHeadFn(torch.autograd.Function):
         if need_conv:
             d_a1 = c64.conv64_pair(g_hi, g_lo if nprod == 3 else None, c64.pack_weights(cw2c, True), nprod)     # data gradient
             d_cw2 = c64.conv64_wgrad_pair(a_hi, a_lo, g_hi, g_lo, nprod)
-            d_cw1, d_cb1 = stem_backward_raw(flows_v, tuple(cw1c.shape), ctx.clamp, ctx.stem_slope, None, sign, d_a1)
+            d_cw1, d_cb1 = stem_backward_raw(flows_v, tuple(cw1c.shape), ctx.clamp, ctx.stem_slope, None, sign, d_a1, nprod=ctx.nprod)
         return (None, None, None, d_masks, d_cw1, d_cb1, d_cw2, d_cb2, *dmlp, *([None] * ndir), *d_resids)

@@ -52,7 +52,7 @@ def stem_forward_raw(fl, w, b, clamp_t: float, slope: float):
     return act, sign
 
 
-def stem_backward_raw(fl, w_shape, clamp_t: float, slope: float, act, sign, dact):
+def stem_backward_raw(fl, w_shape, clamp_t: float, slope: float, act, sign, dact, nprod: int = 3):
     """(dw, db) of the stem from dact (gradient w.r.t. its output) and either the sign bits or the activation map."""
     lib = _lib.load_library()
     ndir = len(fl)
@@ -71,7 +71,7 @@ def stem_backward_raw(fl, w_shape, clamp_t: float, slope: float, act, sign, dact
         _lib.check(lib.rcf_stem_backward(ptrs, strides, ndir, B, H, W, Cf, ks, clamp_t, slope,
                                          None if sign is not None else act.data_ptr(),
                                          sign.data_ptr() if sign is not None else None, g.data_ptr(), dw.data_ptr(),
-                                         db.data_ptr(), ws.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                                         db.data_ptr(), ws.data_ptr(), int(nprod), torch.cuda.current_stream(dev).cuda_stream),
                    "rcf_stem_backward")
     return dw, db
 
