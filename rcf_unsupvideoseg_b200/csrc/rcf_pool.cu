@@ -8,6 +8,7 @@
 // Backward: dG[f,p] = sum_k c[f,k] M[k,p]   and   dM[k,p] += sum_f c[f,k] G[f,p],  c = Poolbar / S.
 // Thread-per-pixel-pack mapping: G is read once, dG written once, the dM term is accumulated in registers
 // on top of what the streaming backward (k_bwd, launched before) already stored.
+#include <type_traits>
 #include "rcf_common.cuh"
 #include "rcf_umma.cuh"
 
@@ -285,11 +286,15 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
     uint2* __restrict__ dgh = a.dfeat_hi[dir] ? reinterpret_cast<uint2*>(a.dfeat_hi[dir] + ((long long)b * a.dfeat_bs[dir] + (long long)p0 * Cf) / 2) + c4 : nullptr;
     uint2* __restrict__ dgl = a.dfeat_lo[dir] ? reinterpret_cast<uint2*>(a.dfeat_lo[dir] + ((long long)b * a.dfeat_bs[dir] + (long long)p0 * Cf) / 2) + c4 : nullptr;
     auto store_pair = [&](int p, const float (&dg)[4]) {
-        uint32_t h0, h1, l0, l1;
-        umma::split_bf16x2(dg[0], dg[1], h0, l0);
-        umma::split_bf16x2(dg[2], dg[3], h1, l1);
-        dgh[(long long)p * nf4] = make_uint2(h0, h1);
-        if (dgl) dgl[(long long)p * nf4] = make_uint2(l0, l1);
+        if (dgl) {
+            uint32_t h0, h1, l0, l1;
+            umma::split_bf16x2(dg[0], dg[1], h0, l0);
+            umma::split_bf16x2(dg[2], dg[3], h1, l1);
+            dgh[(long long)p * nf4] = make_uint2(h0, h1);
+            dgl[(long long)p * nf4] = make_uint2(l0, l1);
+        } else {
+            dgh[(long long)p * nf4] = make_uint2(umma::cvt_bf16x2(dg[0], dg[1]), umma::cvt_bf16x2(dg[2], dg[3]));
+        }
     };
     // fast reduction when 16 lanes share a pixel and K == 4 (Cf = 64, the reference default): recursive halving
     // (2 + 1 shuffles) then two butterflies, instead of 4 x 4 butterflies
@@ -303,53 +308,76 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
             // the first is consumed; the mask quadruple is one LDS.128; no per-iteration slow-path branches.
             done = true;
             const bool up8 = (c4 & 8) != 0, up4 = (c4 & 4) != 0, writer = (c4 & 3) == 0;
-            for (int it0 = 0; it0 < iters; it0 += 8) {
-                float4 gq[8];
+            // MODE: which gradient tensors this launch writes (uniform over the grid) -- 0 none, 1 fp32, 2 bf16 hi,
+            // 3 bf16 (hi, lo), 4 fp32 + pair.  Resolved once per CTA: the pixel loop carries no pointer tests.
+            auto sweep = [&](auto mode_tag) {
+                constexpr int MODE = decltype(mode_tag)::value;
+                for (int it0 = 0; it0 < iters; it0 += 8) {
+                    float4 gq[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int p = grp + (it0 + u) * groups;
-                    gq[u] = (p < pend) ? __ldg(gp + (long long)p * nf4) : zero4;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int p = grp + (it0 + u) * groups;          // < TP by construction
-                    const bool live = p < pend;
-                    const float4 m4 = *reinterpret_cast<const float4*>(msT + p * 4);
-                    const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
-                    float gv[4] = {gq[u].x + bias[0], gq[u].y + bias[1], gq[u].z + bias[2], gq[u].w + bias[3]}, dg[4], part[4];
-                    float dact[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        dact[j] = gv[j] >= 0.0f ? 1.0f : slope;
-                        gv[j] *= dact[j];
-                        dg[j] = 0.0f;
+                    for (int u = 0; u < 8; ++u) {
+                        const int p = grp + (it0 + u) * groups;
+                        gq[u] = (p < pend) ? __ldg(gp + (long long)p * nf4) : zero4;
                     }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        part[k] = 0.0f;
+                    for (int u = 0; u < 8; ++u) {
+                        const int p = grp + (it0 + u) * groups;          // < TP by construction
+                        const bool live = p < pend;                       // dead pixels: the mask tile holds zeros => dg = 0
+                        const float4 m4 = *reinterpret_cast<const float4*>(msT + p * 4);
+                        const float mv[4] = {m4.x, m4.y, m4.z, m4.w};
+                        float gv[4] = {gq[u].x + bias[0], gq[u].y + bias[1], gq[u].z + bias[2], gq[u].w + bias[3]}, dg[4], part[4];
+                        float dact[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            part[k] = fmaf(c[j][k], gv[j], part[k]);
-                            dg[j] = fmaf(c[j][k], mv[k], dg[j]);
+                            dact[j] = gv[j] >= 0.0f ? 1.0f : slope;
+                            gv[j] *= dact[j];
+                            dg[j] = 0.0f;
                         }
-                    }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        dg[j] *= dact[j];
-                        dbias[j] += live ? dg[j] : 0.0f;
+                        for (int k = 0; k < 4; ++k) {
+                            part[k] = 0.0f;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                part[k] = fmaf(c[j][k], gv[j], part[k]);
+                                dg[j] = fmaf(c[j][k], mv[k], dg[j]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            dg[j] *= dact[j];
+                            dbias[j] += dg[j];
+                        }
+                        if (live) {
+                            if constexpr (MODE == 1 || MODE == 4) dgp[(long long)p * nf4] = make_float4(dg[0], dg[1], dg[2], dg[3]);
+                            if constexpr (MODE == 2) {
+                                dgh[(long long)p * nf4] = make_uint2(umma::cvt_bf16x2(dg[0], dg[1]), umma::cvt_bf16x2(dg[2], dg[3]));
+                            }
+                            if constexpr (MODE == 3 || MODE == 4) {
+                                uint32_t h0, h1, l0, l1;
+                                umma::split_bf16x2(dg[0], dg[1], h0, l0);
+                                umma::split_bf16x2(dg[2], dg[3], h1, l1);
+                                dgh[(long long)p * nf4] = make_uint2(h0, h1);
+                                dgl[(long long)p * nf4] = make_uint2(l0, l1);
+                            }
+                        }
+                        const float s0 = up8 ? part[0] : part[2], s1 = up8 ? part[1] : part[3];
+                        const float k0 = up8 ? part[2] : part[0], k1 = up8 ? part[3] : part[1];
+                        const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
+                        const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
+                        float v = (up4 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up4 ? a0 : a1, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        if (live && writer) dms[p * 4 + kown] += v;        // 4 lanes per pixel, one per k
                     }
-                    if (live && dgp) dgp[(long long)p * nf4] = make_float4(dg[0], dg[1], dg[2], dg[3]);
-                    if (live && dgh) store_pair(p, dg);
-                    const float s0 = up8 ? part[0] : part[2], s1 = up8 ? part[1] : part[3];
-                    const float k0 = up8 ? part[2] : part[0], k1 = up8 ? part[3] : part[1];
-                    const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
-                    const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
-                    float v = (up4 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up4 ? a0 : a1, 4);
-                    v += __shfl_xor_sync(0xffffffffu, v, 2);
-                    v += __shfl_xor_sync(0xffffffffu, v, 1);
-                    if (live && writer) dms[p * 4 + kown] += v;        // 4 lanes per pixel, one per k
                 }
-            }
+            };
+            const int mode = dgp ? ((dgh && dgl) ? 4 : 1) : (dgh ? (dgl ? 3 : 2) : 0);
+            if (dgp && dgh && !dgl) done = false;          // fp32 + hi only: not a combination any caller asks for
+            else if (mode == 0) sweep(std::integral_constant<int, 0>{});
+            else if (mode == 1) sweep(std::integral_constant<int, 1>{});
+            else if (mode == 2) sweep(std::integral_constant<int, 2>{});
+            else if (mode == 3) sweep(std::integral_constant<int, 3>{});
+            else sweep(std::integral_constant<int, 4>{});
         }
     }
     if (!done) {

@@ -423,14 +423,17 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
                     if (a.act_hi) {                              // bf16 (hi, lo) pair: 4 channels = 2 words, +16 channels = +8 words
                         const long long wofs = ((long long)n * a.P + pofs + 8 * h) * (Cf / 2) + half * 16 + 2 * t;
                         uint32_t hw[4], lw[4];
+                        if (a.act_lo) {                          // warp-uniform
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) umma::split_bf16x2(o[2 * e], o[2 * e + 1], hw[e], lw[e]);
-                        *reinterpret_cast<uint2*>(a.act_hi + wofs) = make_uint2(hw[0], hw[1]);
-                        *reinterpret_cast<uint2*>(a.act_hi + wofs + 8) = make_uint2(hw[2], hw[3]);
-                        if (a.act_lo) {
+                            for (int e = 0; e < 4; ++e) umma::split_bf16x2(o[2 * e], o[2 * e + 1], hw[e], lw[e]);
                             *reinterpret_cast<uint2*>(a.act_lo + wofs) = make_uint2(lw[0], lw[1]);
                             *reinterpret_cast<uint2*>(a.act_lo + wofs + 8) = make_uint2(lw[2], lw[3]);
+                        } else {                                 // plain bf16 operand: one conversion per channel pair
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) hw[e] = umma::cvt_bf16x2(o[2 * e], o[2 * e + 1]);
                         }
+                        *reinterpret_cast<uint2*>(a.act_hi + wofs) = make_uint2(hw[0], hw[1]);
+                        *reinterpret_cast<uint2*>(a.act_hi + wofs + 8) = make_uint2(hw[2], hw[3]);
                     } else {
                         float* dst = img + (long long)(pofs + 8 * h) * Cf;
                         *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
