@@ -9,6 +9,9 @@
 // Thread-per-pixel-pack mapping: G is read once, dG written once, the dM term is accumulated in registers
 // on top of what the streaming backward (k_bwd, launched before) already stored.
 #include <type_traits>
+#ifndef RCF_POOL_BWD_BATCH
+#define RCF_POOL_BWD_BATCH 8
+#endif
 #include "rcf_common.cuh"
 #include "rcf_umma.cuh"
 
@@ -184,6 +187,21 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
         for (int j = 0; j < 4; ++j) bias[j] = __ldg(a.feat_bias + c4 * 4 + j);
     }
 
+    // The first batch of feature loads is requested BEFORE the mask tile is staged: the tile's global round trip and
+    // the barrier then overlap with it instead of leaving the CTA without a load in flight for the whole prologue.
+    constexpr int UB = 8;
+    const int pend = min(CHUNK, P - p0);
+    const float4* __restrict__ gp = reinterpret_cast<const float4*>(feat + (long long)p0 * Cf) + c4;
+    const int nf4s = nf4;    // float4 stride between consecutive pixels
+    float4 gq[UB];
+    auto load_batch = [&](int pb) {
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int p = pb + u * groups;
+            gq[u] = (p < pend) ? __ldg(gp + (long long)p * nf4s) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+    };
+    load_batch(grp);
     for (int i = tid; i < CHUNK * K; i += RCF_BLOCK) {
         const int k = i / CHUNK, p = i - k * CHUNK;                  // coalesced along pixels per plane
         msT[p * K + k] = (p0 + p < P) ? __ldg(mask + (long long)k * P + p0 + p) : 0.0f;
@@ -195,19 +213,10 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[j][k] = 0.0f;
-    const int pend = min(CHUNK, P - p0);
-    const float4* __restrict__ gp = reinterpret_cast<const float4*>(feat + (long long)p0 * Cf) + c4;
-    const int nf4s = nf4;    // float4 stride between consecutive pixels
     // Explicit batches: the 8 feature loads of a batch are issued before the first one is consumed (nvcc does not
     // hoist them out of a predicated, runtime-bounded loop on its own: one load in flight per thread = 3.3 TB/s).
-    constexpr int UB = 8;
     for (int pb = grp; pb < pend; pb += groups * UB) {
-        float4 gq[UB];
-#pragma unroll
-        for (int u = 0; u < UB; ++u) {
-            const int p = pb + u * groups;
-            gq[u] = (p < pend) ? __ldg(gp + (long long)p * nf4s) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        }
+        if (pb != grp) load_batch(pb);
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             const int p = pb + u * groups;
@@ -260,6 +269,14 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
     float* __restrict__ dfeat = a.dfeat[dir] ? a.dfeat[dir] + (long long)b * a.dfeat_bs[dir] : nullptr;
     const float slope = a.feat_slope;
 
+    const int pend = min(TP, P - p0);
+    const int iters = (TP + groups - 1) / groups;      // uniform trip count: shuffles below stay convergent
+    const float4* __restrict__ gp = reinterpret_cast<const float4*>(feat + (long long)p0 * Cf) + c4;
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    // (Requesting the first feature batch here, ahead of the tile staging, was measured: the eight live float4 push the
+    // 80-register kernel into heavy spilling, 192 -> 300 us.  The forward kernel, which has the registers, does it.)
+    constexpr int PBW = RCF_POOL_BWD_BATCH;          // feature loads in flight per thread on the fast path
+    const bool fast = (K == 4) && (nf4 == 16) && TP % groups == 0 && (iters % PBW) == 0;
     for (int i = tid; i < TP * K; i += RCF_BLOCK) {
         const int k = i / TP, p = i - k * TP;
         const bool in = p0 + p < P;
@@ -278,9 +295,6 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
     }
     __syncthreads();
 
-    const int pend = min(TP, P - p0);
-    const int iters = (TP + groups - 1) / groups;      // uniform trip count: shuffles below stay convergent
-    const float4* __restrict__ gp = reinterpret_cast<const float4*>(feat + (long long)p0 * Cf) + c4;
     float4* __restrict__ dgp = dfeat ? reinterpret_cast<float4*>(dfeat + (long long)p0 * Cf) + c4 : nullptr;
     // bf16 (hi, lo) pair output (what the tcgen05 conv kernels load by TMA): 4 channels = one uint2 per word tensor
     uint2* __restrict__ dgh = a.dfeat_hi[dir] ? reinterpret_cast<uint2*>(a.dfeat_hi[dir] + ((long long)b * a.dfeat_bs[dir] + (long long)p0 * Cf) / 2) + c4 : nullptr;
@@ -298,12 +312,10 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
     };
     // fast reduction when 16 lanes share a pixel and K == 4 (Cf = 64, the reference default): recursive halving
     // (2 + 1 shuffles) then two butterflies, instead of 4 x 4 butterflies
-    const bool fast = (K == 4) && (nf4 == 16);
     const int kown = ((c4 >> 3) & 1) * 2 + ((c4 >> 2) & 1);
-    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     bool done = false;
     if constexpr (K == 4) {
-        if (fast && TP % groups == 0 && (iters & 7) == 0) {
+        if (fast) {
             // Reference default (Cf = 64, K = 4): batches of 8 pixels per thread, all eight feature loads in flight before
             // the first is consumed; the mask quadruple is one LDS.128; no per-iteration slow-path branches.
             done = true;
@@ -312,15 +324,15 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
             // 3 bf16 (hi, lo), 4 fp32 + pair.  Resolved once per CTA: the pixel loop carries no pointer tests.
             auto sweep = [&](auto mode_tag) {
                 constexpr int MODE = decltype(mode_tag)::value;
-                for (int it0 = 0; it0 < iters; it0 += 8) {
-                    float4 gq[8];
+                for (int it0 = 0; it0 < iters; it0 += PBW) {
+                    float4 gq[PBW];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < PBW; ++u) {
                         const int p = grp + (it0 + u) * groups;
                         gq[u] = (p < pend) ? __ldg(gp + (long long)p * nf4) : zero4;
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < PBW; ++u) {
                         const int p = grp + (it0 + u) * groups;          // < TP by construction
                         const bool live = p < pend;                       // dead pixels: the mask tile holds zeros => dg = 0
                         const float4 m4 = *reinterpret_cast<const float4*>(msT + p * 4);
