@@ -211,7 +211,8 @@ RCF_API int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstr
  * the library's own producers write); out: channels-last fp32 [nimg, H, W, 64]; all dense, 16-byte aligned.
  * wpack: RCF_CONV64_WPACK_BYTES device bytes filled by rcf_conv64_pack_weights from the [64,64,3,3] fp32 weight;
  * transpose_flip = 1 packs the operator of the DATA GRADIENT (din = conv(dout, W^T flipped)), so rcf_conv64_forward
- * computes it with the same kernel.
+ * computes it with the same kernel; transpose_flip = 2 packs BOTH in one launch (wpack then holds 2 x
+ * RCF_CONV64_WPACK_BYTES: the forward image followed by the data-gradient image).
  * nprod: bf16 products per fp32 product: 3 = fp32-grade (hi + lo of both operands, ~1e-5), 2 = weights hi + lo,
  * activations in_hi only (TF32 class), 1 = in_hi x w_hi (autocast class).  in_lo may be NULL unless nprod == 3. */
 #define RCF_CONV64_WPACK_BYTES (9 * 16384 + 2 * (9 * 8192 + 9 * 4096))   /* one-CTA image + the two CTA-pair images */

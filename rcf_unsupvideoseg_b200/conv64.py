@@ -40,6 +40,18 @@ def pack_weights(w: torch.Tensor, transpose_flip: bool) -> torch.Tensor:
     return out
 
 
+def pack_weights_both(w: torch.Tensor):
+    """One launch: (forward image, data-gradient image) of the same [64,64,3,3] weight (views of one buffer)."""
+    lib = _lib.load_library()
+    assert tuple(w.shape) == (64, 64, 3, 3) and w.is_cuda
+    w = w.detach().float().contiguous()
+    out = torch.empty(2 * WPACK_BYTES, dtype=torch.uint8, device=w.device)
+    with _lib.device_guard(w.device):
+        _lib.check(lib.rcf_conv64_pack_weights(w.data_ptr(), out.data_ptr(), 2,
+                                               torch.cuda.current_stream(w.device).cuda_stream), "rcf_conv64_pack_weights")
+    return out[:WPACK_BYTES], out[WPACK_BYTES:]
+
+
 def split_bf16(x: torch.Tensor, want_lo: bool = True):
     """fp32 tensor (any dense layout, numel % 4 == 0) -> (hi, lo) bf16 tensors of the same shape / strides, x ~ hi + lo."""
     lib = _lib.load_library()

@@ -57,9 +57,14 @@ __device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, vo
 //   forward  (transpose_flip = 0): row n <-> co, k <-> ci, tap (ty,tx):      out[q] = sum W[co][ci][ty][tx] in[q + (ty-1)Wp + (tx-1)]
 //   data grad (transpose_flip = 1): row n <-> ci, k <-> co, tap (2-ty,2-tx): din[q] = sum W[co][ci][2-ty][2-tx] dout[q + (ty-1)Wp + (tx-1)]
 // rows 0-63 hold the bf16 "hi" word of the weight, rows 64-127 the "lo" word.
+// transpose_flip = 2: both, the data-gradient image C64_WPACK_TOTAL_BYTES after the forward one (blockIdx.y selects).
 __global__ void k_conv64_pack(const float* __restrict__ w, uint8_t* __restrict__ out, int transpose_flip) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 9 * 64 * 64) return;
+    if (transpose_flip == 2) {
+        transpose_flip = (int)blockIdx.y;
+        out += (size_t)blockIdx.y * C64_WPACK_TOTAL_BYTES;
+    }
     const int k = idx & 63, n = (idx >> 6) & 63, tap = idx >> 12;
     float v;
     if (!transpose_flip) v = w[(n * 64 + k) * 9 + tap];
@@ -308,7 +313,9 @@ extern "C" {
 RCF_API int rcf_conv64_pack_weights(const float* w, void* wpack, int transpose_flip, void* stream) {
     if (!w || !wpack) return RCF_ERR_NULL;
     if (((uintptr_t)wpack & 15) != 0) return RCF_ERR_ALIGN;
-    k_conv64_pack<<<(9 * 64 * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)wpack, transpose_flip);
+    if (transpose_flip < 0 || transpose_flip > 2) return RCF_ERR_MODE;
+    const dim3 grid((9 * 64 * 64 + 255) / 256, transpose_flip == 2 ? 2 : 1);
+    k_conv64_pack<<<grid, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)wpack, transpose_flip);
     return (int)cudaGetLastError();
 }
 

@@ -71,7 +71,12 @@ class RcfHeadFn(torch.autograd.Function):
         # conv branch: stem (bf16 pair out) -> tcgen05 conv (fp32 pre-activation, channels-last, bias applied by the pooling kernels)
         clamp = -1.0 if spec.clamp_t is None else float(spec.clamp_t)
         a_hi, a_lo, sign = stem_forward_pair(flows_v, cw1c, cb1c, clamp, stem_slope, want_lo=(nprod == 3), nprod=nprod)
-        feat = c64.conv64_pair(a_hi, a_lo, c64.pack_weights(cw2c, False), nprod)          # [ndir*B,64,H,W] channels-last
+        need_conv_grad = any(ctx.needs_input_grad[4:8])
+        if need_conv_grad:          # the data-gradient operator of the same weights is packed by the same launch
+            wp_fwd, wp_bwd = c64.pack_weights_both(cw2c)
+        else:
+            wp_fwd, wp_bwd = c64.pack_weights(cw2c, False), None
+        feat = c64.conv64_pair(a_hi, a_lo, wp_fwd, nprod)          # [ndir*B,64,H,W] channels-last
 
         desc = _make_desc(spec, B, ndir)
         desc.feat_nhwc = 1
@@ -104,8 +109,10 @@ class RcfHeadFn(torch.autograd.Function):
         ctx.spec, ctx.ndir, ctx.B, ctx.nprod, ctx.stem_slope, ctx.clamp = spec, ndir, B, nprod, stem_slope, clamp
         ctx.masks_shape = tuple(masks.shape)
         ctx.has_lo = a_lo is not None
+        ctx.has_wp = wp_bwd is not None
         ctx.save_for_backward(masks_v, ctx_buf, feat, a_hi, sign, cw1c, cw2c, cb2c, w1c, b1c, w2c, b2c,
-                              *([a_lo] if a_lo is not None else []), *flows_v, *resids_v)
+                              *([a_lo] if a_lo is not None else []), *([wp_bwd] if wp_bwd is not None else []),
+                              *flows_v, *resids_v)
         ctx.mark_non_differentiable(*vis_tensors)
         ctx.set_materialize_grads(False)
         return (loss_buf[:ndir], loss_buf[ndir], *vis_tensors)
@@ -124,6 +131,7 @@ class RcfHeadFn(torch.autograd.Function):
         masks_v, ctx_buf, feat, a_hi, sign, cw1c, cw2c, cb2c, w1c, b1c, w2c, b2c = saved[:12]
         rest = saved[12:]
         a_lo = rest.pop(0) if ctx.has_lo else None
+        wp_bwd = rest.pop(0) if ctx.has_wp else None
         flows_v, resids_v = rest[:ndir], rest[ndir:2 * ndir]
         dev = masks_v.device
         need = ctx.needs_input_grad          # (spec, nprod, slope, masks, cw1, cb1, cw2, cb2, w1, b1, w2, b2, *flows, *resids)
@@ -186,7 +194,9 @@ class RcfHeadFn(torch.autograd.Function):
                                         C.byref(grads), stream), "rcf_backward")
         d_cw1 = d_cb1 = d_cw2 = None
         if need_conv:
-            d_a1 = c64.conv64_pair(g_hi, g_lo if nprod == 3 else None, c64.pack_weights(cw2c, True), nprod)     # data gradient
+            if wp_bwd is None:
+                wp_bwd = c64.pack_weights(cw2c, True)
+            d_a1 = c64.conv64_pair(g_hi, g_lo if nprod == 3 else None, wp_bwd, nprod)     # data gradient
             d_cw2 = c64.conv64_wgrad_pair(a_hi, a_lo, g_hi, g_lo, nprod)
             d_cw1, d_cb1 = stem_backward_raw(flows_v, tuple(cw1c.shape), ctx.clamp, ctx.stem_slope, None, sign, d_a1, nprod=ctx.nprod)
         return (None, None, None, d_masks, d_cw1, d_cb1, d_cw2, d_cb2, *dmlp, *([None] * ndir), *d_resids)
