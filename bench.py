@@ -712,8 +712,15 @@ def extras(pkg, dev):
         "c1_full_head_B2_480x854": (2, 4, 480, 854, dict(free_residual=True, clamp_flow_t=20.0), 10),
         "davis_stage1_train_B8_96x96_full_head": (8, 4, 96, 96, dict(free_residual=True, clamp_flow_t=20.0), 50),
         "stv2_stage1_train_B8_48x48_affine_full_head": (8, 4, 48, 48, dict(free_residual_with_affine=True, clamp_flow_t=20.0), 50),
+        # the AMP configs (configs/rcf_stv2/rcf_stage1.yaml:60, configs/rcf_fbms59/rcf_stage1.yaml:61 `precision: 16`):
+        # BOTH arms inside torch.autocast(fp16) -- the port runs its convs / einsums in fp16 and the solve in fp32 like
+        # the reference (:215-217); the drop-in runs the tcgen05 convs with plain bf16 operands and the loss core in fp32
+        "amp_stv2_stage1_train_B8_48x48_affine_full_head": (8, 4, 48, 48, dict(free_residual_with_affine=True, clamp_flow_t=20.0), 50),
+        "amp_fbms_K3_B2_480x854_affine_full_head": (2, 3, 480, 854, dict(free_residual_with_affine=True, clamp_flow_t=20.0), 10),
     }
+    import contextlib
     for name, (B_, K_, H_, W_, kw, steps) in cases.items():
+        amp = (lambda: torch.autocast("cuda", dtype=torch.float16)) if name.startswith("amp_") else contextlib.nullcontext
         try:
             ins = synthetic_inputs(B_, K_, H_, W_, seed=0, device=dev)
             imgs = torch.zeros(B_, 2, 3, 8, 8)
@@ -733,12 +740,13 @@ def extras(pkg, dev):
                 params = list(head.parameters()) if kw.get("num_flow_feat_channels", 64) > 2 else []
 
                 def fn():
-                    _, l = head(imgs, m, ins[1], ins[2], r1, r2)
-                    torch.autograd.grad(l["seg"], [m, r1, r2, *params])
+                    with amp():
+                        _, l = head(imgs, m, ins[1], ins[2], r1, r2)
+                    torch.autograd.grad(l["seg"].float(), [m, r1, r2, *params])
 
                 ms = _time_cuda(fn, steps)
                 res[impl] = {"ms_per_step": ms, "samples_per_s": B_ / ms * 1e3}
-                if impl == "ours" and H_ * W_ <= 128 * 128:
+                if impl == "ours" and H_ * W_ <= 128 * 128 and not name.startswith("amp_"):
                     # launch-bound regime: the same head captured once into CUDA graphs (fwd graph + bwd graph)
                     try:
                         from rcf_unsupvideoseg_b200.graphed import make_graphed_head
@@ -760,6 +768,62 @@ def extras(pkg, dev):
             out[name] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
             torch.cuda.empty_cache()
     out.update(caller_side_step(pkg, dev))
+    try:
+        out["warp_utils_kernels"] = warp_kernels(pkg, dev)
+    except Exception as ex:  # noqa: BLE001
+        out["warp_utils_kernels"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def warp_kernels(pkg, dev):
+    """utils/warp_utils.py: flow_warp fwd+bwd and get_corresponding_map, ours vs the ATen op
+    sequence the reference runs (grid_sample on a normalised grid; floor/clamp/cat + scatter_add_), same GPU, eager."""
+    import torch
+    import torch.nn.functional as F
+
+    from rcf_unsupvideoseg_b200 import warp_utils as wu
+
+    def ref_flow_warp(x, flow):                    # utils/warp_utils.py:84-94
+        B_, _, H_, W_ = flow.shape
+        ys, xs = torch.meshgrid(torch.arange(H_, device=dev, dtype=x.dtype), torch.arange(W_, device=dev, dtype=x.dtype), indexing="ij")
+        gx = 2.0 * (xs[None] + flow[:, 0]) / (W_ - 1) - 1.0
+        gy = 2.0 * (ys[None] + flow[:, 1]) / (H_ - 1) - 1.0
+        return F.grid_sample(x, torch.stack([gx, gy], dim=-1), mode="bilinear", padding_mode="border", align_corners=True)
+
+    def ref_corr_map(data):                        # utils/warp_utils.py:27-81
+        B_, _, H_, W_ = data.shape
+        x, y = data[:, 0].reshape(B_, -1), data[:, 1].reshape(B_, -1)
+        xf, yf = torch.floor(x), torch.floor(y)
+        acc = torch.zeros(B_, H_ * W_, device=dev, dtype=data.dtype)
+        for cx, cy in ((xf + 1, yf + 1), (xf + 1, yf), (xf, yf + 1), (xf, yf)):
+            cxc, cyc = cx.clamp(0, W_ - 1), cy.clamp(0, H_ - 1)
+            v = (1 - (x - cxc).abs()) * (1 - (y - cyc).abs())
+            v = torch.where((cx != cxc) | (cy != cyc), torch.zeros_like(v), v)
+            acc.scatter_add_(1, (cxc + cyc * W_).long(), v)
+        return acc.view(B_, 1, H_, W_)
+
+    out = {}
+    for tag, (B_, H_, W_) in {"B16_480x854": (16, 480, 854), "B8_96x96": (8, 96, 96)}.items():
+        g = torch.Generator(device=dev).manual_seed(0)
+        x = torch.randn(B_, 2, H_, W_, device=dev, generator=g).requires_grad_(True)
+        flow = (torch.randn(B_, 2, H_, W_, device=dev, generator=g) * 4).requires_grad_(True)
+        ys, xs = torch.meshgrid(torch.arange(H_, device=dev, dtype=torch.float32), torch.arange(W_, device=dev, dtype=torch.float32), indexing="ij")
+        coords = torch.stack([xs, ys])[None] + flow.detach()
+        go = torch.randn(B_, 2, H_, W_, device=dev, generator=g)
+        row = {}
+        for impl, fw_, cm_ in (("ours", lambda: wu.flow_warp(x, flow), lambda: wu.get_corresponding_map(coords)),
+                               ("aten", lambda: ref_flow_warp(x, flow), lambda: ref_corr_map(coords))):
+            def warp_step():
+                torch.autograd.grad(fw_(), [x, flow], grad_outputs=go)
+            row[impl] = {"flow_warp_fwd_bwd_ms": _time_cuda(warp_step, 20), "corresponding_map_ms": _time_cuda(cm_, 20)}
+        row["speedup_flow_warp"] = row["aten"]["flow_warp_fwd_bwd_ms"] / row["ours"]["flow_warp_fwd_bwd_ms"]
+        row["speedup_corresponding_map"] = row["aten"]["corresponding_map_ms"] / row["ours"]["corresponding_map_ms"]
+        px = B_ * H_ * W_
+        row["ours_flow_warp_algorithmic_gbs"] = px * (4 * 2 * 3 + 4 * 2 * 3) / row["ours"]["flow_warp_fwd_bwd_ms"] / 1e6   # fwd: x, flow, out; bwd: gout, gx, gflow (2 ch each)
+        out[tag] = row
+        del x, flow, coords, go
+        torch.cuda.empty_cache()
     return out
 
 
