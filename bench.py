@@ -360,7 +360,23 @@ def run_ours(args):
     head = pkg.FlowAggregationHeadWithResidual(args=None, create_flownet=True, **HEAD_KW).to(dev)
     head.return_flows = False
     head.loss_inv_n = inv_n
-    pin = [t.pin_memory() for t in (masks_h, fw_h, bw_h, rfw_h, rbw_h)]
+    wc_note = None
+    if os.environ.get("RCF_BENCH_WC", "0") == "1":
+        # experiment: write-combined pinned staging buffers for the host->device sources (the CPU only ever writes them)
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        pin = []
+        for t in (masks_h, fw_h, bw_h, rfw_h, rbw_h):
+            ptr = ctypes.c_void_p()
+            rc_ = rt.cudaHostAlloc(ctypes.byref(ptr), ctypes.c_size_t(t.numel() * 4), ctypes.c_uint(0x04))   # cudaHostAllocWriteCombined
+            assert rc_ == 0, f"cudaHostAlloc -> {rc_}"
+            buf = (ctypes.c_float * t.numel()).from_address(ptr.value)
+            w_ = torch.frombuffer(buf, dtype=torch.float32).view(t.shape)
+            w_.copy_(t)
+            pin.append(w_)
+        wc_note = "host->device staging buffers are write-combined pinned memory (cudaHostAllocWriteCombined)"
+    else:
+        pin = [t.pin_memory() for t in (masks_h, fw_h, bw_h, rfw_h, rbw_h)]
     out_pin = [torch.empty(2, dtype=torch.float32).pin_memory(), torch.empty_like(masks_h).pin_memory(),
                torch.empty_like(rfw_h).pin_memory(), torch.empty_like(rbw_h).pin_memory()]
     imgs = torch.zeros(B, 2, 3, 8, 8)
@@ -408,6 +424,38 @@ def run_ours(args):
             keep.pop(0)
 
     e2e_steps = max(3, min(args.steps, 20))
+
+    # The host's ceiling for this traffic pattern: the same host->device and device->host copies on the same two streams
+    # with NO compute between them, all ranks at once (what the PCIe / host-memory fabric gives this many concurrent GPUs).
+    d_out_src = [torch.empty_like(t, device=dev) for t in out_pin]
+
+    def copy_only_step(i):
+        with torch.cuda.stream(s_in):
+            for d, src in zip(d_in[i % NBUF], pin):
+                d.copy_(src, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for dst, src in zip(out_pin, d_out_src):
+                dst.copy_(src, non_blocking=True)
+
+    for i in range(2):
+        copy_only_step(i)
+    s_cmp.wait_stream(s_in); s_cmp.wait_stream(s_out)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    s_in.wait_event(c0); s_out.wait_event(c0)
+    for i in range(e2e_steps):
+        copy_only_step(i)
+    s_cmp.wait_stream(s_in); s_cmp.wait_stream(s_out)
+    c1.record()
+    torch.cuda.synchronize()
+    barrier()
+    tc = torch.tensor([c0.elapsed_time(c1)], device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    copy_only_ms = float(tc) / e2e_steps
+    del d_out_src
+
     for i in range(4):
         e2e_step(i)
     s_cmp.wait_event(ev_out_done)
@@ -443,6 +491,10 @@ def run_ours(args):
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "pcie_gbs_each_way": [h2d / e2e_ms / 1e6, d2h / e2e_ms / 1e6],
                     "note": "PCIe-bound; copies of neighbouring steps overlap compute on 3 streams", "host_numa": numa_note,
+                    "copy_only_ms_per_step": copy_only_ms,
+                    "copy_only_gbs_each_way": [h2d / copy_only_ms / 1e6, d2h / copy_only_ms / 1e6],
+                    "copy_only_note": "the same H2D + D2H copies with no compute, all ranks at once: the host's ceiling for e2e",
+                    "staging": wc_note or "torch pin_memory() (cudaHostAlloc default flags)",
                     "conv_precision": "follows torch.backends.cudnn.allow_tf32 (torch default True -> 2 bf16 products, "
                                       "weights hi+lo; False -> 3 products, fp32-grade)"},
             # value region: k_loss, k_finalize, k_loss_sum | k_segment_bwd, k_bwd per step (single-pass forward), NBLOCKS blocks;
