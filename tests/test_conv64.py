@@ -95,6 +95,43 @@ def test_conv64_one_cta_and_cta_pair_kernels_agree(c64):
     assert lib.rcf_debug_conv64_status() == 0
 
 
+def test_conv64_pack_both_orientations_in_one_launch(c64):
+    """transpose_flip = 2 writes the forward image followed by the data-gradient image: byte-identical to the two single packs."""
+    w = torch.randn(64, 64, 3, 3, device="cuda") / 24
+    f, b = c64.pack_weights_both(w)
+    torch.cuda.synchronize()
+    assert torch.equal(f, c64.pack_weights(w, False)) and torch.equal(b, c64.pack_weights(w, True))
+
+
+def test_stem_tf32_mode_vs_fp64():
+    """nprod < 3 on the stem entry points = one round-to-nearest TF32 product (the allow_tf32 / autocast policy): errors at
+    TF32 level (2^-11 per operand), against 1e-6 for the 3xTF32 mode."""
+    from rcf_unsupvideoseg_b200 import fused_head, stem
+    torch.manual_seed(3)
+    B, H, W = 2, 37, 53
+    fl = [torch.randn(B, 2, H, W, device="cuda") * 6 for _ in range(2)]
+    w = torch.randn(64, 2, 3, 3, device="cuda") / 4
+    b = torch.randn(64, device="cuda") / 4
+    x = torch.cat([f.clamp(-20, 20) for f in fl], 0).double()
+    pre = torch.nn.functional.conv2d(x, w.double(), b.double(), padding=1)
+    ref = torch.nn.functional.leaky_relu(pre, 0.1)
+    g = torch.randn(2 * B, 64, H, W, device="cuda").contiguous(memory_format=torch.channels_last)
+    errs = {}
+    for nprod in (3, 1):
+        hi, lo, sign = fused_head.stem_forward_pair(fl, w, b, 20.0, 0.1, want_lo=True, nprod=nprod)
+        act = hi.float() + lo.float()
+        dw, db = stem.stem_backward_raw(fl, tuple(w.shape), 20.0, 0.1, None, sign, g, nprod=nprod)
+        torch.cuda.synchronize()
+        # the backward is checked for the LeakyReLU mask its own forward produced: pre-activations within the forward's
+        # rounding error of zero (3e-4 of the elements in TF32) take the other branch, in cuDNN's TF32 kernels as well
+        gpre = g.double() * torch.where(act > 0, 1.0, 0.1)
+        dw_ref = torch.nn.grad.conv2d_weight(x, w.shape, gpre, padding=1)
+        db_ref = gpre.sum((0, 2, 3))
+        errs[nprod] = (_rel(act, ref), _rel(dw, dw_ref), _rel(db, db_ref))
+    assert max(errs[3]) < 2e-5, errs          # activation limited by the bf16 pair (2^-17), gradients fp32-grade
+    assert max(errs[1]) < 2e-3 and errs[1][1] > errs[3][1], errs
+
+
 def test_conv64_is_bit_reproducible(c64):
     x = torch.randn(2, 64, 40, 52, device="cuda").contiguous(memory_format=torch.channels_last)
     w = torch.randn(64, 64, 3, 3, device="cuda") / 24
