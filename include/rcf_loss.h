@@ -296,6 +296,8 @@ RCF_API int rcf_debug_time_kernel(int which, void* start_event, void* stop_event
 
 /* Implementation switches for A/B measurements (process-wide; results are bit-identical either way).
  * (options 1 and 2 belonged to a single-launch forward experiment that was measured slower and removed) */
+/* These switches are process-wide measurement aids.  Do not change RCF_OPT_SINGLE_PASS between an rcf_forward and the
+ * rcf_backward that consumes its ctx: the backward would look for coefficients the forward did not write. */
 #define RCF_OPT_L2_HINTS 3       /* evict-first streaming loads of flow/residual in pass 2 (default 1) */
 #define RCF_OPT_SINGLE_PASS 4    /* theta_mode 0 with D == 0: skip pass 1, S_k is accumulated inside pass 2 (default 1) */
 #define RCF_OPT_PDL 5            /* programmatic dependent launch between the library's consecutive kernels (default 1) */

@@ -23,12 +23,7 @@ class _LossOnly(nn.Module):
         self._imgs = torch.empty(imgs_shape, device="meta")      # only .shape is read by forward (reference :322-324)
 
     def forward(self, masks, gt_fw, gt_bw, res_fw, res_bw):
-        prev = self.head.return_flows
-        self.head.return_flows = False
-        try:
-            _, fl = self.head(self._imgs, masks, gt_fw, gt_bw, res_fw, res_bw)
-        finally:
-            self.head.return_flows = prev
+        _, fl = self.head._forward_impl(self._imgs, masks, gt_fw, gt_bw, res_fw, res_bw, want_flows=False)
         return fl["seg_fw"], fl["seg_bw"], fl["seg"]
 
 

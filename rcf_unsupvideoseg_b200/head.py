@@ -349,6 +349,12 @@ class FlowAggregationHeadWithResidual(nn.Module):
 
     def forward(self, imgs, masks, gt_fw_flows, gt_bw_flows, all_pred_residual_fw, all_pred_residual_bw):
         """reference :312-399.  masks [B,2,K,H,W]; gt_*_flows [B,1,2,H,W]; residuals [B,2K,h,w]."""
+        return self._forward_impl(imgs, masks, gt_fw_flows, gt_bw_flows, all_pred_residual_fw, all_pred_residual_bw,
+                                  want_flows=self.return_flows)
+
+    def _forward_impl(self, imgs, masks, gt_fw_flows, gt_bw_flows, all_pred_residual_fw, all_pred_residual_bw, *, want_flows):
+        """forward() with the visualisation switch as an argument (graphed.py captures with want_flows=False without
+        touching the module's `return_flows` attribute, which other callers of the same head may be reading)."""
         flow_loss = {'seg_fw': 0., 'seg_bw': 0.}
         flows: Dict[str, List[torch.Tensor]] = {'gt_flow': [], 'pred_flow': [], 'agg_flow': [],
                                                 'residual_adj': [], 'affine_flow': []}
@@ -358,10 +364,10 @@ class FlowAggregationHeadWithResidual(nn.Module):
         gt_fw_flow = gt_fw_flows[:, 0, ...]
         gt_bw_flow = gt_bw_flows[:, 0, ...]
         loss, total, vis = self._run(masks, [gt_fw_flow, gt_bw_flow], [all_pred_residual_fw, all_pred_residual_bw],
-                                     want_vis=self.return_flows, vis_norm=True, inv_n=float(self.loss_inv_n))
+                                     want_vis=want_flows, vis_norm=True, inv_n=float(self.loss_inv_n))
         flow_loss['seg_fw'] = loss[0]
         flow_loss['seg_bw'] = loss[1]
-        if self.return_flows:
+        if want_flows:
             flows['gt_flow'].append(vis[0])
             flows['pred_flow'].append(vis[1])
             flows['agg_flow'].append(vis[2])
