@@ -190,8 +190,17 @@ def device_guard(dev):
     """`with torch.cuda.device(dev)` only when dev is not already current: the context manager costs ~10 us of host time
     per use, and a step of the drop-in head enters it 8 times (launch-bound at the 96x96 / 48x48 training shapes)."""
     import torch
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    return _NO_GUARD if torch.cuda.current_device() == idx else torch.cuda.device(idx)
+    cur = torch._C._cuda_getDevice()
+    idx = dev.index if dev.index is not None else cur
+    return _NO_GUARD if cur == idx else torch.cuda.device(idx)
+
+
+def raw_stream(dev) -> int:
+    """cudaStream_t of torch's current stream on `dev` as an integer.  `_lib.raw_stream(dev)` builds a
+    Stream object per call (~9 us; ten of them per step of the head at the training shapes); this is one C call."""
+    import torch
+    idx = dev.index if dev.index is not None else torch._C._cuda_getDevice()
+    return torch._C._cuda_getCurrentRawStream(idx)
 
 
 def check(code: int, what: str):

@@ -36,7 +36,7 @@ def pack_weights(w: torch.Tensor, transpose_flip: bool) -> torch.Tensor:
     out = torch.empty(WPACK_BYTES, dtype=torch.uint8, device=w.device)
     with _lib.device_guard(w.device):
         _lib.check(lib.rcf_conv64_pack_weights(w.data_ptr(), out.data_ptr(), int(transpose_flip),
-                                               torch.cuda.current_stream(w.device).cuda_stream), "rcf_conv64_pack_weights")
+                                               _lib.raw_stream(w.device)), "rcf_conv64_pack_weights")
     return out
 
 
@@ -48,7 +48,7 @@ def pack_weights_both(w: torch.Tensor):
     out = torch.empty(2 * WPACK_BYTES, dtype=torch.uint8, device=w.device)
     with _lib.device_guard(w.device):
         _lib.check(lib.rcf_conv64_pack_weights(w.data_ptr(), out.data_ptr(), 2,
-                                               torch.cuda.current_stream(w.device).cuda_stream), "rcf_conv64_pack_weights")
+                                               _lib.raw_stream(w.device)), "rcf_conv64_pack_weights")
     return out[:WPACK_BYTES], out[WPACK_BYTES:]
 
 
@@ -59,7 +59,7 @@ def split_bf16(x: torch.Tensor, want_lo: bool = True):
     lo = torch.empty_like(x, dtype=torch.bfloat16) if want_lo else None
     with _lib.device_guard(x.device):
         _lib.check(lib.rcf_split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr() if want_lo else None, x.numel(),
-                                      torch.cuda.current_stream(x.device).cuda_stream), "rcf_split_bf16")
+                                      _lib.raw_stream(x.device)), "rcf_split_bf16")
     return hi, lo
 
 
@@ -75,7 +75,7 @@ def conv64_pair(x_hi: torch.Tensor, x_lo, wpack: torch.Tensor, nprod: int) -> to
     with _lib.device_guard(x_hi.device):
         _lib.check(lib.rcf_conv64_forward(x_hi.data_ptr(), x_lo.data_ptr() if x_lo is not None else None, wpack.data_ptr(),
                                           out.data_ptr(), N, H, W, int(nprod),
-                                          torch.cuda.current_stream(x_hi.device).cuda_stream), "rcf_conv64_forward")
+                                          _lib.raw_stream(x_hi.device)), "rcf_conv64_forward")
     return out
 
 
@@ -111,7 +111,7 @@ def conv64_wgrad_pair(x_hi, x_lo, g_hi, g_lo, nprod: int) -> torch.Tensor:
     with _lib.device_guard(dev):
         _lib.check(lib.rcf_conv64_wgrad(x_hi.data_ptr(), x_lo.data_ptr() if x_lo is not None else None, g_hi.data_ptr(),
                                         g_lo.data_ptr() if g_lo is not None else None, dw.data_ptr(), ws.data_ptr(), N, H, W,
-                                        int(nprod), torch.cuda.current_stream(dev).cuda_stream), "rcf_conv64_wgrad")
+                                        int(nprod), _lib.raw_stream(dev)), "rcf_conv64_wgrad")
     return dw
 
 

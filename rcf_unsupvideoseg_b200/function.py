@@ -193,7 +193,7 @@ class RcfMotionLossFn(torch.autograd.Function):
             desc.vis_dstride = 2 * P
             desc.vis_scale[0], desc.vis_scale[1] = spec.vis_scale
 
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _lib.raw_stream(dev)
         with _lib.device_guard(dev):
             _lib.check(lib.rcf_forward(C.byref(desc), C.byref(inp), loss_buf.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
                                        C.byref(vis_struct) if vis_struct is not None else None, stream), "rcf_forward")
@@ -294,7 +294,7 @@ class RcfMotionLossFn(torch.autograd.Function):
             if grad_total is not None:
                 gl = gl + grad_total.detach().to(torch.float32)
             gl = gl.contiguous()
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _lib.raw_stream(dev)
         with _lib.device_guard(dev):
             _lib.check(lib.rcf_backward(C.byref(desc), C.byref(inp), gl.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
                                         C.byref(grads), stream), "rcf_backward")

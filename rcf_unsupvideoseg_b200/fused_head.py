@@ -42,7 +42,7 @@ def stem_forward_pair(fl, w, b, clamp_t: float, slope: float, want_lo: bool, npr
     with _lib.device_guard(dev):
         _lib.check(lib.rcf_stem_forward_bf16(ptrs, strides, ndir, B, H, W, ks, w.data_ptr(), b.data_ptr(), float(clamp_t),
                                              float(slope), hi.data_ptr(), lo.data_ptr() if lo is not None else None,
-                                             sign.data_ptr(), int(nprod), torch.cuda.current_stream(dev).cuda_stream),
+                                             sign.data_ptr(), int(nprod), _lib.raw_stream(dev)),
                    "rcf_stem_forward_bf16")
     return hi, lo, sign
 
@@ -102,7 +102,7 @@ class RcfHeadFn(torch.autograd.Function):
             vis_struct.aff = vis_tensors[4].data_ptr() if n_out == 5 else None
             desc.vis_bstride, desc.vis_dstride = 2 * ndir * P, 2 * P
             desc.vis_scale[0], desc.vis_scale[1] = spec.vis_scale
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _lib.raw_stream(dev)
         with _lib.device_guard(dev):
             _lib.check(lib.rcf_forward(C.byref(desc), C.byref(inp), loss_buf.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
                                        C.byref(vis_struct) if vis_struct is not None else None, stream), "rcf_forward")
@@ -188,7 +188,7 @@ class RcfHeadFn(torch.autograd.Function):
             if grad_total is not None:
                 gl = gl + grad_total.detach().to(torch.float32)
             gl = gl.contiguous()
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _lib.raw_stream(dev)
         with _lib.device_guard(dev):
             _lib.check(lib.rcf_backward(C.byref(desc), C.byref(inp), gl.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
                                         C.byref(grads), stream), "rcf_backward")

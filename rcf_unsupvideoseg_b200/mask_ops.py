@@ -49,7 +49,7 @@ class _MaskLossesFn(torch.autograd.Function):
         with _lib.device_guard(x.device):
             _lib.check(lib.rcf_mask_losses_forward(C.byref(cfg), x.data_ptr(), tgt.data_ptr() if tgt is not None else None,
                                                    masks.data_ptr(), losses.data_ptr(), fstats.data_ptr(), ws.data_ptr(),
-                                                   torch.cuda.current_stream(x.device).cuda_stream), "rcf_mask_losses_forward")
+                                                   _lib.raw_stream(x.device)), "rcf_mask_losses_forward")
         ctx.cfg = cfg
         ctx.save_for_backward(masks, fstats, *([tgt] if tgt is not None else []))
         ctx.set_materialize_grads(False)
@@ -70,7 +70,7 @@ class _MaskLossesFn(torch.autograd.Function):
             _lib.check(lib.rcf_mask_losses_backward(C.byref(ctx.cfg), masks.data_ptr(), rest[0].data_ptr() if rest else None,
                                                     gm.data_ptr() if gm is not None else None,
                                                     gl.data_ptr() if gl is not None else None, fstats.data_ptr(),
-                                                    dl.data_ptr(), torch.cuda.current_stream(masks.device).cuda_stream),
+                                                    dl.data_ptr(), _lib.raw_stream(masks.device)),
                        "rcf_mask_losses_backward")
         return (dl,) + (None,) * 9
 

@@ -36,7 +36,7 @@ class _ResizeFn(torch.autograd.Function):
         with _lib.device_guard(x0.device):
             _lib.check(lib.rcf_resize_bilinear_forward(_ptrs(xv), _ptrs(outs), len(xs), B * Cc, h, w, H, W,
                                                        int(bool(align_corners)),
-                                                       torch.cuda.current_stream(x0.device).cuda_stream),
+                                                       _lib.raw_stream(x0.device)),
                        "rcf_resize_bilinear_forward")
         ctx.meta = (B, Cc, h, w, H, W, bool(align_corners), len(xs))
         ctx.set_materialize_grads(False)
@@ -54,7 +54,7 @@ class _ResizeFn(torch.autograd.Function):
             gi = [torch.empty(B, Cc, h, w, dtype=torch.float32, device=gv[0].device) for _ in idx]
             with _lib.device_guard(gv[0].device):
                 _lib.check(lib.rcf_resize_bilinear_backward(_ptrs(gv), _ptrs(gi), len(idx), B * Cc, h, w, H, W, int(align),
-                                                            torch.cuda.current_stream(gv[0].device).cuda_stream),
+                                                            _lib.raw_stream(gv[0].device)),
                            "rcf_resize_bilinear_backward")
             for i, g in zip(idx, gi):
                 res[i] = g
@@ -87,5 +87,5 @@ def stage_flow_hwc(flow_hwc: torch.Tensor, size, align_corners: bool = False, ch
     cs = (C.c_float * Cc)(*[float(v) for v in channel_scale]) if channel_scale is not None else None
     with _lib.device_guard(x.device):
         _lib.check(lib.rcf_flow_stage_hwc(x.data_ptr(), out.data_ptr(), N, Cc, h, w, H, W, int(bool(align_corners)), cs,
-                                          torch.cuda.current_stream(x.device).cuda_stream), "rcf_flow_stage_hwc")
+                                          _lib.raw_stream(x.device)), "rcf_flow_stage_hwc")
     return out

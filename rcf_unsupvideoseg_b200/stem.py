@@ -48,7 +48,7 @@ def stem_forward_raw(fl, w, b, clamp_t: float, slope: float):
         _lib.check(lib.rcf_stem_forward(ptrs, strides, ndir, B, H, W, Cf, ks, w.data_ptr(), b.data_ptr(),
                                         float(clamp_t), float(slope), act.data_ptr(),
                                         sign.data_ptr() if sign is not None else None,
-                                        torch.cuda.current_stream(dev).cuda_stream), "rcf_stem_forward")
+                                        _lib.raw_stream(dev)), "rcf_stem_forward")
     return act, sign
 
 
@@ -71,7 +71,7 @@ def stem_backward_raw(fl, w_shape, clamp_t: float, slope: float, act, sign, dact
         _lib.check(lib.rcf_stem_backward(ptrs, strides, ndir, B, H, W, Cf, ks, clamp_t, slope,
                                          None if sign is not None else act.data_ptr(),
                                          sign.data_ptr() if sign is not None else None, g.data_ptr(), dw.data_ptr(),
-                                         db.data_ptr(), ws.data_ptr(), int(nprod), torch.cuda.current_stream(dev).cuda_stream),
+                                         db.data_ptr(), ws.data_ptr(), int(nprod), _lib.raw_stream(dev)),
                    "rcf_stem_backward")
     return dw, db
 

@@ -45,7 +45,7 @@ class _FlowWarpFn(torch.autograd.Function):
         out = torch.empty_like(xc)
         with _lib.device_guard(xc.device):
             _lib.check(lib.rcf_flow_warp_forward(xc.data_ptr(), fc.data_ptr(), out.data_ptr(), B, C, H, W, int(border),
-                                                 torch.cuda.current_stream(xc.device).cuda_stream), "rcf_flow_warp_forward")
+                                                 _lib.raw_stream(xc.device)), "rcf_flow_warp_forward")
         ctx.save_for_backward(xc, fc)
         ctx.border = border
         return out
@@ -63,7 +63,7 @@ class _FlowWarpFn(torch.autograd.Function):
             _lib.check(lib.rcf_flow_warp_backward(xc.data_ptr(), fc.data_ptr(), g.data_ptr(),
                                                   gx.data_ptr() if gx is not None else None,
                                                   gf.data_ptr() if gf is not None else None, B, C, H, W, int(ctx.border),
-                                                  torch.cuda.current_stream(xc.device).cuda_stream), "rcf_flow_warp_backward")
+                                                  _lib.raw_stream(xc.device)), "rcf_flow_warp_backward")
         return gx, gf, None
 
 
@@ -88,7 +88,7 @@ def get_corresponding_map(data):
     scratch = torch.empty(B * H * W, dtype=torch.int64, device=d.device)
     with _lib.device_guard(d.device):
         _lib.check(lib.rcf_corresponding_map(d.data_ptr(), out.data_ptr(), scratch.data_ptr(), B, H, W,
-                                             torch.cuda.current_stream(d.device).cuda_stream), "rcf_corresponding_map")
+                                             _lib.raw_stream(d.device)), "rcf_corresponding_map")
     return out.type_as(data)
 
 
