@@ -227,6 +227,35 @@ RCF_API int rcf_conv64_forward(const void* in_hi, const void* in_lo, const void*
 RCF_API int rcf_conv64_wgrad_workspace_bytes(int nimg, int H, int W, size_t* bytes);
 RCF_API int rcf_conv64_wgrad(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, float* dw, void* ws,
                              int nimg, int H, int W, int nprod, void* stream);
+
+/* ---- the default head as two calls (what fused_head.py binds): stem -> weight pack -> tcgen05 conv -> rcf_forward, and
+ * rcf_backward -> data gradient -> weight gradient -> stem backward.  Same kernels and results as the individual entry
+ * points above; one call each way keeps the host cost per step (ctypes marshalling, Python glue) off the launch-bound
+ * 96x96 / 48x48 training shapes.  All buffers are caller-owned device memory; feat / dfeat pointers inside `in` / `grads`
+ * are filled by the library from RcfHeadBuffers (desc->feat_nhwc = 1, Cf = 64, feat_bstride = dfeat_bstride = H*W*64). */
+typedef struct RcfHeadBuffers {
+    void* a_hi;            /* bf16 [ndir*B,H,W,64]: LeakyReLU(conv1(clamp(flow))), hi words                         */
+    void* a_lo;            /* same shape, lo words; NULL unless nprod == 3                                          */
+    uint32_t* sign;        /* [ndir*B*H*W*2] sign bits of the stem's pre-activation                                 */
+    void* wpack;           /* forward: 2 x RCF_CONV64_WPACK_BYTES (both orientations are packed); backward: same    */
+    float* feat;           /* fp32 [ndir*B,H,W,64]: conv2 output without bias                                       */
+    /* backward only */
+    void* g_hi;            /* bf16 [ndir*B,H,W,64]: gradient w.r.t. feat, hi words                                  */
+    void* g_lo;            /* lo words; NULL when nprod == 1                                                        */
+    float* d_a1;           /* fp32 [ndir*B,H,W,64]: gradient w.r.t. the stem's output                               */
+    void* wgrad_ws;        /* rcf_conv64_wgrad_workspace_bytes(ndir*B, H, W)                                        */
+    void* stem_ws;         /* rcf_stem_workspace_bytes(ndir, B, H, W, 64, ks)                                       */
+    float* d_cw1;          /* [64,2,ks,ks] */
+    float* d_cb1;          /* [64]         */
+    float* d_cw2;          /* [64,64,3,3]  */
+} RcfHeadBuffers;
+RCF_API int rcf_head_forward(const RcfDesc* desc, const RcfInputs* in, const float* cw1, const float* cb1, const float* cw2,
+                             int ks, float stem_slope, int nprod, const RcfHeadBuffers* hb, float* loss, void* ctx, void* ws,
+                             const RcfVisOut* vis, void* stream);
+/* need_conv_grads = 0: only rcf_backward runs (no gradient reaches the conv parameters). */
+RCF_API int rcf_head_backward(const RcfDesc* desc, const RcfInputs* in, const float* grad_loss, const void* ctx, void* ws,
+                              RcfGrads* grads, int ks, float stem_slope, int nprod, int need_conv_grads,
+                              const RcfHeadBuffers* hb, void* stream);
 /* x (n fp32 values, n % 4 == 0) -> hi = bf16(x), lo = bf16(x - hi) (lo may be NULL). */
 RCF_API int rcf_split_bf16(const float* x, void* hi, void* lo, size_t n, void* stream);
 /* Measurement hook: device buffer of 64 x 8 int64 filled by CTA 0 of the following conv launches with clock64 stamps

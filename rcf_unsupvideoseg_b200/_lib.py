@@ -62,13 +62,18 @@ class RcfGrads(C.Structure):
     ]
 
 
+class RcfHeadBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("a_hi", "a_lo", "sign", "wpack", "feat", "g_hi", "g_lo", "d_a1", "wgrad_ws", "stem_ws",
+                                          "d_cw1", "d_cb1", "d_cw2")]
+
+
 EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "rcf_forward", "rcf_backward",
                     "rcf_debug_time_kernel", "rcf_flow_warp_forward", "rcf_flow_warp_backward", "rcf_corresponding_map",
                     "rcf_debug_set_option", "rcf_stem_forward", "rcf_stem_workspace_bytes", "rcf_stem_backward",
                     "rcf_resize_bilinear_forward", "rcf_resize_bilinear_backward", "rcf_flow_stage_hwc",
                     "rcf_mask_prep_workspace_floats", "rcf_mask_losses_forward", "rcf_mask_losses_backward",
                     "rcf_conv64_pack_weights", "rcf_conv64_forward", "rcf_split_bf16", "rcf_debug_conv64_status", "rcf_stem_forward_bf16", "rcf_conv64_wgrad_workspace_bytes", "rcf_conv64_wgrad",
-                    "rcf_debug_conv64_trace")
+                    "rcf_debug_conv64_trace", "rcf_head_forward", "rcf_head_backward")
 
 _lib = None
 _lock = threading.Lock()
@@ -159,6 +164,14 @@ def load_library(build_if_missing: bool = True):
         lib.rcf_conv64_wgrad.restype = C.c_int
         lib.rcf_conv64_wgrad.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_void_p]
+        lib.rcf_head_forward.restype = C.c_int
+        lib.rcf_head_forward.argtypes = [C.POINTER(RcfDesc), C.POINTER(RcfInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_float, C.c_int, C.POINTER(RcfHeadBuffers), C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+        lib.rcf_head_backward.restype = C.c_int
+        lib.rcf_head_backward.argtypes = [C.POINTER(RcfDesc), C.POINTER(RcfInputs), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(RcfGrads), C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(RcfHeadBuffers),
+                                          C.c_void_p]
         lib.rcf_split_bf16.restype = C.c_int
         lib.rcf_split_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         lib.rcf_debug_conv64_trace.restype = C.c_int

@@ -1,0 +1,78 @@
+// rcf_head.cu -- the default head (64 feature channels, 3x3 second conv) as one C call each way.
+//
+// Pure host code: it chains the library's own entry points (stem -> weight pack -> tcgen05 conv -> rcf_forward;
+// rcf_backward -> data gradient -> weight gradient -> stem backward) on one stream, so the Python mirror
+// (fused_head.py) crosses the ctypes boundary twice per step instead of nine times.  Reference lines: the body of
+// FlowAggregationHeadWithResidual.forward for one call, models/flow_aggregation_head_with_residual.py:312-399.
+#include <cstdint>
+
+#include "rcf_loss.h"
+
+namespace {
+constexpr int HEAD_CF = 64;
+
+int check_head(const RcfDesc* d, const RcfInputs* in, const RcfHeadBuffers* hb) {
+    if (!d || !in || !hb) return RCF_ERR_NULL;
+    if (d->Cf != HEAD_CF || d->theta_mode != 1 || !d->feat_nhwc) return RCF_ERR_MODE;
+    if (d->ndir < 1 || d->ndir > 2) return RCF_ERR_SHAPE;
+    const long long img = (long long)d->H * d->W * HEAD_CF;
+    for (int i = 0; i < d->ndir; ++i)
+        if (d->feat_bstride[i] != img) return RCF_ERR_SHAPE;
+    return RCF_OK;
+}
+}  // namespace
+
+extern "C" int rcf_head_forward(const RcfDesc* desc, const RcfInputs* in, const float* cw1, const float* cb1, const float* cw2,
+                                int ks, float stem_slope, int nprod, const RcfHeadBuffers* hb, float* loss, void* ctx, void* ws,
+                                const RcfVisOut* vis, void* stream) {
+    int rc = check_head(desc, in, hb);
+    if (rc != RCF_OK) return rc;
+    if (!cw1 || !cb1 || !cw2 || !hb->a_hi || !hb->sign || !hb->wpack || !hb->feat) return RCF_ERR_NULL;
+    const int ndir = desc->ndir, B = desc->B, H = desc->H, W = desc->W;
+    const long long img = (long long)H * W * HEAD_CF;
+    rc = rcf_stem_forward_bf16(in->flow, desc->flow_bstride, ndir, B, H, W, ks, cw1, cb1, desc->clamp_t, stem_slope, hb->a_hi,
+                               nprod == 3 ? hb->a_lo : nullptr, hb->sign, nprod, stream);
+    if (rc != RCF_OK) return rc;
+    rc = rcf_conv64_pack_weights(cw2, hb->wpack, 2, stream);
+    if (rc != RCF_OK) return rc;
+    rc = rcf_conv64_forward(hb->a_hi, nprod == 3 ? hb->a_lo : nullptr, hb->wpack, hb->feat, ndir * B, H, W, nprod, stream);
+    if (rc != RCF_OK) return rc;
+    RcfInputs in2 = *in;
+    for (int i = 0; i < ndir; ++i) in2.feat[i] = hb->feat + (long long)i * B * img;
+    return rcf_forward(desc, &in2, loss, ctx, ws, vis, stream);
+}
+
+extern "C" int rcf_head_backward(const RcfDesc* desc, const RcfInputs* in, const float* grad_loss, const void* ctx, void* ws,
+                                 RcfGrads* grads, int ks, float stem_slope, int nprod, int need_conv_grads,
+                                 const RcfHeadBuffers* hb, void* stream) {
+    int rc = check_head(desc, in, hb);
+    if (rc != RCF_OK) return rc;
+    if (!grads || !hb->feat) return RCF_ERR_NULL;
+    const int ndir = desc->ndir, B = desc->B, H = desc->H, W = desc->W;
+    const long long img = (long long)H * W * HEAD_CF;
+    RcfInputs in2 = *in;
+    RcfGrads g2 = *grads;
+    for (int i = 0; i < ndir; ++i) {
+        in2.feat[i] = hb->feat + (long long)i * B * img;
+        g2.dfeat[i] = nullptr;
+        g2.dfeat_hi[i] = g2.dfeat_lo[i] = nullptr;
+        if (need_conv_grads) {
+            if (!hb->g_hi || (nprod >= 2 && !hb->g_lo)) return RCF_ERR_NULL;
+            g2.dfeat_hi[i] = static_cast<uint16_t*>(hb->g_hi) + (long long)i * B * img;
+            if (nprod >= 2) g2.dfeat_lo[i] = static_cast<uint16_t*>(hb->g_lo) + (long long)i * B * img;
+        }
+    }
+    if (!need_conv_grads) g2.dfeat_bias = nullptr;
+    rc = rcf_backward(desc, &in2, grad_loss, ctx, ws, &g2, stream);
+    if (rc != RCF_OK || !need_conv_grads) return rc;
+    if (!hb->a_hi || !hb->sign || !hb->wpack || !hb->d_a1 || !hb->wgrad_ws || !hb->stem_ws || !hb->d_cw1 || !hb->d_cb1 || !hb->d_cw2)
+        return RCF_ERR_NULL;
+    const void* wp_bwd = static_cast<const uint8_t*>(hb->wpack) + RCF_CONV64_WPACK_BYTES;
+    rc = rcf_conv64_forward(hb->g_hi, nprod == 3 ? hb->g_lo : nullptr, wp_bwd, hb->d_a1, ndir * B, H, W, nprod, stream);
+    if (rc != RCF_OK) return rc;
+    rc = rcf_conv64_wgrad(hb->a_hi, nprod == 3 ? hb->a_lo : nullptr, hb->g_hi, nprod >= 2 ? hb->g_lo : nullptr, hb->d_cw2, hb->wgrad_ws,
+                          ndir * B, H, W, nprod, stream);
+    if (rc != RCF_OK) return rc;
+    return rcf_stem_backward(in->flow, desc->flow_bstride, ndir, B, H, W, HEAD_CF, ks, desc->clamp_t, stem_slope, nullptr, hb->sign,
+                             hb->d_a1, hb->d_cw1, hb->d_cb1, hb->stem_ws, nprod, stream);
+}

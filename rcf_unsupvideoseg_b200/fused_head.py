@@ -23,7 +23,7 @@ import torch
 from . import _lib
 from . import conv64 as c64
 from .function import LossSpec, _as_dir_view, _inner_dense, _make_desc, _sizes
-from .stem import _views, stem_backward_raw
+from .stem import _views
 
 
 def stem_forward_pair(fl, w, b, clamp_t: float, slope: float, want_lo: bool, nprod: int = 3):
@@ -47,10 +47,33 @@ def stem_forward_pair(fl, w, b, clamp_t: float, slope: float, want_lo: bool, npr
     return hi, lo, sign
 
 
+def _align(n: int) -> int:
+    return (n + 255) & ~255
+
+
+_AUX_BYTES = {}
+
+
+def _aux_sizes(lib, dev, ndir, B, H, W, ks):
+    """(wgrad workspace bytes, stem workspace bytes) for a shape, asked once."""
+    key = (dev.index, ndir, B, H, W, ks)
+    hit = _AUX_BYTES.get(key)
+    if hit is None:
+        a, b = C.c_size_t(), C.c_size_t()
+        _lib.check(lib.rcf_conv64_wgrad_workspace_bytes(ndir * B, H, W, C.byref(a)), "rcf_conv64_wgrad_workspace_bytes")
+        _lib.check(lib.rcf_stem_workspace_bytes(ndir, B, H, W, 64, ks, C.byref(b)), "rcf_stem_workspace_bytes")
+        hit = _AUX_BYTES[key] = (a.value, b.value)
+    return hit
+
+
 class RcfHeadFn(torch.autograd.Function):
     """Inputs: spec (LossSpec with Cf = 64), nprod, stem_slope, masks [B,ndir,K,H,W], conv-1 weight/bias, conv-2 weight/bias,
     MLP w1,b1,w2,b2, then ndir flows [B,2,H,W] (no grad) and ndir residuals [B,2K,H,W].
-    Returns (loss [ndir], total, *vis) like RcfMotionLossFn."""
+    Returns (loss [ndir], total, *vis) like RcfMotionLossFn.
+
+    One library call each way (rcf_head_forward / rcf_head_backward) and ONE device arena each way for everything that is
+    not returned to autograd (activation pair, sign bits, packed weights, feature map, ctx, scratch): at the 96x96 / 48x48
+    training shapes a step is bound by host time, not by the GPU."""
 
     @staticmethod
     def forward(ctx, spec: LossSpec, nprod: int, stem_slope: float, masks, cw1, cb1, cw2, cb2, w1, b1, w2, b2, *per_dir):
@@ -63,20 +86,12 @@ class RcfHeadFn(torch.autograd.Function):
         assert spec.Cf == 64 and (K, H, W) == (spec.K, spec.H, spec.W)
         dev = masks.device
         P = H * W
+        nimg = ndir * B
         masks_v = masks if (masks.dtype == torch.float32 and _inner_dense(masks, 3)) else masks.float().contiguous()
         flows_v = _views(flows)
         resids_v = [_as_dir_view(r) for r in resids]
         cw1c, cb1c, cw2c, cb2c, w1c, b1c, w2c, b2c = (t.detach().float().contiguous() for t in (cw1, cb1, cw2, cb2, w1, b1, w2, b2))
-
-        # conv branch: stem (bf16 pair out) -> tcgen05 conv (fp32 pre-activation, channels-last, bias applied by the pooling kernels)
-        clamp = -1.0 if spec.clamp_t is None else float(spec.clamp_t)
-        a_hi, a_lo, sign = stem_forward_pair(flows_v, cw1c, cb1c, clamp, stem_slope, want_lo=(nprod == 3), nprod=nprod)
-        need_conv_grad = any(ctx.needs_input_grad[4:8])
-        if need_conv_grad:          # the data-gradient operator of the same weights is packed by the same launch
-            wp_fwd, wp_bwd = c64.pack_weights_both(cw2c)
-        else:
-            wp_fwd, wp_bwd = c64.pack_weights(cw2c, False), None
-        feat = c64.conv64_pair(a_hi, a_lo, wp_fwd, nprod)          # [ndir*B,64,H,W] channels-last
+        ks = cw1c.shape[-1]
 
         desc = _make_desc(spec, B, ndir)
         desc.feat_nhwc = 1
@@ -86,12 +101,27 @@ class RcfHeadFn(torch.autograd.Function):
             desc.mask_bstride[i] = masks_v.stride(0)
             inp.flow[i] = flows_v[i].data_ptr(); desc.flow_bstride[i] = flows_v[i].stride(0)
             inp.resid[i] = resids_v[i].data_ptr(); desc.resid_bstride[i] = resids_v[i].stride(0)
-            inp.feat[i] = feat.data_ptr() + i * B * P * 64 * 4; desc.feat_bstride[i] = P * 64
+            desc.feat_bstride[i] = P * 64
         inp.w1, inp.b1, inp.w2, inp.b2 = (t.data_ptr() for t in (w1c, b1c, w2c, b2c))
         inp.feat_bias = cb2c.data_ptr()
         ctx_bytes, ws_bytes = _sizes(lib, desc, spec, B, ndir)
-        ctx_buf = torch.empty(ctx_bytes, dtype=torch.uint8, device=dev)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+        # arena: [a_hi | a_lo? | sign | wpack x2 | feat | ctx | ws]
+        act_b = nimg * P * 64 * 2
+        offs, o = {}, 0
+        for name, nbytes in (("a_hi", act_b), ("a_lo", act_b if nprod == 3 else 0), ("sign", nimg * P * 8),
+                             ("wpack", 2 * c64.WPACK_BYTES), ("feat", nimg * P * 64 * 4), ("ctx", ctx_bytes), ("ws", ws_bytes)):
+            offs[name] = o
+            o += _align(nbytes)
+        arena = torch.empty(o, dtype=torch.uint8, device=dev)
+        base = arena.data_ptr()
+        hb = _lib.RcfHeadBuffers()
+        hb.a_hi = base + offs["a_hi"]
+        hb.a_lo = base + offs["a_lo"] if nprod == 3 else None
+        hb.sign = base + offs["sign"]
+        hb.wpack = base + offs["wpack"]
+        hb.feat = base + offs["feat"]
+
         loss_buf = torch.empty(ndir + 1, dtype=torch.float32, device=dev)
         vis_tensors, vis_struct = (), None
         if spec.want_vis:
@@ -102,17 +132,15 @@ class RcfHeadFn(torch.autograd.Function):
             vis_struct.aff = vis_tensors[4].data_ptr() if n_out == 5 else None
             desc.vis_bstride, desc.vis_dstride = 2 * ndir * P, 2 * P
             desc.vis_scale[0], desc.vis_scale[1] = spec.vis_scale
-        stream = _lib.raw_stream(dev)
         with _lib.device_guard(dev):
-            _lib.check(lib.rcf_forward(C.byref(desc), C.byref(inp), loss_buf.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
-                                       C.byref(vis_struct) if vis_struct is not None else None, stream), "rcf_forward")
-        ctx.spec, ctx.ndir, ctx.B, ctx.nprod, ctx.stem_slope, ctx.clamp = spec, ndir, B, nprod, stem_slope, clamp
+            _lib.check(lib.rcf_head_forward(C.byref(desc), C.byref(inp), cw1c.data_ptr(), cb1c.data_ptr(), cw2c.data_ptr(), int(ks),
+                                            float(stem_slope), int(nprod), C.byref(hb), loss_buf.data_ptr(), base + offs["ctx"],
+                                            base + offs["ws"], C.byref(vis_struct) if vis_struct is not None else None,
+                                            _lib.raw_stream(dev)), "rcf_head_forward")
+        ctx.spec, ctx.ndir, ctx.B, ctx.nprod, ctx.stem_slope, ctx.ks = spec, ndir, B, nprod, float(stem_slope), int(ks)
         ctx.masks_shape = tuple(masks.shape)
-        ctx.has_lo = a_lo is not None
-        ctx.has_wp = wp_bwd is not None
-        ctx.save_for_backward(masks_v, ctx_buf, feat, a_hi, sign, cw1c, cw2c, cb2c, w1c, b1c, w2c, b2c,
-                              *([a_lo] if a_lo is not None else []), *([wp_bwd] if wp_bwd is not None else []),
-                              *flows_v, *resids_v)
+        ctx.offs = offs
+        ctx.save_for_backward(masks_v, arena, cw1c, cb2c, w1c, b1c, w2c, b2c, *flows_v, *resids_v)
         ctx.mark_non_differentiable(*vis_tensors)
         ctx.set_materialize_grads(False)
         return (loss_buf[:ndir], loss_buf[ndir], *vis_tensors)
@@ -121,18 +149,16 @@ class RcfHeadFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss, grad_total, *grad_vis):
         lib = _lib.load_library()
-        spec, ndir, B, nprod = ctx.spec, ctx.ndir, ctx.B, ctx.nprod
+        spec, ndir, B, nprod, ks = ctx.spec, ctx.ndir, ctx.B, ctx.nprod, ctx.ks
         n_in = 12 + 2 * ndir
         if grad_loss is None and grad_total is None:
             return (None,) * n_in
         K, H, W = spec.K, spec.H, spec.W
         P = H * W
+        nimg = ndir * B
         saved = list(ctx.saved_tensors)
-        masks_v, ctx_buf, feat, a_hi, sign, cw1c, cw2c, cb2c, w1c, b1c, w2c, b2c = saved[:12]
-        rest = saved[12:]
-        a_lo = rest.pop(0) if ctx.has_lo else None
-        wp_bwd = rest.pop(0) if ctx.has_wp else None
-        flows_v, resids_v = rest[:ndir], rest[ndir:2 * ndir]
+        masks_v, arena, cw1c, cb2c, w1c, b1c, w2c, b2c = saved[:8]
+        flows_v, resids_v = saved[8:8 + ndir], saved[8 + ndir:8 + 2 * ndir]
         dev = masks_v.device
         need = ctx.needs_input_grad          # (spec, nprod, slope, masks, cw1, cb1, cw2, cb2, w1, b1, w2, b2, *flows, *resids)
         need_masks = need[3]
@@ -148,38 +174,58 @@ class RcfHeadFn(torch.autograd.Function):
         inp.feat_bias = cb2c.data_ptr()
         d_masks = torch.empty(ctx.masks_shape, dtype=torch.float32, device=dev) if need_masks else None
         d_resids = [None] * ndir
-        g_hi = g_lo = None
-        if need_conv:
-            g_hi = torch.empty((ndir * B, 64, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
-            g_lo = torch.empty_like(g_hi) if nprod >= 2 else None
         for i in range(ndir):
             inp.mask[i] = masks_v.data_ptr() + i * masks_v.stride(1) * 4
             desc.mask_bstride[i] = masks_v.stride(0)
             inp.flow[i] = flows_v[i].data_ptr(); desc.flow_bstride[i] = flows_v[i].stride(0)
             inp.resid[i] = resids_v[i].data_ptr(); desc.resid_bstride[i] = resids_v[i].stride(0)
-            inp.feat[i] = feat.data_ptr() + i * B * P * 64 * 4; desc.feat_bstride[i] = P * 64
+            desc.feat_bstride[i] = P * 64
+            desc.dfeat_bstride[i] = P * 64
             if d_masks is not None:
                 grads.dmask[i] = d_masks.data_ptr() + i * d_masks.stride(1) * 4
                 desc.dmask_bstride[i] = d_masks.stride(0)
             if need_resid[i]:
                 d_resids[i] = torch.empty(B, 2 * K, H, W, dtype=torch.float32, device=dev)
                 grads.dresid[i] = d_resids[i].data_ptr(); desc.dresid_bstride[i] = d_resids[i].stride(0)
-            if g_hi is not None:
-                grads.dfeat_hi[i] = g_hi.data_ptr() + i * B * P * 64 * 2
-                if g_lo is not None:
-                    grads.dfeat_lo[i] = g_lo.data_ptr() + i * B * P * 64 * 2
-                desc.dfeat_bstride[i] = P * 64
-        d_cb2 = None
-        if need_conv:
-            d_cb2 = torch.empty(64, dtype=torch.float32, device=dev)
-            grads.dfeat_bias = d_cb2.data_ptr()
+        d_cw1 = d_cb1 = d_cw2 = d_cb2 = None
         dmlp = [None] * 4
         if need_mlp:
             dmlp = [torch.empty(64, 64, 1, dtype=torch.float32, device=dev), torch.empty(64, dtype=torch.float32, device=dev),
                     torch.empty(2, 64, 1, dtype=torch.float32, device=dev), torch.empty(2, dtype=torch.float32, device=dev)]
             grads.dw1, grads.db1, grads.dw2, grads.db2 = (t.data_ptr() for t in dmlp)
         _, ws_bytes = _sizes(lib, desc, spec, B, ndir)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+        base_f, offs = arena.data_ptr(), ctx.offs
+        hb = _lib.RcfHeadBuffers()
+        hb.a_hi = base_f + offs["a_hi"]
+        hb.a_lo = base_f + offs["a_lo"] if nprod == 3 else None
+        hb.sign = base_f + offs["sign"]
+        hb.wpack = base_f + offs["wpack"]
+        hb.feat = base_f + offs["feat"]
+        # backward arena: [ws | g_hi | g_lo? | d_a1 | wgrad ws | stem ws]
+        parts = [("ws", ws_bytes)]
+        if need_conv:
+            wg_b, st_b = _aux_sizes(lib, dev, ndir, B, H, W, ks)
+            act_b = nimg * P * 64 * 2
+            parts += [("g_hi", act_b), ("g_lo", act_b if nprod >= 2 else 0), ("d_a1", 2 * act_b), ("wgrad_ws", wg_b), ("stem_ws", st_b)]
+        boffs, o = {}, 0
+        for name, nbytes in parts:
+            boffs[name] = o
+            o += _align(nbytes)
+        barena = torch.empty(max(o, 256), dtype=torch.uint8, device=dev)
+        bbase = barena.data_ptr()
+        if need_conv:
+            d_cw1 = torch.empty(tuple(cw1c.shape), dtype=torch.float32, device=dev)
+            d_cb1 = torch.empty(64, dtype=torch.float32, device=dev)
+            d_cw2 = torch.empty(64, 64, 3, 3, dtype=torch.float32, device=dev)
+            d_cb2 = torch.empty(64, dtype=torch.float32, device=dev)
+            grads.dfeat_bias = d_cb2.data_ptr()
+            hb.g_hi = bbase + boffs["g_hi"]
+            hb.g_lo = bbase + boffs["g_lo"] if nprod >= 2 else None
+            hb.d_a1 = bbase + boffs["d_a1"]
+            hb.wgrad_ws = bbase + boffs["wgrad_ws"]
+            hb.stem_ws = bbase + boffs["stem_ws"]
+            hb.d_cw1, hb.d_cb1, hb.d_cw2 = d_cw1.data_ptr(), d_cb1.data_ptr(), d_cw2.data_ptr()
         if grad_loss is None:
             gl = grad_total.detach().to(torch.float32).contiguous()
             desc.grad_loss_total = 1
@@ -188,15 +234,8 @@ class RcfHeadFn(torch.autograd.Function):
             if grad_total is not None:
                 gl = gl + grad_total.detach().to(torch.float32)
             gl = gl.contiguous()
-        stream = _lib.raw_stream(dev)
         with _lib.device_guard(dev):
-            _lib.check(lib.rcf_backward(C.byref(desc), C.byref(inp), gl.data_ptr(), ctx_buf.data_ptr(), ws.data_ptr(),
-                                        C.byref(grads), stream), "rcf_backward")
-        d_cw1 = d_cb1 = d_cw2 = None
-        if need_conv:
-            if wp_bwd is None:
-                wp_bwd = c64.pack_weights(cw2c, True)
-            d_a1 = c64.conv64_pair(g_hi, g_lo if nprod == 3 else None, wp_bwd, nprod)     # data gradient
-            d_cw2 = c64.conv64_wgrad_pair(a_hi, a_lo, g_hi, g_lo, nprod)
-            d_cw1, d_cb1 = stem_backward_raw(flows_v, tuple(cw1c.shape), ctx.clamp, ctx.stem_slope, None, sign, d_a1, nprod=ctx.nprod)
+            _lib.check(lib.rcf_head_backward(C.byref(desc), C.byref(inp), gl.data_ptr(), base_f + offs["ctx"], bbase + boffs["ws"],
+                                             C.byref(grads), int(ks), float(ctx.stem_slope), int(nprod), int(need_conv),
+                                             C.byref(hb), _lib.raw_stream(dev)), "rcf_head_backward")
         return (None, None, None, d_masks, d_cw1, d_cb1, d_cw2, d_cb2, *dmlp, *([None] * ndir), *d_resids)
