@@ -248,13 +248,19 @@ typedef struct RcfHeadBuffers {
     float* d_cw1;          /* [64,2,ks,ks] */
     float* d_cb1;          /* [64]         */
     float* d_cw2;          /* [64,64,3,3]  */
+    /* residual predicted at a lower resolution (allow_residual_resize, reference :271-273, :294-296); resid_h > 0 only */
+    float* resid_up;       /* fp32 [ndir][B,2K,H,W]: the bilinearly up-sampled residuals (forward writes, backward reads) */
+    float* dresid_up;      /* fp32 [ndir][B,2K,H,W]: backward scratch for the full-resolution residual gradient        */
 } RcfHeadBuffers;
+/* resid_h, resid_w > 0: in->resid[i] are dense [B,2K,resid_h,resid_w] tensors that the library up-samples to [H,W]
+ * (align_corners = 0) into hb->resid_up first; the backward then returns grads->dresid[i] at [resid_h,resid_w] too
+ * (dense).  0: residuals are given at [H,W] with desc->resid_bstride as usual. */
 RCF_API int rcf_head_forward(const RcfDesc* desc, const RcfInputs* in, const float* cw1, const float* cb1, const float* cw2,
-                             int ks, float stem_slope, int nprod, const RcfHeadBuffers* hb, float* loss, void* ctx, void* ws,
-                             const RcfVisOut* vis, void* stream);
+                             int ks, float stem_slope, int nprod, int resid_h, int resid_w, const RcfHeadBuffers* hb, float* loss,
+                             void* ctx, void* ws, const RcfVisOut* vis, void* stream);
 /* need_conv_grads = 0: only rcf_backward runs (no gradient reaches the conv parameters). */
 RCF_API int rcf_head_backward(const RcfDesc* desc, const RcfInputs* in, const float* grad_loss, const void* ctx, void* ws,
-                              RcfGrads* grads, int ks, float stem_slope, int nprod, int need_conv_grads,
+                              RcfGrads* grads, int ks, float stem_slope, int nprod, int need_conv_grads, int resid_h, int resid_w,
                               const RcfHeadBuffers* hb, void* stream);
 /* x (n fp32 values, n % 4 == 0) -> hi = bf16(x), lo = bf16(x - hi) (lo may be NULL). */
 RCF_API int rcf_split_bf16(const float* x, void* hi, void* lo, size_t n, void* stream);

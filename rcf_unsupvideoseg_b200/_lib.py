@@ -64,7 +64,7 @@ class RcfGrads(C.Structure):
 
 class RcfHeadBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("a_hi", "a_lo", "sign", "wpack", "feat", "g_hi", "g_lo", "d_a1", "wgrad_ws", "stem_ws",
-                                          "d_cw1", "d_cb1", "d_cw2")]
+                                          "d_cw1", "d_cb1", "d_cw2", "resid_up", "dresid_up")]
 
 
 EXPORTED_SYMBOLS = ("rcf_abi_version", "rcf_error_string", "rcf_query_sizes", "rcf_forward", "rcf_backward",
@@ -166,12 +166,12 @@ def load_library(build_if_missing: bool = True):
                                          C.c_int, C.c_int, C.c_void_p]
         lib.rcf_head_forward.restype = C.c_int
         lib.rcf_head_forward.argtypes = [C.POINTER(RcfDesc), C.POINTER(RcfInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                         C.c_float, C.c_int, C.POINTER(RcfHeadBuffers), C.c_void_p, C.c_void_p, C.c_void_p,
-                                         C.c_void_p, C.c_void_p]
+                                         C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(RcfHeadBuffers), C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rcf_head_backward.restype = C.c_int
         lib.rcf_head_backward.argtypes = [C.POINTER(RcfDesc), C.POINTER(RcfInputs), C.c_void_p, C.c_void_p, C.c_void_p,
-                                          C.POINTER(RcfGrads), C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(RcfHeadBuffers),
-                                          C.c_void_p]
+                                          C.POINTER(RcfGrads), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(RcfHeadBuffers), C.c_void_p]
         lib.rcf_split_bf16.restype = C.c_int
         lib.rcf_split_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         lib.rcf_debug_conv64_trace.restype = C.c_int

@@ -23,8 +23,8 @@ int check_head(const RcfDesc* d, const RcfInputs* in, const RcfHeadBuffers* hb) 
 }  // namespace
 
 extern "C" int rcf_head_forward(const RcfDesc* desc, const RcfInputs* in, const float* cw1, const float* cb1, const float* cw2,
-                                int ks, float stem_slope, int nprod, const RcfHeadBuffers* hb, float* loss, void* ctx, void* ws,
-                                const RcfVisOut* vis, void* stream) {
+                                int ks, float stem_slope, int nprod, int resid_h, int resid_w, const RcfHeadBuffers* hb, float* loss,
+                                void* ctx, void* ws, const RcfVisOut* vis, void* stream) {
     int rc = check_head(desc, in, hb);
     if (rc != RCF_OK) return rc;
     if (!cw1 || !cb1 || !cw2 || !hb->a_hi || !hb->sign || !hb->wpack || !hb->feat) return RCF_ERR_NULL;
@@ -38,12 +38,25 @@ extern "C" int rcf_head_forward(const RcfDesc* desc, const RcfInputs* in, const 
     rc = rcf_conv64_forward(hb->a_hi, nprod == 3 ? hb->a_lo : nullptr, hb->wpack, hb->feat, ndir * B, H, W, nprod, stream);
     if (rc != RCF_OK) return rc;
     RcfInputs in2 = *in;
+    RcfDesc d2 = *desc;
     for (int i = 0; i < ndir; ++i) in2.feat[i] = hb->feat + (long long)i * B * img;
-    return rcf_forward(desc, &in2, loss, ctx, ws, vis, stream);
+    if (resid_h > 0 && resid_w > 0) {                      // reference :271-273, :294-296 (both directions in one launch)
+        if (!hb->resid_up) return RCF_ERR_NULL;
+        const long long per = (long long)B * 2 * desc->K * H * W;
+        const float* rin[2] = {in->resid[0], ndir > 1 ? in->resid[1] : nullptr};
+        float* rout[2] = {hb->resid_up, ndir > 1 ? hb->resid_up + per : nullptr};
+        rc = rcf_resize_bilinear_forward(rin, rout, ndir, B * 2 * desc->K, resid_h, resid_w, H, W, 0, stream);
+        if (rc != RCF_OK) return rc;
+        for (int i = 0; i < ndir; ++i) {
+            in2.resid[i] = rout[i];
+            d2.resid_bstride[i] = (long long)2 * desc->K * H * W;
+        }
+    }
+    return rcf_forward(&d2, &in2, loss, ctx, ws, vis, stream);
 }
 
 extern "C" int rcf_head_backward(const RcfDesc* desc, const RcfInputs* in, const float* grad_loss, const void* ctx, void* ws,
-                                 RcfGrads* grads, int ks, float stem_slope, int nprod, int need_conv_grads,
+                                 RcfGrads* grads, int ks, float stem_slope, int nprod, int need_conv_grads, int resid_h, int resid_w,
                                  const RcfHeadBuffers* hb, void* stream) {
     int rc = check_head(desc, in, hb);
     if (rc != RCF_OK) return rc;
@@ -63,8 +76,35 @@ extern "C" int rcf_head_backward(const RcfDesc* desc, const RcfInputs* in, const
         }
     }
     if (!need_conv_grads) g2.dfeat_bias = nullptr;
-    rc = rcf_backward(desc, &in2, grad_loss, ctx, ws, &g2, stream);
-    if (rc != RCF_OK || !need_conv_grads) return rc;
+    RcfDesc d2 = *desc;
+    const bool lowres = resid_h > 0 && resid_w > 0;
+    const long long per = (long long)B * 2 * desc->K * H * W;
+    if (lowres) {
+        if (!hb->resid_up) return RCF_ERR_NULL;
+        for (int i = 0; i < ndir; ++i) {
+            in2.resid[i] = hb->resid_up + (long long)i * per;
+            d2.resid_bstride[i] = (long long)2 * desc->K * H * W;
+            if (grads->dresid[i]) {
+                if (!hb->dresid_up) return RCF_ERR_NULL;
+                g2.dresid[i] = hb->dresid_up + (long long)i * per;
+                d2.dresid_bstride[i] = (long long)2 * desc->K * H * W;
+            }
+        }
+    }
+    rc = rcf_backward(&d2, &in2, grad_loss, ctx, ws, &g2, stream);
+    if (rc != RCF_OK) return rc;
+    if (lowres) {                                          // gradient of the up-sampling: a deterministic gather
+        const float* gout[2] = {nullptr, nullptr};
+        float* gin[2] = {nullptr, nullptr};
+        int n = 0;
+        for (int i = 0; i < ndir; ++i)
+            if (grads->dresid[i]) { gout[n] = g2.dresid[i]; gin[n] = grads->dresid[i]; ++n; }
+        if (n > 0) {
+            rc = rcf_resize_bilinear_backward(gout, gin, n, B * 2 * desc->K, resid_h, resid_w, H, W, 0, stream);
+            if (rc != RCF_OK) return rc;
+        }
+    }
+    if (!need_conv_grads) return RCF_OK;
     if (!hb->a_hi || !hb->sign || !hb->wpack || !hb->d_a1 || !hb->wgrad_ws || !hb->stem_ws || !hb->d_cw1 || !hb->d_cb1 || !hb->d_cw2)
         return RCF_ERR_NULL;
     const void* wp_bwd = static_cast<const uint8_t*>(hb->wpack) + RCF_CONV64_WPACK_BYTES;

@@ -89,7 +89,14 @@ class RcfHeadFn(torch.autograd.Function):
         nimg = ndir * B
         masks_v = masks if (masks.dtype == torch.float32 and _inner_dense(masks, 3)) else masks.float().contiguous()
         flows_v = _views(flows)
-        resids_v = [_as_dir_view(r) for r in resids]
+        # residuals predicted at a lower resolution (all directions alike): the library up-samples them itself
+        rh, rw = resids[0].shape[-2:]
+        lowres = (rh, rw) != (H, W)
+        if lowres:
+            assert all(tuple(r.shape) == (B, 2 * K, rh, rw) for r in resids)
+            resids_v = [r.detach().float().contiguous() for r in resids]
+        else:
+            resids_v = [_as_dir_view(r) for r in resids]
         cw1c, cb1c, cw2c, cb2c, w1c, b1c, w2c, b2c = (t.detach().float().contiguous() for t in (cw1, cb1, cw2, cb2, w1, b1, w2, b2))
         ks = cw1c.shape[-1]
 
@@ -100,17 +107,19 @@ class RcfHeadFn(torch.autograd.Function):
             inp.mask[i] = masks_v.data_ptr() + i * masks_v.stride(1) * 4
             desc.mask_bstride[i] = masks_v.stride(0)
             inp.flow[i] = flows_v[i].data_ptr(); desc.flow_bstride[i] = flows_v[i].stride(0)
-            inp.resid[i] = resids_v[i].data_ptr(); desc.resid_bstride[i] = resids_v[i].stride(0)
+            inp.resid[i] = resids_v[i].data_ptr()
+            desc.resid_bstride[i] = 2 * K * P if lowres else resids_v[i].stride(0)
             desc.feat_bstride[i] = P * 64
         inp.w1, inp.b1, inp.w2, inp.b2 = (t.data_ptr() for t in (w1c, b1c, w2c, b2c))
         inp.feat_bias = cb2c.data_ptr()
         ctx_bytes, ws_bytes = _sizes(lib, desc, spec, B, ndir)
 
-        # arena: [a_hi | a_lo? | sign | wpack x2 | feat | ctx | ws]
+        # arena: [a_hi | a_lo? | sign | wpack x2 | feat | ctx | ws | up-sampled residuals?]
         act_b = nimg * P * 64 * 2
         offs, o = {}, 0
         for name, nbytes in (("a_hi", act_b), ("a_lo", act_b if nprod == 3 else 0), ("sign", nimg * P * 8),
-                             ("wpack", 2 * c64.WPACK_BYTES), ("feat", nimg * P * 64 * 4), ("ctx", ctx_bytes), ("ws", ws_bytes)):
+                             ("wpack", 2 * c64.WPACK_BYTES), ("feat", nimg * P * 64 * 4), ("ctx", ctx_bytes), ("ws", ws_bytes),
+                             ("resid_up", nimg * 2 * K * P * 4 if lowres else 0)):
             offs[name] = o
             o += _align(nbytes)
         arena = torch.empty(o, dtype=torch.uint8, device=dev)
@@ -121,6 +130,7 @@ class RcfHeadFn(torch.autograd.Function):
         hb.sign = base + offs["sign"]
         hb.wpack = base + offs["wpack"]
         hb.feat = base + offs["feat"]
+        hb.resid_up = base + offs["resid_up"] if lowres else None
 
         loss_buf = torch.empty(ndir + 1, dtype=torch.float32, device=dev)
         vis_tensors, vis_struct = (), None
@@ -134,13 +144,15 @@ class RcfHeadFn(torch.autograd.Function):
             desc.vis_scale[0], desc.vis_scale[1] = spec.vis_scale
         with _lib.device_guard(dev):
             _lib.check(lib.rcf_head_forward(C.byref(desc), C.byref(inp), cw1c.data_ptr(), cb1c.data_ptr(), cw2c.data_ptr(), int(ks),
-                                            float(stem_slope), int(nprod), C.byref(hb), loss_buf.data_ptr(), base + offs["ctx"],
+                                            float(stem_slope), int(nprod), int(rh) if lowres else 0, int(rw) if lowres else 0,
+                                            C.byref(hb), loss_buf.data_ptr(), base + offs["ctx"],
                                             base + offs["ws"], C.byref(vis_struct) if vis_struct is not None else None,
                                             _lib.raw_stream(dev)), "rcf_head_forward")
         ctx.spec, ctx.ndir, ctx.B, ctx.nprod, ctx.stem_slope, ctx.ks = spec, ndir, B, nprod, float(stem_slope), int(ks)
         ctx.masks_shape = tuple(masks.shape)
         ctx.offs = offs
-        ctx.save_for_backward(masks_v, arena, cw1c, cb2c, w1c, b1c, w2c, b2c, *flows_v, *resids_v)
+        ctx.resid_hw = (int(rh), int(rw)) if lowres else None
+        ctx.save_for_backward(masks_v, arena, cw1c, cb2c, w1c, b1c, w2c, b2c, *flows_v, *([] if lowres else resids_v))
         ctx.mark_non_differentiable(*vis_tensors)
         ctx.set_materialize_grads(False)
         return (loss_buf[:ndir], loss_buf[ndir], *vis_tensors)
@@ -158,7 +170,8 @@ class RcfHeadFn(torch.autograd.Function):
         nimg = ndir * B
         saved = list(ctx.saved_tensors)
         masks_v, arena, cw1c, cb2c, w1c, b1c, w2c, b2c = saved[:8]
-        flows_v, resids_v = saved[8:8 + ndir], saved[8 + ndir:8 + 2 * ndir]
+        lowres = ctx.resid_hw is not None
+        flows_v, resids_v = saved[8:8 + ndir], (None if lowres else saved[8 + ndir:8 + 2 * ndir])
         dev = masks_v.device
         need = ctx.needs_input_grad          # (spec, nprod, slope, masks, cw1, cb1, cw2, cb2, w1, b1, w2, b2, *flows, *resids)
         need_masks = need[3]
@@ -178,14 +191,16 @@ class RcfHeadFn(torch.autograd.Function):
             inp.mask[i] = masks_v.data_ptr() + i * masks_v.stride(1) * 4
             desc.mask_bstride[i] = masks_v.stride(0)
             inp.flow[i] = flows_v[i].data_ptr(); desc.flow_bstride[i] = flows_v[i].stride(0)
-            inp.resid[i] = resids_v[i].data_ptr(); desc.resid_bstride[i] = resids_v[i].stride(0)
+            if not lowres:
+                inp.resid[i] = resids_v[i].data_ptr(); desc.resid_bstride[i] = resids_v[i].stride(0)
             desc.feat_bstride[i] = P * 64
             desc.dfeat_bstride[i] = P * 64
             if d_masks is not None:
                 grads.dmask[i] = d_masks.data_ptr() + i * d_masks.stride(1) * 4
                 desc.dmask_bstride[i] = d_masks.stride(0)
             if need_resid[i]:
-                d_resids[i] = torch.empty(B, 2 * K, H, W, dtype=torch.float32, device=dev)
+                rshape = (B, 2 * K, *ctx.resid_hw) if lowres else (B, 2 * K, H, W)
+                d_resids[i] = torch.empty(rshape, dtype=torch.float32, device=dev)
                 grads.dresid[i] = d_resids[i].data_ptr(); desc.dresid_bstride[i] = d_resids[i].stride(0)
         d_cw1 = d_cb1 = d_cw2 = d_cb2 = None
         dmlp = [None] * 4
@@ -202,8 +217,11 @@ class RcfHeadFn(torch.autograd.Function):
         hb.sign = base_f + offs["sign"]
         hb.wpack = base_f + offs["wpack"]
         hb.feat = base_f + offs["feat"]
-        # backward arena: [ws | g_hi | g_lo? | d_a1 | wgrad ws | stem ws]
+        hb.resid_up = base_f + offs["resid_up"] if lowres else None
+        # backward arena: [ws | full-resolution dR? | g_hi | g_lo? | d_a1 | wgrad ws | stem ws]
         parts = [("ws", ws_bytes)]
+        if lowres and any(need_resid):
+            parts.append(("dresid_up", nimg * 2 * K * P * 4))
         if need_conv:
             wg_b, st_b = _aux_sizes(lib, dev, ndir, B, H, W, ks)
             act_b = nimg * P * 64 * 2
@@ -214,6 +232,8 @@ class RcfHeadFn(torch.autograd.Function):
             o += _align(nbytes)
         barena = torch.empty(max(o, 256), dtype=torch.uint8, device=dev)
         bbase = barena.data_ptr()
+        if "dresid_up" in boffs:
+            hb.dresid_up = bbase + boffs["dresid_up"]
         if need_conv:
             d_cw1 = torch.empty(tuple(cw1c.shape), dtype=torch.float32, device=dev)
             d_cb1 = torch.empty(64, dtype=torch.float32, device=dev)
@@ -237,5 +257,6 @@ class RcfHeadFn(torch.autograd.Function):
         with _lib.device_guard(dev):
             _lib.check(lib.rcf_head_backward(C.byref(desc), C.byref(inp), gl.data_ptr(), base_f + offs["ctx"], bbase + boffs["ws"],
                                              C.byref(grads), int(ks), float(ctx.stem_slope), int(nprod), int(need_conv),
+                                             ctx.resid_hw[0] if lowres else 0, ctx.resid_hw[1] if lowres else 0,
                                              C.byref(hb), _lib.raw_stream(dev)), "rcf_head_backward")
         return (None, None, None, d_masks, d_cw1, d_cb1, d_cw2, d_cb2, *dmlp, *([None] * ndir), *d_resids)

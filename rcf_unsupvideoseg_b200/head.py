@@ -287,9 +287,13 @@ class FlowAggregationHeadWithResidual(nn.Module):
         in_autocast = torch.is_autocast_enabled()
         if self._tc_head_supported():
             with torch.autocast(device_type="cuda", enabled=False):
-                resids = self._resize_residuals([r.float() for r in resids])
-                for r in resids:
-                    assert r.shape[-2:] == (H, W), f"residual spatial size {tuple(r.shape[-2:])} != mask size {(H, W)}"
+                resids = [r.float() for r in resids]
+                same_lowres = (self.allow_residual_resize and tuple(resids[0].shape[-2:]) != (H, W)
+                               and all(r.shape == resids[0].shape for r in resids))
+                if not same_lowres:          # (all directions at one lower resolution: up-sampled inside the library call)
+                    resids = self._resize_residuals(resids)
+                    for r in resids:
+                        assert r.shape[-2:] == (H, W), f"residual spatial size {tuple(r.shape[-2:])} != mask size {(H, W)}"
                 spec = self._spec(K, H, W, want_vis=want_vis, vis_norm=vis_norm, inv_n=inv_n, clamp_fused=True)
                 nprod = self.conv_precision if self.conv_precision is not None else default_nprod(in_autocast)
                 seq = self.flow_feat_before_agg
