@@ -2,14 +2,15 @@
 flow_feat_after_agg and the relaxed-common-fate loss (reference models/flow_aggregation_head_with_residual.py:84-101,
 :235-310, :359-368) -- as ONE autograd node over the C ABI, with no ATen / cuDNN kernel on the path:
 
-  forward   rcf_stem_forward_bf16 (mma.sync 3xTF32)  ->  A1 as a bf16 (hi, lo) pair + sign bits
-            rcf_conv64_forward   (TMA + tcgen05.mma)  ->  pre-activation feature map, fp32 channels-last
-            rcf_forward                               ->  pooling (+ bias, LeakyReLU), segment MLP, loss
-  backward  rcf_backward                              ->  dM, dR, MLP gradients, conv-2 bias gradient, dfeat as a bf16 pair
-            rcf_conv64_forward (transposed weights)   ->  dA1
-            rcf_conv64_wgrad   (tcgen05, K = pixels)  ->  dW2
-            rcf_stem_backward                         ->  dW1, db1
+  forward   rcf_head_forward  = [residual up-sampling when predicted at a lower resolution]
+                                 stem (mma.sync TF32; 3xTF32 in the fp32-grade mode) -> A1 as a bf16 (hi, lo) pair + sign bits
+                                 weight pack (both orientations) -> tcgen05 conv -> pre-activation feature map (fp32 channels-last)
+                                 rcf_forward: pooling (+ bias, LeakyReLU), segment MLP, loss
+  backward  rcf_head_backward = rcf_backward: dM, dR, MLP gradients, conv-2 bias gradient, dfeat as a bf16 pair
+                                 [gradient of the up-sampling] -> tcgen05 data gradient -> dA1
+                                 tcgen05 weight gradient (K = pixels) -> dW2;  stem backward -> dW1, db1
 
+One ctypes crossing and one device arena each way (the 96x96 / 48x48 training shapes are host-bound).
 The intermediate activations never pass through autograd, so they can travel in the operand format of the tensor-core
 kernels (two bf16 tensors, x ~ hi + lo) instead of fp32.  Used by FlowAggregationHeadWithResidual when the head has its
 default shape (64 channels, 3x3 kernels); other shapes take the general path in head.py / function.py.
