@@ -78,6 +78,7 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.l2_hints = g_l2_hints;   // pass 2 streams flow/residual evict-first so the masks of pass 1 survive in L2
     a.nchunk1 = L.nchunk1; a.nchunk2 = L.nchunk2; a.nchunkb = L.nchunkb; a.nchunkp = L.nchunkp;
     a.chunk2 = L.chunk2;
+    a.pool_sums = L.pool_sums;
 }
 
 int validate_inputs(const RcfDesc& d, const RcfInputs& in) {
@@ -194,7 +195,7 @@ extern "C" int rcf_forward(const RcfDesc* desc, const RcfInputs* in, float* loss
         // coefficient pack is just theta, which k_loss / k_bwd read directly (no k_segment_fwd launch either)
         { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_loss(a, vec, s)); }
     } else {
-        { ScopedTime t(RCF_TIME_MOMENTS, s); RCF_CUDA(rcf_launch_moments(a, vec, s)); }
+        if (!a.pool_sums) { ScopedTime t(RCF_TIME_MOMENTS, s); RCF_CUDA(rcf_launch_moments(a, vec, s)); }
         if (desc->theta_mode == 1) { ScopedTime t(RCF_TIME_POOL, s); RCF_CUDA(rcf_launch_pool(a, vec_ok_inputs(*desc, *in, true), s)); }
         RCF_CUDA(rcf_launch_segment_fwd(a, s));
         { ScopedTime t(RCF_TIME_LOSS, s); RCF_CUDA(rcf_launch_loss(a, vec, s)); }

@@ -66,6 +66,7 @@ struct RcfLayout {
     int nfd, P, ns, gm, cf, cb, segd;
     int nchunk1, nchunk2, nchunkb, nchunkp;
     int chunk2;   // pixels per CTA of pass 2
+    int pool_sums;   // S_k partials come from k_pool_nhwc (nchunk1 == nchunkp), no k_moments launch
     // ctx (bytes offsets)
     size_t c_segd, c_coef, c_mlp, c_gm, c_bytes;
     // ws
@@ -86,11 +87,16 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.cb = rcf_cb(d.D);
     L.segd = rcf_segd(d.D);
     L.nchunk1 = (L.P + rcf_chunk_mom(d.D, d.K) - 1) / rcf_chunk_mom(d.D, d.K);
+    // Drop-in head without the affine fit: pass 1 would only produce S_k = sum of the masks, and the channels-last pooling
+    // kernel has every mask tile in shared memory anyway -- it writes the per-chunk mask sums itself (its own chunking),
+    // k_moments is not launched.
+    L.pool_sums = (d.theta_mode == 1 && d.D == 0 && d.feat_nhwc && d.Cf > 0) ? 1 : 0;
     L.chunk2 = rcf_chunk_loss(d.D, d.K, L.P, L.nfd);
     L.nchunk2 = (L.P + L.chunk2 - 1) / L.chunk2;
     L.nchunkb = (L.P + RCF_CHUNK_BWD - 1) / RCF_CHUNK_BWD;
     const int pc = rcf_pool_chunk(d.K, d.feat_nhwc, L.P, L.nfd);
     L.nchunkp = (L.P + pc - 1) / pc;
+    if (L.pool_sums) L.nchunk1 = L.nchunkp;
     const size_t nseg = (size_t)L.nfd * d.K;
     size_t o = 0;
     L.c_segd = o; o = rcf_align256(o + nseg * L.segd * sizeof(double));
@@ -154,6 +160,7 @@ struct RcfK {
     double* thbar;
     int nchunk1, nchunk2, nchunkb, nchunkp;
     int chunk2;    // pixels per CTA of pass 2 (a multiple of RCF_CHUNK_LOSS)
+    int pool_sums; // k_pool_nhwc also writes the mask-sum partials of pass 1 (see rcf_make_layout)
     int l2_hints;  // pass 2 streams flow/residual with an L2 evict-first policy (keeps the masks resident)
     int pdl;          // launch with programmatic stream serialization (kernels call rcf_pdl_prologue() first)
     int mlp_smem;     // segment kernels stage the MLP weights in shared memory (Cf % 4 == 0 and Cf <= 128)

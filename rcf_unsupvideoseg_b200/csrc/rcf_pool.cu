@@ -207,6 +207,15 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
         msT[p * K + k] = (p0 + p < P) ? __ldg(mask + (long long)k * P + p0 + p) : 0.0f;
     }
     __syncthreads();
+    if (a.pool_sums && (tid >> 5) < K) {          // S_k partial of this chunk (reference :242-243): warp k sums column k
+        const int k = tid >> 5, lane = tid & 31;
+        float v0 = 0.0f, v1 = 0.0f;
+        int p = lane;
+        for (; p + 32 < CHUNK; p += 64) { v0 += msT[p * K + k]; v1 += msT[(p + 32) * K + k]; }
+        for (; p < CHUNK; p += 32) v0 += msT[p * K + k];
+        const float v = warp_sum(v0 + v1);
+        if (lane == 0) a.part1[((size_t)fd * K + k) * a.nchunk1 + chunk] = v;
+    }
 
     float acc[4][K];
 #pragma unroll
