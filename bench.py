@@ -498,9 +498,9 @@ def run_ours(args):
                     "conv_precision": "follows torch.backends.cudnn.allow_tf32 (torch default True -> 2 bf16 products, "
                                       "weights hi+lo; False -> 3 products, fp32-grade)"},
             # value region: k_loss, k_finalize, k_loss_sum | k_segment_bwd, k_bwd per step (single-pass forward), NBLOCKS blocks;
-            # e2e region: the library's 20 kernels of the default head per step (profiles/r02_timelines_final.md lists 21
-            # launches per step: these 20 + autograd's one-element fill of the upstream gradient)
-            "gpu_launches": 5 * args.steps * NBLOCKS + 20 * e2e_steps,
+            # e2e region: the library's 19 kernels of the default head per step (profiles/r02_timelines_final.md lists 21: one more,
+            # k_bias_grad_final, was folded into k_bias_grad_fd afterwards) + autograd's one-element fill of the upstream gradient)
+            "gpu_launches": 5 * args.steps * NBLOCKS + 19 * e2e_steps,
             "roofline": {"bound": "hbm", "kernel": "k_bwd<K=4,D=0,PX=4> (streaming backward)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": read_traffic("k_bwd<4, 0, 4>"),
                          "peak_source": peak_src, "kernel_ms": kb_mean, "kernel_ms_min": kb_ms[0],

@@ -72,6 +72,7 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.dbpart = reinterpret_cast<float*>(w + L.w_dbpart);
     a.dbfd = reinterpret_cast<double*>(w + L.w_dbfd);
     a.poolsum = reinterpret_cast<double*>(w + L.w_poolsum);
+    a.cnt = reinterpret_cast<unsigned int*>(w + L.w_cnt);
     a.nblkpb = L.nblkpb; a.poolchunk = L.poolchunk; a.pooltp = L.pooltp;
     a.mlp_smem = (d.theta_mode == 1 && d.Cf % 4 == 0 && d.Cf <= 128 && aligned16(in.w1)) ? 1 : 0;
     a.pdl = g_pdl;

@@ -70,7 +70,7 @@ struct RcfLayout {
     // ctx (bytes offsets)
     size_t c_segd, c_coef, c_mlp, c_gm, c_bytes;
     // ws
-    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_dbpart, w_dbfd, w_poolsum, w_bytes;
+    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_dbpart, w_dbfd, w_poolsum, w_cnt, w_bytes;
     int nblkpb;   // CTAs per frame-direction of the channels-last pooling backward (pooltp pixels each)
     int poolchunk, pooltp;
 };
@@ -119,6 +119,7 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.w_dbpart = o;  o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * L.nblkpb * d.Cf * sizeof(float) : 0));   // per-CTA bias-gradient partials
     L.w_dbfd = o;    o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * 16 * d.Cf * sizeof(double) : 0));   // <= 16 splits per fd
     L.w_poolsum = o; o = rcf_align256(o + nseg * d.Cf * sizeof(double));
+    L.w_cnt = o;     o = rcf_align256(o + 64);      // arrival counters of the "last CTA finishes the reduction" kernels
     L.w_bytes = o ? o : 256;
     return L;
 }
@@ -181,6 +182,8 @@ struct RcfK {
     float* dbpart;            // ws: [nfd][nblkpb][Cf]
     double* dbfd;             // ws: [nfd * S][Cf], S <= 16 splits of the partial rows
     double* poolsum;          // ws: [nfd][Cf*K] pooled sums (un-normalised), reduced over chunks by k_pool_reduce
+    unsigned int* cnt;        // ws: arrival counters -- [1] k_bias_grad_fd (zeroed by k_pool_bwd_nhwc); [0] unused (folding k_loss_sum into
+                              // k_finalize the same way was measured: +0.7 us on the C2 loss-core step, so that pair stays two launches)
     int nblkpb;
     int poolchunk, pooltp;    // pixels per CTA of k_pool_nhwc / k_pool_bwd_nhwc
 };
@@ -196,6 +199,22 @@ struct RcfK {
 __device__ __forceinline__ void rcf_pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+// "The last CTA to arrive finishes the job": every CTA publishes its partial results, then one thread takes a ticket; the
+// CTA that draws the last ticket sees all partials (fence + atomic) and runs the final, fixed-order reduction itself, so
+// the separate single-CTA launch that used to follow disappears.  The counter is zeroed by the PRECEDING kernel of the
+// same stream (a plain store by one thread), so graph replays and back-to-back calls need no memset.  Returns true in
+// every thread of the last CTA.  Partials written by other CTAs must then be read with __ldcg (L1 is not coherent).
+__device__ __forceinline__ bool rcf_last_cta(unsigned int* counter, unsigned int total) {
+    __shared__ int s_last;
+    __syncthreads();                                   // this CTA's partials are written
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(counter, 1u) == total - 1u) ? 1 : 0;
+        __threadfence();
+    }
+    __syncthreads();
+    return s_last != 0;
 }
 template <typename... KArgs, typename... Args>
 static inline cudaError_t rcf_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int pdl,

@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_pool_nhwc(const RcfK a) {
 template <int K>
 __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
     rcf_pdl_prologue();
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.cnt[1] = 0u;      // arrival counter of k_bias_grad_fd (next launch)
     const int TP = a.pooltp;                 // pixels per CTA
     extern __shared__ float sm[];
     float* msT = sm;                         // [TP][K]
@@ -508,14 +509,11 @@ __global__ void __launch_bounds__(256) k_bias_grad_fd(const RcfK a) {
         for (int q = 0; q < R; ++q) v += red[q * Cf + f];
         a.dbfd[((size_t)fd * S + s) * Cf + f] = v;
     }
-}
-// Level 2, one CTA: sum the nfd * S rows of level 1 (<= ~128 rows) the same way.
-__global__ void __launch_bounds__(256) k_bias_grad_final(const RcfK a, int nrows) {
-    rcf_pdl_prologue();
-    __shared__ double red[256];
-    const int Cf = a.Cf, R = 256 / Cf, f = threadIdx.x % Cf, r = threadIdx.x / Cf;
+    // Level 2 by the last CTA to arrive (counter zeroed by k_pool_bwd_nhwc): sum the nfd * S rows of level 1 the same way.
+    if (!rcf_last_cta(a.cnt + 1, gridDim.x * gridDim.y)) return;
+    const int nrows = gridDim.x * gridDim.y;
     double v = 0.0;
-    for (int row = r; row < nrows; row += R) v += a.dbfd[(size_t)row * Cf + f];
+    for (int row = r; row < nrows; row += R) v += __ldcg(a.dbfd + (size_t)row * Cf + f);
     red[threadIdx.x] = v;
     __syncthreads();
     if (r == 0 && threadIdx.x < Cf) {
@@ -559,10 +557,7 @@ static cudaError_t launch_pool_bwd_nhwc_k(const RcfK& a, bool, cudaStream_t s) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !a.dfeat_bias) return e;
     int S = (64 + a.nfd - 1) / a.nfd; S = S < 1 ? 1 : (S > 16 ? 16 : S);
-    rcf_launch(k_bias_grad_fd, dim3(S, a.nfd), 256, 0, s, a.pdl, a);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    rcf_launch(k_bias_grad_final, 1, 256, 0, s, a.pdl, a, S * a.nfd);
+    rcf_launch(k_bias_grad_fd, dim3(S, a.nfd), 256, 0, s, a.pdl, a);      // its last CTA also does the second level
     return cudaGetLastError();
 }
 
