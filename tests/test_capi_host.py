@@ -58,6 +58,7 @@ int main(void) {
   F(RcfDesc,vis_bstride); F(RcfDesc,vis_dstride); F(RcfDesc,vis_scale); F(RcfDesc,feat_lrelu_slope); F(RcfDesc,feat_nhwc);
   F(RcfInputs,mask); F(RcfInputs,flow); F(RcfInputs,resid); F(RcfInputs,feat); F(RcfInputs,theta); F(RcfInputs,w1); F(RcfInputs,b1); F(RcfInputs,w2); F(RcfInputs,b2); F(RcfInputs,feat_bias);
   F(RcfVisOut,gt); F(RcfVisOut,pred); F(RcfVisOut,agg); F(RcfVisOut,res); F(RcfVisOut,aff);
+  printf("RcfHeadBuffers %zu\n", sizeof(RcfHeadBuffers)); F(RcfHeadBuffers,a_hi); F(RcfHeadBuffers,feat); F(RcfHeadBuffers,g_hi); F(RcfHeadBuffers,d_cw2); F(RcfHeadBuffers,resid_up); F(RcfHeadBuffers,dresid_up);
   F(RcfGrads,dmask); F(RcfGrads,dresid); F(RcfGrads,dfeat); F(RcfGrads,dtheta); F(RcfGrads,dw1); F(RcfGrads,db1); F(RcfGrads,dw2); F(RcfGrads,db2); F(RcfGrads,dfeat_bias); F(RcfGrads,dfeat_hi); F(RcfGrads,dfeat_lo);
   return 0; }
 '''
@@ -68,7 +69,7 @@ int main(void) {
         subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
         out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
     structs = {"RcfDesc": _lib.RcfDesc, "RcfInputs": _lib.RcfInputs, "RcfVisOut": _lib.RcfVisOut, "RcfGrads": _lib.RcfGrads,
-               "RcfMaskCfg": _lib.RcfMaskCfg}
+               "RcfMaskCfg": _lib.RcfMaskCfg, "RcfHeadBuffers": _lib.RcfHeadBuffers}
     for line in out.splitlines():
         name, val = line.split()
         if "." in name:
@@ -98,6 +99,23 @@ def test_query_sizes_and_validation(lib):
     assert lib.rcf_forward(C.byref(d), C.byref(inp), None, None, None, None, None) == -1
     assert lib.rcf_backward(C.byref(d), C.byref(inp), None, None, None, None, None) == -1
     assert lib.rcf_abi_version() == _lib.RCF_ABI_VERSION
+
+
+def test_head_entry_points_validate_before_any_launch(lib):
+    """rcf_head_forward / rcf_head_backward (the default head as one call each way) reject NULL / wrong-mode arguments with
+    status codes on the host, without touching a device."""
+    from rcf_unsupvideoseg_b200 import _lib
+    d = _lib.RcfDesc()
+    d.B, d.K, d.H, d.W, d.Cf, d.D, d.ndir, d.theta_mode, d.feat_nhwc = 2, 4, 24, 32, 64, 0, 2, 1, 1
+    inp, hb, g = _lib.RcfInputs(), _lib.RcfHeadBuffers(), _lib.RcfGrads()
+    assert lib.rcf_head_forward(None, C.byref(inp), None, None, None, 3, 0.1, 2, 0, 0, C.byref(hb), None, None, None, None, None) == -1
+    assert lib.rcf_head_forward(C.byref(d), C.byref(inp), None, None, None, 3, 0.1, 2, 0, 0, C.byref(hb), None, None, None, None, None) == -2   # RCF_ERR_SHAPE: feat_bstride != H*W*64
+    d.feat_bstride[0] = d.feat_bstride[1] = 24 * 32 * 64
+    assert lib.rcf_head_forward(C.byref(d), C.byref(inp), None, None, None, 3, 0.1, 2, 0, 0, C.byref(hb), None, None, None, None, None) == -1   # NULL weights / buffers
+    d.Cf = 32
+    assert lib.rcf_head_forward(C.byref(d), C.byref(inp), None, None, None, 3, 0.1, 2, 0, 0, C.byref(hb), None, None, None, None, None) == -5   # not the default head
+    d.Cf = 64
+    assert lib.rcf_head_backward(C.byref(d), C.byref(inp), None, None, None, None, 3, 0.1, 2, 1, 0, 0, C.byref(hb), None) == -1
 
 
 def test_no_oracle_import_in_product():
