@@ -1,4 +1,4 @@
-// rcf_loss_dev.cuh -- pass-2 tile body (shared by k_loss and the fused forward kernel).
+// rcf_loss_dev.cuh -- pass-2 tile body of k_loss.
 #pragma once
 #include "rcf_common.cuh"
 

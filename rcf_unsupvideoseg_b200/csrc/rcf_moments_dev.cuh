@@ -1,4 +1,4 @@
-// rcf_moments_dev.cuh -- pass-1 tile body (shared by k_moments and the fused forward kernel).
+// rcf_moments_dev.cuh -- pass-1 tile body of k_moments.
 #pragma once
 #include <type_traits>
 #include "rcf_common.cuh"
@@ -120,7 +120,7 @@ __device__ __forceinline__ void moments_tile(const RcfK& a, int fd, int chunk, f
         } else
         if constexpr (D == 0) {
             // mask sums only: issue every load of the tile (ITER*K 128-bit loads per thread) before the first add,
-            // so the tile runs at full memory-level parallelism even at 2 CTAs/SM inside the fused forward kernel
+            // so the tile runs at full memory-level parallelism
             float mm[ITER][KG][PX];
 #pragma unroll
             for (int it = 0; it < ITER; ++it) {

@@ -1,4 +1,4 @@
-// rcf_segment_dev.cuh -- per-segment device routines shared by rcf_segment.cu and the fused forward kernel.
+// rcf_segment_dev.cuh -- per-segment device routines of rcf_segment.cu.
 #pragma once
 #include "rcf_common.cuh"
 

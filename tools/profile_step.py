@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--time", action="store_true", help="print CUDA-event time per step and per kernel")
     ap.add_argument("--graph", action="store_true", help="also time the step replayed from a CUDA graph")
-    ap.add_argument("--opt", type=str, default="", help="comma list of option=value for rcf_debug_set_option, e.g. 1=0,2=6")
+    ap.add_argument("--opt", type=str, default="", help="comma list of option=value for rcf_debug_set_option, e.g. 3=0,5=0 (no L2 hints, no programmatic dependent launch)")
     a = ap.parse_args()
     dev = torch.device("cuda")
     g = torch.Generator(device=dev).manual_seed(0)
