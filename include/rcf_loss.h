@@ -96,6 +96,9 @@ typedef struct RcfDesc {
        the gradient of the total loss[ndir] = flow_loss['seg'] (reference :397), applied to every direction.  The
        reference's caller only ever differentiates 'seg' (rcf_model.py:464-470). */
     int32_t grad_loss_total;
+    int32_t dfeat_f16;         /* channels-last head only: RcfGrads.dfeat_hi receives IEEE fp16 words of dfeat * 2^e (dfeat_lo unused),
+                                  e chosen on the device from the gradient's magnitude (see rcf_head_backward); the library's own
+                                  tcgen05 kernels consume it and divide the scale out of their results */
 } RcfDesc;
 
 typedef struct RcfInputs {
@@ -216,6 +219,15 @@ RCF_API int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstr
  * nprod: bf16 products per fp32 product: 3 = fp32-grade (hi + lo of both operands, ~1e-5), 2 = weights hi + lo,
  * activations in_hi only (TF32 class), 1 = in_hi x w_hi (autocast class).  in_lo may be NULL unless nprod == 3. */
 #define RCF_CONV64_WPACK_BYTES (9 * 16384 + 2 * (9 * 8192 + 9 * 4096))   /* one-CTA image + the two CTA-pair images */
+/* Operand-format flags, OR-ed into `nprod` of rcf_conv64_forward / rcf_conv64_wgrad (nprod must then be 1) and into
+ * `transpose_flip` of rcf_conv64_pack_weights: the 16-bit words are IEEE fp16 (11-bit significand) instead of bf16.
+ *   RCF_CONV64_A_F16: the activation operand (in_hi of rcf_conv64_forward, x_hi of rcf_conv64_wgrad) is fp16;
+ *   RCF_CONV64_W_F16: the packed weights are fp16 (pass it to the pack call AND to the conv call that uses that image).
+ * One product of fp16 activations and fp16 weights has TF32-class accuracy (2^-11 per operand) at the cost of the plain
+ * bf16 mode; gradients stay bf16 (their range does not fit fp16 without scaling).  rcf_head_* select this for nprod = 2. */
+#define RCF_CONV64_A_F16 0x100
+#define RCF_CONV64_W_F16 0x200
+#define RCF_STEM_OUT_F16 0x100   /* OR-ed into `nprod` of rcf_stem_forward_bf16: act_hi is written as fp16 (saturating) */
 RCF_API int rcf_conv64_pack_weights(const float* w, void* wpack, int transpose_flip, void* stream);
 RCF_API int rcf_conv64_forward(const void* in_hi, const void* in_lo, const void* wpack, float* out, int nimg, int H, int W,
                                int nprod, void* stream);

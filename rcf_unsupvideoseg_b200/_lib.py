@@ -32,6 +32,7 @@ class RcfDesc(C.Structure):
         ("dmask_bstride", _i64x2), ("dresid_bstride", _i64x2), ("dfeat_bstride", _i64x2),
         ("vis_bstride", C.c_int64), ("vis_dstride", C.c_int64), ("vis_scale", C.c_float * 2),
         ("feat_lrelu_slope", C.c_float), ("feat_nhwc", C.c_int32), ("grad_loss_total", C.c_int32),
+        ("dfeat_f16", C.c_int32),
     ]
 
 

@@ -14,6 +14,7 @@ import torch
 from . import _lib
 
 WPACK_BYTES = 9 * 16384 + 2 * (9 * 8192 + 9 * 4096)      # RCF_CONV64_WPACK_BYTES
+A_F16, W_F16 = 0x100, 0x200                               # RCF_CONV64_A_F16 / RCF_CONV64_W_F16 (include/rcf_loss.h)
 
 
 def default_nprod(autocast: bool = False) -> int:
@@ -28,14 +29,15 @@ def conv64_supported(conv: torch.nn.Conv2d) -> bool:
             and conv.groups == 1 and conv.padding_mode == "zeros")
 
 
-def pack_weights(w: torch.Tensor, transpose_flip: bool) -> torch.Tensor:
-    """[64,64,3,3] fp32 -> the swizzled bf16 (hi, lo) B tiles of the kernel; transpose_flip packs the data-gradient operator."""
+def pack_weights(w: torch.Tensor, transpose_flip: bool, f16: bool = False) -> torch.Tensor:
+    """[64,64,3,3] fp32 -> the swizzled bf16 (hi, lo) B tiles of the kernel; transpose_flip packs the data-gradient operator.
+    f16: the hi words are fp16 (use with nprod = 1 and w_f16 = True in the conv call)."""
     lib = _lib.load_library()
     assert tuple(w.shape) == (64, 64, 3, 3) and w.is_cuda
     w = w.detach().float().contiguous()
     out = torch.empty(WPACK_BYTES, dtype=torch.uint8, device=w.device)
     with _lib.device_guard(w.device):
-        _lib.check(lib.rcf_conv64_pack_weights(w.data_ptr(), out.data_ptr(), int(transpose_flip),
+        _lib.check(lib.rcf_conv64_pack_weights(w.data_ptr(), out.data_ptr(), int(transpose_flip) | (W_F16 if f16 else 0),
                                                _lib.raw_stream(w.device)), "rcf_conv64_pack_weights")
     return out
 
@@ -63,18 +65,20 @@ def split_bf16(x: torch.Tensor, want_lo: bool = True):
     return hi, lo
 
 
-def conv64_pair(x_hi: torch.Tensor, x_lo, wpack: torch.Tensor, nprod: int) -> torch.Tensor:
-    """x_hi / x_lo: [N,64,H,W] bf16, channels-last memory format (x ~ hi + lo); returns fp32 channels-last."""
+def conv64_pair(x_hi: torch.Tensor, x_lo, wpack: torch.Tensor, nprod: int, a_f16: bool = False, w_f16: bool = False) -> torch.Tensor:
+    """x_hi / x_lo: [N,64,H,W] bf16, channels-last memory format (x ~ hi + lo); returns fp32 channels-last.
+    a_f16 / w_f16 (nprod = 1 only, both or neither: mixing fp16 with bf16 operands is an illegal tcgen05 instruction): x_hi is
+    a float16 tensor / wpack was packed with f16=True."""
     lib = _lib.load_library()
     if not x_hi.is_cuda:
         raise RuntimeError("conv64: CUDA tensors required (no CPU fallback)")
     N, C, H, W = x_hi.shape
-    assert C == 64 and x_hi.dtype == torch.bfloat16 and x_hi.is_contiguous(memory_format=torch.channels_last)
+    assert C == 64 and x_hi.dtype == (torch.float16 if a_f16 else torch.bfloat16) and x_hi.is_contiguous(memory_format=torch.channels_last)
     assert nprod < 3 or (x_lo is not None and x_lo.shape == x_hi.shape and x_lo.is_contiguous(memory_format=torch.channels_last))
     out = torch.empty((N, 64, H, W), dtype=torch.float32, device=x_hi.device, memory_format=torch.channels_last)
     with _lib.device_guard(x_hi.device):
         _lib.check(lib.rcf_conv64_forward(x_hi.data_ptr(), x_lo.data_ptr() if x_lo is not None else None, wpack.data_ptr(),
-                                          out.data_ptr(), N, H, W, int(nprod),
+                                          out.data_ptr(), N, H, W, int(nprod) | (A_F16 if a_f16 else 0) | (W_F16 if w_f16 else 0),
                                           _lib.raw_stream(x_hi.device)), "rcf_conv64_forward")
     return out
 
@@ -92,13 +96,15 @@ def conv64_raw(x: torch.Tensor, wpack: torch.Tensor, nprod: int) -> torch.Tensor
 _WS_BYTES = {}
 
 
-def conv64_wgrad_pair(x_hi, x_lo, g_hi, g_lo, nprod: int) -> torch.Tensor:
-    """dW [64,64,3,3] fp32 from the layer input x ~ x_hi + x_lo and the output gradient g ~ g_hi + g_lo (bf16 channels-last)."""
+def conv64_wgrad_pair(x_hi, x_lo, g_hi, g_lo, nprod: int, f16: bool = False) -> torch.Tensor:
+    """dW [64,64,3,3] fp32 from the layer input x ~ x_hi + x_lo and the output gradient g ~ g_hi + g_lo (bf16 channels-last).
+    f16 (nprod = 1 only): x_hi and g_hi are float16 tensors (tcgen05 wants both operands in one format)."""
     lib = _lib.load_library()
     N, C, H, W = x_hi.shape
     assert C == 64 and g_hi.shape == x_hi.shape
     for t in (x_hi, x_lo, g_hi, g_lo):
-        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=torch.channels_last))
+        assert t is None or (t.dtype in (torch.bfloat16, torch.float16) and t.is_contiguous(memory_format=torch.channels_last))
+    assert x_hi.dtype == g_hi.dtype == (torch.float16 if f16 else torch.bfloat16)
     dev = x_hi.device
     key = (dev.index, N, H, W)
     if key not in _WS_BYTES:
@@ -111,7 +117,7 @@ def conv64_wgrad_pair(x_hi, x_lo, g_hi, g_lo, nprod: int) -> torch.Tensor:
     with _lib.device_guard(dev):
         _lib.check(lib.rcf_conv64_wgrad(x_hi.data_ptr(), x_lo.data_ptr() if x_lo is not None else None, g_hi.data_ptr(),
                                         g_lo.data_ptr() if g_lo is not None else None, dw.data_ptr(), ws.data_ptr(), N, H, W,
-                                        int(nprod), _lib.raw_stream(dev)), "rcf_conv64_wgrad")
+                                        int(nprod) | ((A_F16 | W_F16) if f16 else 0), _lib.raw_stream(dev)), "rcf_conv64_wgrad")
     return dw
 
 

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "rcf_common.cuh"
+#include "rcf_internal.h"
 
 namespace {
 
@@ -73,6 +74,8 @@ void fill_common(RcfK& a, const RcfDesc& d, const RcfInputs& in, const RcfLayout
     a.dbfd = reinterpret_cast<double*>(w + L.w_dbfd);
     a.poolsum = reinterpret_cast<double*>(w + L.w_poolsum);
     a.cnt = reinterpret_cast<unsigned int*>(w + L.w_cnt);
+    a.gmax = reinterpret_cast<float*>(w + L.w_gmax);
+    a.dfeat_f16 = 0;
     a.nblkpb = L.nblkpb; a.poolchunk = L.poolchunk; a.pooltp = L.pooltp;
     a.mlp_smem = (d.theta_mode == 1 && d.Cf % 4 == 0 && d.Cf <= 128 && aligned16(in.w1)) ? 1 : 0;
     a.pdl = g_pdl;
@@ -140,6 +143,11 @@ extern "C" int rcf_debug_set_option(int option, int value) {
     if (option == RCF_OPT_SINGLE_PASS) { g_single_pass = value ? 1 : 0; return RCF_OK; }
     if (option == RCF_OPT_PDL) { g_pdl = value ? 1 : 0; return RCF_OK; }
     return RCF_ERR_MODE;
+}
+
+const float* rcf_ws_gmax(const RcfDesc* desc, const void* ws) {
+    const RcfLayout L = rcf_make_layout(*desc);
+    return reinterpret_cast<const float*>(static_cast<const unsigned char*>(ws) + L.w_gmax);
 }
 
 extern "C" int rcf_abi_version(void) { return RCF_ABI_VERSION; }
@@ -225,7 +233,8 @@ extern "C" int rcf_backward(const RcfDesc* desc, const RcfInputs* in, const floa
         a.dmask[i] = grads->dmask[i]; a.dresid[i] = grads->dresid[i];
         a.dfeat[i] = desc->theta_mode == 1 ? grads->dfeat[i] : nullptr;
         a.dfeat_hi[i] = (desc->theta_mode == 1 && desc->feat_nhwc) ? static_cast<uint32_t*>(grads->dfeat_hi[i]) : nullptr;
-        a.dfeat_lo[i] = a.dfeat_hi[i] ? static_cast<uint32_t*>(grads->dfeat_lo[i]) : nullptr;
+        a.dfeat_lo[i] = (a.dfeat_hi[i] && !desc->dfeat_f16) ? static_cast<uint32_t*>(grads->dfeat_lo[i]) : nullptr;
+        if (a.dfeat_hi[i] && desc->dfeat_f16) a.dfeat_f16 = 1;
         if (a.dfeat_hi[i] && (!aligned16(a.dfeat_hi[i]) || (a.dfeat_lo[i] && !aligned16(a.dfeat_lo[i])) || desc->dfeat_bstride[i] % 8))
             return RCF_ERR_ALIGN;
         if (a.dfeat_hi[i]) any_dfeat = true;

@@ -70,7 +70,7 @@ struct RcfLayout {
     // ctx (bytes offsets)
     size_t c_segd, c_coef, c_mlp, c_gm, c_bytes;
     // ws
-    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_dbpart, w_dbfd, w_poolsum, w_cnt, w_bytes;
+    size_t w_part1, w_partp, w_part2, w_coefb, w_gscale, w_poolbar, w_dh, w_thbar, w_dbpart, w_dbfd, w_poolsum, w_cnt, w_gmax, w_bytes;
     int nblkpb;   // CTAs per frame-direction of the channels-last pooling backward (pooltp pixels each)
     int poolchunk, pooltp;
 };
@@ -120,6 +120,7 @@ static inline RcfLayout rcf_make_layout(const RcfDesc& d) {
     L.w_dbfd = o;    o = rcf_align256(o + (d.feat_nhwc ? (size_t)L.nfd * 16 * d.Cf * sizeof(double) : 0));   // <= 16 splits per fd
     L.w_poolsum = o; o = rcf_align256(o + nseg * d.Cf * sizeof(double));
     L.w_cnt = o;     o = rcf_align256(o + 64);      // arrival counters of the "last CTA finishes the reduction" kernels
+    L.w_gmax = o;    o = rcf_align256(o + (size_t)L.nfd * sizeof(float));   // per frame-direction max |dPool/S| (fp16 gradient scale)
     L.w_bytes = o ? o : 256;
     return L;
 }
@@ -182,6 +183,8 @@ struct RcfK {
     float* dbpart;            // ws: [nfd][nblkpb][Cf]
     double* dbfd;             // ws: [nfd * S][Cf], S <= 16 splits of the partial rows
     double* poolsum;          // ws: [nfd][Cf*K] pooled sums (un-normalised), reduced over chunks by k_pool_reduce
+    float* gmax;              // ws: [nfd] max |poolbar| per frame-direction, written by k_segment_bwd; source of rcf_grad_scale
+    int dfeat_f16;            // dfeat_hi is written as fp16 words scaled by rcf_grad_scale(gmax) (RcfDesc.dfeat_f16)
     unsigned int* cnt;        // ws: arrival counters -- [1] k_bias_grad_fd (zeroed by k_pool_bwd_nhwc); [0] unused (folding k_loss_sum into
                               // k_finalize the same way was measured: +0.7 us on the C2 loss-core step, so that pair stays two launches)
     int nblkpb;
@@ -200,6 +203,23 @@ __device__ __forceinline__ void rcf_pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// Power-of-two scale that brings the feature-map gradient into fp16's normal range: dG[p][f] = dact * sum_k c[f][k] M[k][p]
+// with sum_k M = 1 and |dact| <= 1, so |dG| <= max |c| =: m; s = 2^(14 - exponent(m)) puts the largest element in
+// [2^13, 2^14) (fp16 overflows at 2^16) and keeps 11 significant bits for everything down to 2^-28 of it.  Every consumer
+// recomputes s from the same nfd floats, so all of them agree bit for bit; scaling by s and by 1/s is exact.
+// Call with all 32 lanes of a warp.
+__device__ __forceinline__ float rcf_grad_scale(const float* __restrict__ gmax, int nfd) {
+    float m = 0.0f;
+    for (int i = (int)(threadIdx.x & 31); i < nfd; i += 32) m = fmaxf(m, __ldcg(gmax + i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (!(m > 0.0f) || !(m < 3.0e38f)) return 1.0f;          // zero / inf / nan gradient: no scaling
+    int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;   // m = f * 2^e, f in [0.5, 1)  (subnormal m: e = -126, fine)
+    e = 14 - e;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    return __uint_as_float((uint32_t)(e + 127) << 23);
+}
+
 // "The last CTA to arrive finishes the job": every CTA publishes its partial results, then one thread takes a ticket; the
 // CTA that draws the last ticket sees all partials (fence + atomic) and runs the final, fixed-order reduction itself, so
 // the separate single-CTA launch that used to follow disappears.  The counter is zeroed by the PRECEDING kernel of the

@@ -33,6 +33,7 @@ struct Conv64Args {
     const uint8_t* wpack;   // C64_W_BYTES, see k_conv64_pack
     int* status;            // device word: set to 1 when a barrier wait timed out (protocol bug), never read on the hot path
     int debug;              // measurement switches: 1 no epilogue stores, 4 no MMAs (results invalid)
+    uint32_t fmt;           // operand formats: bit 0 activations are fp16, bit 1 packed weights are fp16 (else bf16)
     long long* trace;       // optional: clock64 stamps of CTA 0's pipeline events, [tile][8] (tools/trace_conv64.py)
 };
 #define C64_TRACE(slot) do { if (a.trace && blockIdx.x == 0 && it < 64 && lane == 0) a.trace[it * 8 + (slot)] = clock64(); } while (0)
@@ -58,7 +59,8 @@ __device__ __forceinline__ bool wait_or_abort(uint64_t* bar, uint32_t parity, vo
 //   data grad (transpose_flip = 1): row n <-> ci, k <-> co, tap (2-ty,2-tx): din[q] = sum W[co][ci][2-ty][2-tx] dout[q + (ty-1)Wp + (tx-1)]
 // rows 0-63 hold the bf16 "hi" word of the weight, rows 64-127 the "lo" word.
 // transpose_flip = 2: both, the data-gradient image C64_WPACK_TOTAL_BYTES after the forward one (blockIdx.y selects).
-__global__ void k_conv64_pack(const float* __restrict__ w, uint8_t* __restrict__ out, int transpose_flip) {
+// w_f16: the "hi" words are fp16 (11-bit significand, the single-product TF32-class mode), the "lo" words are zero.
+__global__ void k_conv64_pack(const float* __restrict__ w, uint8_t* __restrict__ out, int transpose_flip, int w_f16) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 9 * 64 * 64) return;
     if (transpose_flip == 2) {
@@ -71,6 +73,7 @@ __global__ void k_conv64_pack(const float* __restrict__ w, uint8_t* __restrict__
     else v = w[(k * 64 + n) * 9 + (8 - tap)];
     uint32_t hi, lo;
     split_bf16(v, hi, lo);
+    if (w_f16) { hi = (cvt_f16x2(v, 0.0f) & 0xffffu) << 16; lo = 0u; }
     const int chunk = ((k >> 3) ^ (n & 7)) << 4;     // both row n and row 64 + n have (row & 7) == (n & 7)
     uint8_t* base = out + tap * C64_TAP_BYTES + chunk + (k & 7) * 2;
     *reinterpret_cast<uint16_t*>(base + n * 128) = (uint16_t)(hi >> 16);
@@ -133,7 +136,8 @@ k_conv64(const Conv64Args a, const __grid_constant__ CUtensorMap tm_hi, const __
         }
         __syncwarp();
         wait_or_abort(&bars->wbar, 0, abort_flag);
-        constexpr uint32_t IDESC64 = make_idesc_bf16(128, 64, 0, 0), IDESC128 = make_idesc_bf16(128, 128, 0, 0);
+        const uint32_t IDESC64 = idesc_with_formats(make_idesc_bf16(128, 64, 0, 0), a.fmt);
+        const uint32_t IDESC128 = idesc_with_formats(make_idesc_bf16(128, 128, 0, 0), a.fmt);
         const uint64_t wdesc = make_desc_sw128(smem_u32(sW), 16, 1024);
         const uint32_t Wp8 = (uint32_t)g.Wp * 8;                     // one tile row, in 16-byte units
         int it = 0;
@@ -298,7 +302,7 @@ int rcf_make_tmap_nhwc64(CUtensorMap* tm, const void* base, int nimg, int H, int
 }
 
 int rcf_conv64_pair_launch(const void* in_hi, const void* in_lo, const void* wpack_pair, float* out, int nimg, int H, int W,
-                           int nprod, cudaStream_t s);
+                           int nprod, uint32_t fmt, cudaStream_t s);
 
 int* rcf_conv64_status_addr() {
     static int* addr = nullptr;          // resolved once (outside any stream capture of later calls)
@@ -312,10 +316,12 @@ extern "C" {
 
 RCF_API int rcf_conv64_pack_weights(const float* w, void* wpack, int transpose_flip, void* stream) {
     if (!w || !wpack) return RCF_ERR_NULL;
+    const int w_f16 = (transpose_flip & RCF_CONV64_W_F16) ? 1 : 0;
+    transpose_flip &= 0xff;
     if (((uintptr_t)wpack & 15) != 0) return RCF_ERR_ALIGN;
     if (transpose_flip < 0 || transpose_flip > 2) return RCF_ERR_MODE;
     const dim3 grid((9 * 64 * 64 + 255) / 256, transpose_flip == 2 ? 2 : 1);
-    k_conv64_pack<<<grid, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)wpack, transpose_flip);
+    k_conv64_pack<<<grid, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)wpack, transpose_flip, w_f16);
     return (int)cudaGetLastError();
 }
 
@@ -329,6 +335,9 @@ RCF_API int rcf_split_bf16(const float* x, void* hi, void* lo, size_t n, void* s
 
 RCF_API int rcf_conv64_forward(const void* in_hi, const void* in_lo, const void* wpack, float* out, int nimg, int H, int W,
                                int nprod, void* stream) {
+    const uint32_t fmt = ((nprod & RCF_CONV64_A_F16) ? 1u : 0u) | ((nprod & RCF_CONV64_W_F16) ? 2u : 0u);
+    nprod &= 0xff;
+    if (fmt && nprod != 1) return RCF_ERR_MODE;          // fp16 operands are the single-product mode
     if (!in_hi || !wpack || !out || (nprod == 3 && !in_lo)) return RCF_ERR_NULL;
     if (nimg < 1 || H < 1 || W < 1 || (long long)nimg * H * W > (1ll << 31)) return RCF_ERR_SHAPE;
     if (nprod < 1 || nprod > 3) return RCF_ERR_MODE;
@@ -341,10 +350,10 @@ RCF_API int rcf_conv64_forward(const void* in_hi, const void* in_lo, const void*
         g_conv64_attr_done = 1;
     }
     if (g_conv64_pair)
-        return rcf_conv64_pair_launch(in_hi, in_lo, (const uint8_t*)wpack + C64_W_BYTES, out, nimg, H, W, nprod, (cudaStream_t)stream);
+        return rcf_conv64_pair_launch(in_hi, in_lo, (const uint8_t*)wpack + C64_W_BYTES, out, nimg, H, W, nprod, fmt, (cudaStream_t)stream);
     Conv64Args a;
     a.g = conv64_make_geom(nimg, H, W);
-    a.out = out; a.wpack = (const uint8_t*)wpack; a.debug = g_conv64_debug; a.trace = g_conv64_trace;
+    a.out = out; a.wpack = (const uint8_t*)wpack; a.debug = g_conv64_debug; a.trace = g_conv64_trace; a.fmt = fmt;
     a.status = rcf_conv64_status_addr();
     if (!a.status) return (int)cudaErrorInvalidSymbol;
     alignas(64) CUtensorMap tm_hi, tm_lo;

@@ -39,6 +39,7 @@ struct PairArgs {
     int* status;
     int npairs;                // ceil(ntiles / 2)
     int debug;                 // measurement switch: 1 no epilogue stores
+    uint32_t fmt;              // operand formats: bit 0 activations fp16, bit 1 weights fp16 (else bf16)
 };
 
 struct PairBars {
@@ -105,7 +106,8 @@ k_conv64_pair(const PairArgs a, const __grid_constant__ CUtensorMap tm_hi, const
             asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(&bars->wpeer) & PEER_BIT_MASK) : "memory");
         if (rank == 0) {
             pwait(&bars->wpeer, 0, abort_flag);
-            constexpr uint32_t IDESC64 = make_idesc_bf16(256, 64, 0, 0), IDESC128 = make_idesc_bf16(256, 128, 0, 0);
+            const uint32_t IDESC64 = idesc_with_formats(make_idesc_bf16(256, 64, 0, 0), a.fmt);
+            const uint32_t IDESC128 = idesc_with_formats(make_idesc_bf16(256, 128, 0, 0), a.fmt);
             const uint64_t ydesc = make_desc_sw128(smem_u32(sY), 16, 1024), zdesc = make_desc_sw128(smem_u32(sZ), 16, 1024);
             const uint32_t Wp8 = (uint32_t)g.Wp * 8;
             int it = 0;
@@ -248,8 +250,9 @@ int launch_pair(const PairArgs& a, const CUtensorMap& hi, const CUtensorMap& lo,
 }  // namespace
 
 int rcf_conv64_pair_launch(const void* in_hi, const void* in_lo, const void* wpack_pair, float* out, int nimg, int H, int W,
-                           int nprod, cudaStream_t s) {
+                           int nprod, uint32_t fmt, cudaStream_t s) {
     PairArgs a;
+    a.fmt = fmt;
     a.g = conv64_make_geom(nimg, H, W);
     a.out = out; a.wpack = (const uint8_t*)wpack_pair;
     a.npairs = (a.g.ntiles + 1) / 2;

@@ -21,6 +21,7 @@
 
 #include "rcf_common.cuh"
 #include "rcf_umma.cuh"
+#include "rcf_internal.h"
 
 int rcf_make_tmap_nhwc64(CUtensorMap* tm, const void* base, int nimg, int H, int W, int bw, int bh);
 int* rcf_conv64_status_addr();
@@ -46,6 +47,7 @@ struct WgradArgs {
     WgradGeom g;
     float* part;               // [gridDim.x][2][128][192]
     int* status;
+    uint32_t fmt;              // operand formats: bit 0 the layer input x (A operand) is fp16, bit 1 the gradient (B) is fp16
 };
 
 struct WgBars {
@@ -89,7 +91,7 @@ k_conv64_wgrad(const WgradArgs a, const __grid_constant__ CUtensorMap tm_xh, con
     const int nchunk = g.L >> 4;
 
     if (warp == WG_MMA_WARP) {
-        constexpr uint32_t IDESC = make_idesc_bf16(128, 192, 1, 1);
+        const uint32_t IDESC = idesc_with_formats(make_idesc_bf16(128, 192, 1, 1), a.fmt);
         int it = 0;
         for (int tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
             const int s = it % WG_STAGES, ph = (it / WG_STAGES) & 1;
@@ -172,9 +174,10 @@ k_conv64_wgrad(const WgradArgs a, const __grid_constant__ CUtensorMap tm_xh, con
 // dW[co][ci][ty][tx] = sum over CTAs (fixed order) of the partial accumulators:
 //   accumulator 0, lane a*64 + ci, column u*64 + co  ->  (ty = a,     tx = 2 - u)
 //   accumulator 1, lane a*64 + ci, column u*64 + co  ->  (ty = a + 1, tx = 2 - u); its a = 0 half duplicates ty = 1 and is dropped
-__global__ void __launch_bounds__(256) k_conv64_wgrad_reduce(const float* __restrict__ part, int nparts, float* __restrict__ dw) {
+__global__ void __launch_bounds__(256) k_conv64_wgrad_reduce(const float* __restrict__ part, int nparts, float* __restrict__ dw,
+                                                             const float* __restrict__ gmax, int nfd) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per output element, co fastest within a warp
-    if (idx >= 64 * 64 * 9) return;
+    if (idx >= 64 * 64 * 9) return;                                 // (64 * 64 * 9 is a multiple of 32: whole warps leave)
     const int co = idx & 63, ci = (idx >> 6) & 63, tap = idx >> 12;
     const int ty = tap / 3, tx = tap - ty * 3;
     const int accn = ty == 2 ? 1 : 0, arow = ty == 2 ? 1 : ty;
@@ -188,7 +191,9 @@ __global__ void __launch_bounds__(256) k_conv64_wgrad_reduce(const float* __rest
         s3 += __ldg(part + (size_t)(p + 3) * WG_PART_FLOATS + off);
     }
     for (; p < nparts; ++p) s0 += __ldg(part + (size_t)p * WG_PART_FLOATS + off);
-    dw[(co * 64 + ci) * 9 + tap] = (s0 + s1) + (s2 + s3);
+    // fp16 gradient words carry a power-of-two scale: divide it out (exact).  After the loads, so the sum loop is unchanged.
+    const float inv = gmax ? 1.0f / rcf_grad_scale(gmax, nfd) : 1.0f;
+    dw[(co * 64 + ci) * 9 + tap] = ((s0 + s1) + (s2 + s3)) * inv;
 }
 
 WgradGeom wgrad_geom(int nimg, int H, int W, int nprod) {
@@ -251,6 +256,16 @@ RCF_API int rcf_conv64_wgrad_workspace_bytes(int nimg, int H, int W, size_t* byt
 
 RCF_API int rcf_conv64_wgrad(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, float* dw, void* ws,
                              int nimg, int H, int W, int nprod, void* stream) {
+    return rcf_conv64_wgrad_ex(x_hi, x_lo, g_hi, g_lo, dw, ws, nimg, H, W, nprod, nullptr, 0, stream);
+}
+
+}  // extern "C"
+
+int rcf_conv64_wgrad_ex(const void* x_hi, const void* x_lo, const void* g_hi, const void* g_lo, float* dw, void* ws, int nimg,
+                        int H, int W, int nprod, const float* gmax, int nfd, void* stream) {
+    const uint32_t fmt = ((nprod & RCF_CONV64_A_F16) ? 1u : 0u) | ((nprod & RCF_CONV64_W_F16) ? 2u : 0u);
+    nprod &= 0xff;
+    if (fmt && nprod != 1) return RCF_ERR_MODE;          // fp16 operands are the single-product mode
     if (!x_hi || !g_hi || !dw || !ws || (nprod == 3 && !x_lo) || (nprod >= 2 && !g_lo)) return RCF_ERR_NULL;
     if (nimg < 1 || H < 1 || W < 1 || (long long)nimg * H * W > (1ll << 31)) return RCF_ERR_SHAPE;
     if (nprod < 1 || nprod > 3) return RCF_ERR_MODE;
@@ -258,6 +273,7 @@ RCF_API int rcf_conv64_wgrad(const void* x_hi, const void* x_lo, const void* g_h
     WgradArgs a;
     a.g = wgrad_geom(nimg, H, W, nprod);
     a.part = (float*)ws;
+    a.fmt = fmt;
     a.status = rcf_conv64_status_addr();
     if (!a.status) return (int)cudaErrorInvalidSymbol;
     alignas(64) CUtensorMap xh, xl, gh, gl;
@@ -273,8 +289,6 @@ RCF_API int rcf_conv64_wgrad(const void* x_hi, const void* x_lo, const void* g_h
     else if (nprod == 2) e = launch_wgrad<2>(a, xh, xl, gh, gl, grid, smem, s);
     else e = launch_wgrad<3>(a, xh, xl, gh, gl, grid, smem, s);
     if (e != RCF_OK) return e;
-    k_conv64_wgrad_reduce<<<(64 * 64 * 9 + 255) / 256, 256, 0, s>>>((const float*)ws, grid, dw);
+    k_conv64_wgrad_reduce<<<(64 * 64 * 9 + 255) / 256, 256, 0, s>>>((const float*)ws, grid, dw, gmax, nfd);
     return (int)cudaGetLastError();
 }
-
-}  // extern "C"

@@ -7,9 +7,28 @@
 #include <cstdint>
 
 #include "rcf_loss.h"
+#include "rcf_internal.h"
 
 namespace {
 constexpr int HEAD_CF = 64;
+
+// Conv precision of the head (the `nprod` argument, chosen by the caller from torch's settings):
+//   3  fp32-grade: bf16 (hi, lo) pairs of both operands, three products per fp32 product
+//   2  TF32-class (torch's default, allow_tf32): ONE product of IEEE fp16 operands everywhere (11-bit significands, 2^-11 per
+//      operand -- what TF32 keeps; tcgen05 kind::f16 wants both operands in the same format, mixing fp16 with bf16 is an
+//      illegal instruction).  Activations and weights fit fp16's range as they are (the stem saturates at +-65504); the
+//      feature-map gradient does not, so rcf_backward writes it multiplied by a power of two chosen on the device from
+//      its magnitude (RcfDesc.dfeat_f16, rcf_grad_scale) and the weight-gradient / stem reductions divide it out again
+//   1  autocast: plain bf16 operands everywhere
+struct HeadModes { int stem, pack, fwd, dgrad, wgrad; bool a_lo, g_lo, g_f16; };
+HeadModes head_modes(int nprod) {
+    if (nprod >= 3) return {3, 2, 3, 3, 3, true, true, false};
+    if (nprod == 2) {
+        const int f = RCF_CONV64_A_F16 | RCF_CONV64_W_F16;
+        return {2 | RCF_STEM_OUT_F16, 2 | RCF_CONV64_W_F16, 1 | f, 1 | f, 1 | f, false, false, true};
+    }
+    return {1, 2, 1, 1, 1, false, false, false};
+}
 
 int check_head(const RcfDesc* d, const RcfInputs* in, const RcfHeadBuffers* hb) {
     if (!d || !in || !hb) return RCF_ERR_NULL;
@@ -30,12 +49,14 @@ extern "C" int rcf_head_forward(const RcfDesc* desc, const RcfInputs* in, const 
     if (!cw1 || !cb1 || !cw2 || !hb->a_hi || !hb->sign || !hb->wpack || !hb->feat) return RCF_ERR_NULL;
     const int ndir = desc->ndir, B = desc->B, H = desc->H, W = desc->W;
     const long long img = (long long)H * W * HEAD_CF;
+    const HeadModes m = head_modes(nprod);
+    if (m.a_lo && !hb->a_lo) return RCF_ERR_NULL;
     rc = rcf_stem_forward_bf16(in->flow, desc->flow_bstride, ndir, B, H, W, ks, cw1, cb1, desc->clamp_t, stem_slope, hb->a_hi,
-                               nprod == 3 ? hb->a_lo : nullptr, hb->sign, nprod, stream);
+                               m.a_lo ? hb->a_lo : nullptr, hb->sign, m.stem, stream);
     if (rc != RCF_OK) return rc;
-    rc = rcf_conv64_pack_weights(cw2, hb->wpack, 2, stream);
+    rc = rcf_conv64_pack_weights(cw2, hb->wpack, m.pack, stream);
     if (rc != RCF_OK) return rc;
-    rc = rcf_conv64_forward(hb->a_hi, nprod == 3 ? hb->a_lo : nullptr, hb->wpack, hb->feat, ndir * B, H, W, nprod, stream);
+    rc = rcf_conv64_forward(hb->a_hi, m.a_lo ? hb->a_lo : nullptr, hb->wpack, hb->feat, ndir * B, H, W, m.fwd, stream);
     if (rc != RCF_OK) return rc;
     RcfInputs in2 = *in;
     RcfDesc d2 = *desc;
@@ -63,6 +84,7 @@ extern "C" int rcf_head_backward(const RcfDesc* desc, const RcfInputs* in, const
     if (!grads || !hb->feat) return RCF_ERR_NULL;
     const int ndir = desc->ndir, B = desc->B, H = desc->H, W = desc->W;
     const long long img = (long long)H * W * HEAD_CF;
+    const HeadModes m = head_modes(nprod);
     RcfInputs in2 = *in;
     RcfGrads g2 = *grads;
     for (int i = 0; i < ndir; ++i) {
@@ -70,9 +92,9 @@ extern "C" int rcf_head_backward(const RcfDesc* desc, const RcfInputs* in, const
         g2.dfeat[i] = nullptr;
         g2.dfeat_hi[i] = g2.dfeat_lo[i] = nullptr;
         if (need_conv_grads) {
-            if (!hb->g_hi || (nprod >= 2 && !hb->g_lo)) return RCF_ERR_NULL;
+            if (!hb->g_hi || (m.g_lo && !hb->g_lo)) return RCF_ERR_NULL;
             g2.dfeat_hi[i] = static_cast<uint16_t*>(hb->g_hi) + (long long)i * B * img;
-            if (nprod >= 2) g2.dfeat_lo[i] = static_cast<uint16_t*>(hb->g_lo) + (long long)i * B * img;
+            if (m.g_lo) g2.dfeat_lo[i] = static_cast<uint16_t*>(hb->g_lo) + (long long)i * B * img;
         }
     }
     if (!need_conv_grads) g2.dfeat_bias = nullptr;
@@ -91,6 +113,7 @@ extern "C" int rcf_head_backward(const RcfDesc* desc, const RcfInputs* in, const
             }
         }
     }
+    d2.dfeat_f16 = (need_conv_grads && m.g_f16) ? 1 : 0;
     rc = rcf_backward(&d2, &in2, grad_loss, ctx, ws, &g2, stream);
     if (rc != RCF_OK) return rc;
     if (lowres) {                                          // gradient of the up-sampling: a deterministic gather
@@ -108,11 +131,13 @@ extern "C" int rcf_head_backward(const RcfDesc* desc, const RcfInputs* in, const
     if (!hb->a_hi || !hb->sign || !hb->wpack || !hb->d_a1 || !hb->wgrad_ws || !hb->stem_ws || !hb->d_cw1 || !hb->d_cb1 || !hb->d_cw2)
         return RCF_ERR_NULL;
     const void* wp_bwd = static_cast<const uint8_t*>(hb->wpack) + RCF_CONV64_WPACK_BYTES;
-    rc = rcf_conv64_forward(hb->g_hi, nprod == 3 ? hb->g_lo : nullptr, wp_bwd, hb->d_a1, ndir * B, H, W, nprod, stream);
+    rc = rcf_conv64_forward(hb->g_hi, m.g_lo ? hb->g_lo : nullptr, wp_bwd, hb->d_a1, ndir * B, H, W, m.dgrad, stream);
     if (rc != RCF_OK) return rc;
-    rc = rcf_conv64_wgrad(hb->a_hi, nprod == 3 ? hb->a_lo : nullptr, hb->g_hi, nprod >= 2 ? hb->g_lo : nullptr, hb->d_cw2, hb->wgrad_ws,
-                          ndir * B, H, W, nprod, stream);
+    // fp16 mode: g_hi = dG * s, hence d_a1 = dA1 * s; the two reductions below divide s out (gmax: where s comes from)
+    const float* gmax = m.g_f16 ? rcf_ws_gmax(&d2, ws) : nullptr;
+    rc = rcf_conv64_wgrad_ex(hb->a_hi, m.a_lo ? hb->a_lo : nullptr, hb->g_hi, m.g_lo ? hb->g_lo : nullptr, hb->d_cw2, hb->wgrad_ws,
+                             ndir * B, H, W, m.wgrad, gmax, ndir * B, stream);
     if (rc != RCF_OK) return rc;
-    return rcf_stem_backward(in->flow, desc->flow_bstride, ndir, B, H, W, HEAD_CF, ks, desc->clamp_t, stem_slope, nullptr, hb->sign,
-                             hb->d_a1, hb->d_cw1, hb->d_cb1, hb->stem_ws, nprod, stream);
+    return rcf_stem_backward_ex(in->flow, desc->flow_bstride, ndir, B, H, W, HEAD_CF, ks, desc->clamp_t, stem_slope, nullptr, hb->sign,
+                                hb->d_a1, hb->d_cw1, hb->d_cb1, hb->stem_ws, nprod, gmax, ndir * B, stream);
 }

@@ -303,14 +303,24 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) bias[j] = __ldg(a.feat_bias + c4 * 4 + j);
     }
+    // fp16 gradient words (RcfDesc.dfeat_f16): dG is multiplied by the power of two rcf_grad_scale derives from k_segment_bwd's
+    // per-frame-direction maxima before it is rounded; every consumer divides the same factor out again (exact)
+    __shared__ float s_gs;
+    if (tid < 32) {
+        const float v = a.dfeat_f16 ? rcf_grad_scale(a.gmax, a.nfd) : 1.0f;
+        if (tid == 0) s_gs = v;
+    }
     __syncthreads();
+    const float gs = s_gs;
 
     float4* __restrict__ dgp = dfeat ? reinterpret_cast<float4*>(dfeat + (long long)p0 * Cf) + c4 : nullptr;
     // bf16 (hi, lo) pair output (what the tcgen05 conv kernels load by TMA): 4 channels = one uint2 per word tensor
     uint2* __restrict__ dgh = a.dfeat_hi[dir] ? reinterpret_cast<uint2*>(a.dfeat_hi[dir] + ((long long)b * a.dfeat_bs[dir] + (long long)p0 * Cf) / 2) + c4 : nullptr;
     uint2* __restrict__ dgl = a.dfeat_lo[dir] ? reinterpret_cast<uint2*>(a.dfeat_lo[dir] + ((long long)b * a.dfeat_bs[dir] + (long long)p0 * Cf) / 2) + c4 : nullptr;
     auto store_pair = [&](int p, const float (&dg)[4]) {
-        if (dgl) {
+        if (a.dfeat_f16) {
+            dgh[(long long)p * nf4] = make_uint2(umma::cvt_f16x2(dg[0] * gs, dg[1] * gs), umma::cvt_f16x2(dg[2] * gs, dg[3] * gs));
+        } else if (dgl) {
             uint32_t h0, h1, l0, l1;
             umma::split_bf16x2(dg[0], dg[1], h0, l0);
             umma::split_bf16x2(dg[2], dg[3], h1, l1);
@@ -374,6 +384,9 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
                             if constexpr (MODE == 2) {
                                 dgh[(long long)p * nf4] = make_uint2(umma::cvt_bf16x2(dg[0], dg[1]), umma::cvt_bf16x2(dg[2], dg[3]));
                             }
+                            if constexpr (MODE == 5) {        // fp16 words of the scaled gradient
+                                dgh[(long long)p * nf4] = make_uint2(umma::cvt_f16x2(dg[0] * gs, dg[1] * gs), umma::cvt_f16x2(dg[2] * gs, dg[3] * gs));
+                            }
                             if constexpr (MODE == 3 || MODE == 4) {
                                 uint32_t h0, h1, l0, l1;
                                 umma::split_bf16x2(dg[0], dg[1], h0, l0);
@@ -393,12 +406,13 @@ __global__ void __launch_bounds__(RCF_BLOCK, 3) k_pool_bwd_nhwc(const RcfK a) {
                     }
                 }
             };
-            const int mode = dgp ? ((dgh && dgl) ? 4 : 1) : (dgh ? (dgl ? 3 : 2) : 0);
-            if (dgp && dgh && !dgl) done = false;          // fp32 + hi only: not a combination any caller asks for
+            const int mode = dgp ? ((dgh && dgl) ? 4 : 1) : (dgh ? (a.dfeat_f16 ? 5 : (dgl ? 3 : 2)) : 0);
+            if (dgp && dgh && (!dgl || a.dfeat_f16)) done = false;          // fp32 + hi only: not a combination any caller asks for
             else if (mode == 0) sweep(std::integral_constant<int, 0>{});
             else if (mode == 1) sweep(std::integral_constant<int, 1>{});
             else if (mode == 2) sweep(std::integral_constant<int, 2>{});
             else if (mode == 3) sweep(std::integral_constant<int, 3>{});
+            else if (mode == 5) sweep(std::integral_constant<int, 5>{});
             else sweep(std::integral_constant<int, 4>{});
         }
     }

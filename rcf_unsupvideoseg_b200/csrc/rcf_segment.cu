@@ -234,6 +234,9 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
                     if (q0 + u * blockDim.x < Cf * Cf / 4) reinterpret_cast<float4*>(w1s)[q0 + u * blockDim.x] = w[u];
             }
         const double* mlp = a.mlp + (size_t)fd * K * 2 * Cf;
+        __shared__ unsigned int s_pbmax;
+        float pbmax = 0.0f;
+        if (tid == 0) s_pbmax = 0u;
         for (int t = tid; t < Cf * K; t += blockDim.x) {
             const int i = t / K, k = t - i * K;
             const double hp = mlp[(size_t)k * 2 * Cf + Cf + i];
@@ -253,9 +256,15 @@ __global__ void __launch_bounds__(RCF_BLOCK) k_segment_bwd(const RcfK a) {
                 for (int i = 0; i < Cf; ++i) v += (double)__ldg(a.w1 + (size_t)i * Cf + j) * dh[i * K + k];
             }
             pbar[j * K + k] = v;
-            a.poolbar[((size_t)fd * Cf + j) * K + k] = (float)(v / sd[k * SEGD]);
+            const float pb = (float)(v / sd[k * SEGD]);
+            a.poolbar[((size_t)fd * Cf + j) * K + k] = pb;
+            pbmax = fmaxf(pbmax, fabsf(pb));
         }
+        // max |poolbar| of this frame-direction (bounds the feature-map gradient: see rcf_grad_scale); non-negative floats
+        // order like their bit patterns, so one shared-memory atomicMax on the bits does it
+        atomicMax(&s_pbmax, __float_as_uint(pbmax));
         __syncthreads();
+        if (tid == 0) a.gmax[fd] = __uint_as_float(s_pbmax);
         for (int k = tid >> 5; k < K; k += blockDim.x >> 5) {      // one warp per segment, fp64 butterfly
             const int lane = tid & 31;
             double v = 0.0;

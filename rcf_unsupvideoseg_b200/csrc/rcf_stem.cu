@@ -11,6 +11,7 @@
 //                 in fp64 => bit-reproducible.  No input gradient: the RAFT flow carries no grad.
 #include "rcf_common.cuh"
 #include "rcf_umma.cuh"
+#include "rcf_internal.h"
 
 namespace {
 
@@ -24,6 +25,7 @@ struct StemK {
     float* act;          // [N][P][Cf]
     uint32_t* act_hi;    // tensor-core path, optional: the activation as bf16 pairs [N][P][Cf/2] (hi word; lo word = act - hi)
     uint32_t* act_lo;    //   instead of the fp32 map: what the tcgen05 conv (rcf_conv64.cu) loads by TMA
+    int act_f16;         // act_hi holds IEEE fp16 words (saturating) instead of bf16: the single-product TF32-class conv mode
     const float* act_in; // backward: forward output (sign of the pre-activation) -- CUDA-core path
     uint32_t* sign_out;  // tensor-core path: [N][P][Cf/32] bit f%32 of word f/32 set <=> pre-activation of channel f is <= 0
     const uint32_t* sign_in;
@@ -428,6 +430,9 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_fwd_mma(c
                             for (int e = 0; e < 4; ++e) umma::split_bf16x2(o[2 * e], o[2 * e + 1], hw[e], lw[e]);
                             *reinterpret_cast<uint2*>(a.act_lo + wofs) = make_uint2(lw[0], lw[1]);
                             *reinterpret_cast<uint2*>(a.act_lo + wofs + 8) = make_uint2(lw[2], lw[3]);
+                        } else if (a.act_f16) {                  // fp16 operand (11-bit significand), saturating
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) hw[e] = umma::cvt_f16x2(o[2 * e], o[2 * e + 1]);
                         } else {                                 // plain bf16 operand: one conversion per channel pair
 #pragma unroll
                             for (int e = 0; e < 4; ++e) hw[e] = umma::cvt_bf16x2(o[2 * e], o[2 * e + 1]);
@@ -575,11 +580,14 @@ __global__ void __launch_bounds__(RCF_BLOCK, (KS <= 3) ? 2 : 1) k_stem_bwd_mma(c
 }
 
 __global__ void __launch_bounds__(256) k_stem_bwd_final(const float* __restrict__ part, int nparts, int Cf, int NT,
-                                                        float* __restrict__ dw, float* __restrict__ db) {
+                                                        float* __restrict__ dw, float* __restrict__ db,
+                                                        const float* __restrict__ gmax, int nfd) {
     rcf_pdl_prologue();
     const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;   // warp per output f*(NT+1)+t
     if (o >= Cf * (NT + 1)) return;
-    const double v = warp_sum_strided(part + o, nparts, (long long)Cf * (NT + 1), lane);
+    // dact arrived multiplied by the fp16 gradient scale (a power of two): divide it out of the sums (exact)
+    const double inv = gmax ? 1.0 / (double)rcf_grad_scale(gmax, nfd) : 1.0;
+    const double v = warp_sum_strided(part + o, nparts, (long long)Cf * (NT + 1), lane) * inv;
     if (lane == 0) {
         const int f = o / (NT + 1), t = o - f * (NT + 1);
         if (t < NT) dw[(size_t)f * NT + t] = (float)v;
@@ -656,6 +664,9 @@ extern "C" int rcf_stem_forward(const float* const* flow, const int64_t* flow_bs
 extern "C" int rcf_stem_forward_bf16(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W,
                                      int ks, const float* w, const float* b, float clamp_t, float slope, void* act_hi,
                                      void* act_lo, uint32_t* sign, int nprod, void* stream) {
+    const int out_f16 = (nprod & RCF_STEM_OUT_F16) ? 1 : 0;
+    nprod &= 0xff;
+    if (out_f16 && act_lo) return RCF_ERR_MODE;           // the fp16 word stands alone (no lo word)
     const int v = stem_check(ndir, B, H, W, STEM_MMA_CF, ks);
     if (v != RCF_OK) return v;
     if (!flow || !flow_bstride || !flow[0] || (ndir > 1 && !flow[1]) || !w || !b || !act_hi) return RCF_ERR_NULL;
@@ -665,6 +676,7 @@ extern "C" int rcf_stem_forward_bf16(const float* const* flow, const int64_t* fl
     fill(a, flow, flow_bstride, ndir, B, H, W, STEM_MMA_CF, clamp_t, slope);
     a.w = w; a.b = b; a.act = nullptr; a.sign_out = sign;
     a.act_hi = static_cast<uint32_t*>(act_hi); a.act_lo = static_cast<uint32_t*>(act_lo);
+    a.act_f16 = out_f16;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int g = stem_grid_bwd(a.ntiles);
     if (nprod >= 3) {
@@ -695,6 +707,13 @@ static int launch_stem_bwd_mma(const StemK& a, int g, cudaStream_t s) {
 extern "C" int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W,
                                  int Cf, int ks, float clamp_t, float slope, const float* act, const uint32_t* sign,
                                  const float* dact, float* dw, float* db, void* ws, int nprod, void* stream) {
+    return rcf_stem_backward_ex(flow, flow_bstride, ndir, B, H, W, Cf, ks, clamp_t, slope, act, sign, dact, dw, db, ws, nprod,
+                                nullptr, 0, stream);
+}
+
+int rcf_stem_backward_ex(const float* const* flow, const int64_t* flow_bstride, int ndir, int B, int H, int W, int Cf, int ks,
+                         float clamp_t, float slope, const float* act, const uint32_t* sign, const float* dact, float* dw,
+                         float* db, void* ws, int nprod, const float* gmax, int nfd, void* stream) {
     const int v = stem_check(ndir, B, H, W, Cf, ks);
     if (v != RCF_OK) return v;
     if (!flow || !flow_bstride || !flow[0] || (ndir > 1 && !flow[1]) || (!act && !sign) || !dact || !dw || !db || !ws)
@@ -744,6 +763,7 @@ extern "C" int rcf_stem_backward(const float* const* flow, const int64_t* flow_b
         RCF_CUDA(cudaGetLastError());
     }
     const int nout = Cf * (NT + 1);
-    RCF_CUDA(rcf_launch(k_stem_bwd_final, (nout * 32 + 255) / 256, 256, 0, s, rcf_pdl_enabled(), (const float*)a.part, g, Cf, NT, dw, db));
+    RCF_CUDA(rcf_launch(k_stem_bwd_final, (nout * 32 + 255) / 256, 256, 0, s, rcf_pdl_enabled(), (const float*)a.part, g, Cf, NT, dw, db,
+                        gmax, nfd));
     return RCF_OK;
 }

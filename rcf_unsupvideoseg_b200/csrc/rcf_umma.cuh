@@ -42,6 +42,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Operand formats of kind::f16 are per operand: format code 0 = fp16, 1 = bf16.  `fmt` bit 0: A is fp16, bit 1: B is fp16.
+__host__ __device__ constexpr uint32_t idesc_with_formats(uint32_t idesc_bf16, uint32_t fmt) {
+    return idesc_bf16 & ~(((fmt & 1u) << 7) | (((fmt >> 1) & 1u) << 10));
+}
+
 // ---- tcgen05 ---------------------------------------------------------------------------------------------------------
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {      // one full warp; result lands in *smem_slot
@@ -198,6 +203,12 @@ __device__ __forceinline__ void split_bf16(float x, uint32_t& hi_bits, uint32_t&
 __device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
     uint32_t d;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+// two floats -> packed fp16x2 (round to nearest even, saturating to +-65504 instead of inf): `a` in the LOW half
+__device__ __forceinline__ uint32_t cvt_f16x2(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
     return d;
 }
 // hi = bf16x2(a, b); lo = bf16x2(a - float(hi.a), b - float(hi.b))

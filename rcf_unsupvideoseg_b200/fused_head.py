@@ -226,7 +226,7 @@ class RcfHeadFn(torch.autograd.Function):
         if need_conv:
             wg_b, st_b = _aux_sizes(lib, dev, ndir, B, H, W, ks)
             act_b = nimg * P * 64 * 2
-            parts += [("g_hi", act_b), ("g_lo", act_b if nprod >= 2 else 0), ("d_a1", 2 * act_b), ("wgrad_ws", wg_b), ("stem_ws", st_b)]
+            parts += [("g_hi", act_b), ("g_lo", act_b if nprod == 3 else 0), ("d_a1", 2 * act_b), ("wgrad_ws", wg_b), ("stem_ws", st_b)]
         boffs, o = {}, 0
         for name, nbytes in parts:
             boffs[name] = o
@@ -242,7 +242,7 @@ class RcfHeadFn(torch.autograd.Function):
             d_cb2 = torch.empty(64, dtype=torch.float32, device=dev)
             grads.dfeat_bias = d_cb2.data_ptr()
             hb.g_hi = bbase + boffs["g_hi"]
-            hb.g_lo = bbase + boffs["g_lo"] if nprod >= 2 else None
+            hb.g_lo = bbase + boffs["g_lo"] if nprod == 3 else None
             hb.d_a1 = bbase + boffs["d_a1"]
             hb.wgrad_ws = bbase + boffs["wgrad_ws"]
             hb.stem_ws = bbase + boffs["stem_ws"]

@@ -55,7 +55,7 @@ int main(void) {
   F(RcfDesc,robust); F(RcfDesc,unbounded_residual); F(RcfDesc,eps); F(RcfDesc,q); F(RcfDesc,resid_scale); F(RcfDesc,pred_div);
   F(RcfDesc,clamp_t); F(RcfDesc,inv_n); F(RcfDesc,mask_bstride); F(RcfDesc,flow_bstride); F(RcfDesc,resid_bstride);
   F(RcfDesc,feat_bstride); F(RcfDesc,dmask_bstride); F(RcfDesc,dresid_bstride); F(RcfDesc,dfeat_bstride);
-  F(RcfDesc,vis_bstride); F(RcfDesc,vis_dstride); F(RcfDesc,vis_scale); F(RcfDesc,feat_lrelu_slope); F(RcfDesc,feat_nhwc);
+  F(RcfDesc,vis_bstride); F(RcfDesc,vis_dstride); F(RcfDesc,vis_scale); F(RcfDesc,feat_lrelu_slope); F(RcfDesc,feat_nhwc); F(RcfDesc,dfeat_f16);
   F(RcfInputs,mask); F(RcfInputs,flow); F(RcfInputs,resid); F(RcfInputs,feat); F(RcfInputs,theta); F(RcfInputs,w1); F(RcfInputs,b1); F(RcfInputs,w2); F(RcfInputs,b2); F(RcfInputs,feat_bias);
   F(RcfVisOut,gt); F(RcfVisOut,pred); F(RcfVisOut,agg); F(RcfVisOut,res); F(RcfVisOut,aff);
   printf("RcfHeadBuffers %zu\n", sizeof(RcfHeadBuffers)); F(RcfHeadBuffers,a_hi); F(RcfHeadBuffers,feat); F(RcfHeadBuffers,g_hi); F(RcfHeadBuffers,d_cw2); F(RcfHeadBuffers,resid_up); F(RcfHeadBuffers,dresid_up);

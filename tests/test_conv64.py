@@ -95,6 +95,31 @@ def test_conv64_one_cta_and_cta_pair_kernels_agree(c64):
     assert lib.rcf_debug_conv64_status() == 0
 
 
+@pytest.mark.parametrize("N,H,W", [(1, 8, 8), (2, 19, 23), (2, 96, 96), (1, 70, 130)])
+def test_conv64_fp16_operand_formats_vs_fp64(c64, N, H, W):
+    """The TF32-class single-product mode of the head (rcf_head_* with nprod = 2): IEEE fp16 operands (11-bit significands)
+    on both sides of every product; the gradient carries a power-of-two scale that the caller divides out again."""
+    torch.manual_seed(N * 1000 + H)
+    x = (torch.randn(N, 64, H, W, device="cuda") * 3).contiguous(memory_format=torch.channels_last)
+    g = (torch.randn(N, 64, H, W, device="cuda") * 1e-7).contiguous(memory_format=torch.channels_last)     # loss-gradient magnitudes
+    w = torch.randn(64, 64, 3, 3, device="cuda") / 24
+    s = 2.0 ** 36                                                   # what rcf_grad_scale would pick for max |g| ~ 4e-7
+    wf, wb = c64.pack_weights(w, False, f16=True), c64.pack_weights(w, True, f16=True)
+    y = c64.conv64_pair(x.half(), None, wf, 1, a_f16=True, w_f16=True)
+    dx = c64.conv64_pair((g * s).half(), None, wb, 1, a_f16=True, w_f16=True) / s
+    dw = c64.conv64_wgrad_pair(x.half(), None, (g * s).half(), None, 1, f16=True) / s
+    torch.cuda.synchronize()
+    y_ref = F.conv2d(x.double(), w.double(), padding=1)
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, w.double(), g.double(), padding=1)
+    dw_ref = torch.nn.grad.conv2d_weight(x.double(), w.shape, g.double(), padding=1)
+    e = (_rel(y, y_ref), _rel(dx, dx_ref), _rel(dw, dw_ref))
+    assert max(e) < 1e-3, e                                         # 2^-11 per operand
+    y1 = c64.conv64_pair(x.bfloat16(), None, c64.pack_weights(w, False), 1)
+    assert e[0] < 0.5 * _rel(y1, y_ref)                             # and well below the plain bf16 product
+    from rcf_unsupvideoseg_b200 import _lib
+    assert _lib.load_library().rcf_debug_conv64_status() == 0
+
+
 def test_conv64_pack_both_orientations_in_one_launch(c64):
     """transpose_flip = 2 writes the forward image followed by the data-gradient image: byte-identical to the two single packs."""
     w = torch.randn(64, 64, 3, 3, device="cuda") / 24

@@ -232,14 +232,15 @@ def test_c2_batch16_against_tiled_c1_reference(rcf, case):
 
 def test_head_at_torch_default_tf32_bounds_parameter_gradient_error(rcf):
     """torch's DEFAULT settings allow TF32 convolutions (what the reference's convs then run in).  The tcgen05 convs follow
-    that switch: allow_tf32 = False -> 3 bf16 products per fp32 product (fp32-grade), True -> 2 products (weights hi+lo,
-    activations rounded to bf16: 8 instead of TF32's 10 mantissa bits on the activation side, full fp32 on the weight side).
-    Against the reference's fp64 results on a 12x14-pixel golden case (no averaging over pixels: the worst case for
-    rounding noise): loss 1e-5 and mask / residual gradients 1e-4 in BOTH modes; parameter gradients 2e-4 fp32-grade,
-    3e-2 in the 2-product mode -- printed next to what the cuDNN TF32 kernels give on the same inputs."""
+    that switch: allow_tf32 = False -> 3 bf16 products per fp32 product (fp32-grade); True -> ONE product of IEEE fp16
+    operands (11-bit significands = what TF32 keeps; the feature-map gradient carries a device-chosen power-of-two scale so
+    that it fits fp16's range), the stem one TF32 product.  Against the reference's fp64 results on a 12x14-pixel golden
+    case (no averaging over pixels: the worst case for rounding noise): loss 1e-5 and mask / residual gradients 1e-4 in
+    BOTH modes; parameter gradients 2e-4 fp32-grade, 1e-2 in the TF32-class mode -- printed next to what the cuDNN TF32
+    kernels give on the same inputs (measured: 5.6e-3 / 1.8e-3 on the two conv weights against cuDNN's 4.3e-3 / 1.7e-3)."""
     g = Golden("free_l1")
     errs = {}
-    for mode, allow, tc in (("tcgen05, 2 products (allow_tf32)", True, True), ("tcgen05, 3 products", False, True),
+    for mode, allow, tc in (("tcgen05, fp16 operands (allow_tf32)", True, True), ("tcgen05, 3 products", False, True),
                             ("cuDNN TF32 (round-1 path)", True, False)):
         torch.backends.cudnn.allow_tf32 = allow
         try:
@@ -257,7 +258,9 @@ def test_head_at_torch_default_tf32_bounds_parameter_gradient_error(rcf):
                       for k, p in head.named_parameters()}
         print(f"parameter-gradient rel-L2 errors, {mode}: " + ", ".join(f"{k} {v:.1e}" for k, v in errs[mode].items()))
     assert max(errs["tcgen05, 3 products"].values()) <= 2e-4
-    assert max(errs["tcgen05, 2 products (allow_tf32)"].values()) <= 3e-2
+    assert max(errs["tcgen05, fp16 operands (allow_tf32)"].values()) <= 1e-2
+    worst_cudnn = max(errs["cuDNN TF32 (round-1 path)"].values())
+    assert max(errs["tcgen05, fp16 operands (allow_tf32)"].values()) <= 2.0 * worst_cudnn      # the same accuracy class as cuDNN's TF32
 
 
 def test_full_size_properties(rcf):
