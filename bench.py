@@ -495,8 +495,8 @@ def run_ours(args):
                     "copy_only_gbs_each_way": [h2d / copy_only_ms / 1e6, d2h / copy_only_ms / 1e6],
                     "copy_only_note": "the same H2D + D2H copies with no compute, all ranks at once: the host's ceiling for e2e",
                     "staging": wc_note or "torch pin_memory() (cudaHostAlloc default flags)",
-                    "conv_precision": "follows torch.backends.cudnn.allow_tf32 (torch default True -> 2 bf16 products, "
-                                      "weights hi+lo; False -> 3 products, fp32-grade)"},
+                    "conv_precision": "follows torch.backends.cudnn.allow_tf32 (torch default True -> one product of fp16 "
+                                      "operands, TF32-class; False -> 3 bf16 products per fp32 product, fp32-grade)"},
             # value region: k_loss, k_finalize, k_loss_sum | k_segment_bwd, k_bwd per step (single-pass forward), NBLOCKS blocks;
             # e2e region: the library's 19 kernels of the default head per step (profiles/r02_timelines_final.md lists 21: one more,
             # k_bias_grad_final, was folded into k_bias_grad_fd afterwards) + autograd's one-element fill of the upstream gradient)
@@ -640,8 +640,9 @@ def module_throughput(pkg, dev):
         for nprod in (2, 3, 1):
             ms = _graph_time(_module_step(pkg, dev, B, K, H, W, dict(free_residual=True, clamp_flow_t=20.0), nprod=nprod), 5)
             out[f"{name}_nprod{nprod}"] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3}
-    out["note"] = ("nprod = bf16 products per fp32 product in the tcgen05 convs: 3 fp32-grade (torch.backends.cudnn.allow_tf32 = "
-                   "False), 2 weights hi+lo x bf16 activations (torch default), 1 plain bf16 (autocast)")
+    out["note"] = ("nprod = conv precision of the head: 3 fp32-grade (three bf16 products per fp32 product; "
+                   "torch.backends.cudnn.allow_tf32 = False), 2 TF32-class (ONE product of fp16 operands, the feature-map gradient "
+                   "carried as scaled fp16; torch's default), 1 plain bf16 (autocast)")
     return out
 
 
@@ -671,6 +672,9 @@ def conv_kernels(pkg, dev):
                                "definition": "bf16 FLOPs the kernel issues to the tensor cores (nprod products per fp32 product; the weight "
                                              "gradient also computes the centre tap row twice: x 12/9) / CUDA-event time / the measured "
                                              "cuBLAS bf16 rate (MEASURED_PEAKS.json); halo rows (4-5 %) not counted"}}
+    out["kernel_modes"] = ("kernel-level nprod: 1 = one product per tap (bf16 operands; the head's TF32-class default runs this same "
+                           "instruction stream with fp16 operand formats), 2 = activations x [W_hi | W_lo] stacked in N = 128 "
+                           "(no longer used by the head), 3 = three products (fp32-grade)")
     for nprod in (1, 2, 3):
         t_f = _time_cuda(lambda: c64.conv64_pair(hi, lo, wp, nprod), 10) * 1e3
         t_d = _time_cuda(lambda: c64.conv64_pair(g_hi, g_lo, wpt, nprod), 10) * 1e3

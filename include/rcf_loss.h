@@ -244,7 +244,11 @@ RCF_API int rcf_conv64_wgrad(const void* x_hi, const void* x_lo, const void* g_h
  * rcf_backward -> data gradient -> weight gradient -> stem backward.  Same kernels and results as the individual entry
  * points above; one call each way keeps the host cost per step (ctypes marshalling, Python glue) off the launch-bound
  * 96x96 / 48x48 training shapes.  All buffers are caller-owned device memory; feat / dfeat pointers inside `in` / `grads`
- * are filled by the library from RcfHeadBuffers (desc->feat_nhwc = 1, Cf = 64, feat_bstride = dfeat_bstride = H*W*64). */
+ * are filled by the library from RcfHeadBuffers (desc->feat_nhwc = 1, Cf = 64, feat_bstride = dfeat_bstride = H*W*64).
+ * nprod here is the head's conv-precision LEVEL: 3 = fp32-grade (bf16 (hi, lo) pairs, three products per fp32 product,
+ * 3xTF32 stem; a_lo / g_lo required), 2 = TF32-class (ONE product of IEEE fp16 operands: a_hi and the packed weights hold
+ * fp16, g_hi holds fp16(dfeat * 2^e) with e chosen on the device -- RcfDesc.dfeat_f16 --, the 2^e is divided out of dW2, dW1
+ * and db1 inside; one-product TF32 stem), 1 = plain bf16 (autocast class). */
 typedef struct RcfHeadBuffers {
     void* a_hi;            /* bf16 [ndir*B,H,W,64]: LeakyReLU(conv1(clamp(flow))), hi words                         */
     void* a_lo;            /* same shape, lo words; NULL unless nprod == 3                                          */

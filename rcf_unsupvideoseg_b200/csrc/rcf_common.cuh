@@ -204,8 +204,9 @@ __device__ __forceinline__ void rcf_pdl_prologue() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 // Power-of-two scale that brings the feature-map gradient into fp16's normal range: dG[p][f] = dact * sum_k c[f][k] M[k][p]
-// with sum_k M = 1 and |dact| <= 1, so |dG| <= max |c| =: m; s = 2^(14 - exponent(m)) puts the largest element in
-// [2^13, 2^14) (fp16 overflows at 2^16) and keeps 11 significant bits for everything down to 2^-28 of it.  Every consumer
+// with sum_k M = 1 and |dact| <= 1, so |dG| <= max |c| =: m; s = 2^(12 - exponent(m)) puts the largest element in
+// [2^11, 2^12) (fp16 overflows at 2^16: a factor 16 of headroom for masks that do not sum to one; the conversion
+// saturates beyond it) and keeps 11 significant bits for everything down to 2^-26 of it.  Every consumer
 // recomputes s from the same nfd floats, so all of them agree bit for bit; scaling by s and by 1/s is exact.
 // Call with all 32 lanes of a warp.
 __device__ __forceinline__ float rcf_grad_scale(const float* __restrict__ gmax, int nfd) {
@@ -215,7 +216,7 @@ __device__ __forceinline__ float rcf_grad_scale(const float* __restrict__ gmax, 
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (!(m > 0.0f) || !(m < 3.0e38f)) return 1.0f;          // zero / inf / nan gradient: no scaling
     int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;   // m = f * 2^e, f in [0.5, 1)  (subnormal m: e = -126, fine)
-    e = 14 - e;
+    e = 12 - e;
     e = e < -100 ? -100 : (e > 100 ? 100 : e);
     return __uint_as_float((uint32_t)(e + 127) << 23);
 }

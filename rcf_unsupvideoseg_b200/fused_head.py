@@ -3,10 +3,11 @@ flow_feat_after_agg and the relaxed-common-fate loss (reference models/flow_aggr
 :235-310, :359-368) -- as ONE autograd node over the C ABI, with no ATen / cuDNN kernel on the path:
 
   forward   rcf_head_forward  = [residual up-sampling when predicted at a lower resolution]
-                                 stem (mma.sync TF32; 3xTF32 in the fp32-grade mode) -> A1 as a bf16 (hi, lo) pair + sign bits
+                                 stem (mma.sync TF32; 3xTF32 in the fp32-grade mode) -> A1 as a bf16 (hi, lo) pair (fp32-grade),
+                                 one fp16 tensor (TF32-class, torch's default) or one bf16 tensor (autocast) + sign bits
                                  weight pack (both orientations) -> tcgen05 conv -> pre-activation feature map (fp32 channels-last)
                                  rcf_forward: pooling (+ bias, LeakyReLU), segment MLP, loss
-  backward  rcf_head_backward = rcf_backward: dM, dR, MLP gradients, conv-2 bias gradient, dfeat as a bf16 pair
+  backward  rcf_head_backward = rcf_backward: dM, dR, MLP gradients, conv-2 bias gradient, dfeat as a bf16 pair / scaled fp16 / bf16
                                  [gradient of the up-sampling] -> tcgen05 data gradient -> dA1
                                  tcgen05 weight gradient (K = pixels) -> dW2;  stem backward -> dW1, db1
 
