@@ -263,6 +263,39 @@ def test_head_at_torch_default_tf32_bounds_parameter_gradient_error(rcf):
     assert max(errs["tcgen05, fp16 operands (allow_tf32)"].values()) <= 2.0 * worst_cudnn      # the same accuracy class as cuDNN's TF32
 
 
+def test_tf32_class_mode_tracks_fp32_grade_mode_at_full_size(rcf):
+    """C1 shape (B = 2, K = 4, 480x854), default head: the torch-default conv precision (one product of fp16 operands, the
+    feature-map gradient ~1e-7 per element carried as fp16 with a device-chosen power-of-two scale) against the fp32-grade
+    mode of the same head on the same inputs.  Checks the scale logic at realistic gradient magnitudes (nothing saturates,
+    nothing underflows) and that with 410k pixels to average over the TF32-class errors are small."""
+    B, K, H, W = 2, 4, 480, 854
+    masks, fw, bw, rfw, rbw = _torch_inputs(B, K, H, W, seed=11)
+    torch.manual_seed(3)
+    head = rcf.FlowAggregationHeadWithResidual(args=None, create_flownet=True, mask_layer=K, mask_size=(H, W),
+                                               clamp_flow_t=20.0, free_residual=True).cuda()
+    head.return_flows = False
+    imgs = torch.zeros(B, 2, 3, 8, 8)
+    out = {}
+    for nprod in (3, 2):
+        head.conv_precision = nprod
+        m = masks.clone().requires_grad_(True)
+        r1, r2 = rfw.clone().requires_grad_(True), rbw.clone().requires_grad_(True)
+        for p_ in head.parameters():
+            p_.grad = None
+        _, loss = head(imgs, m, fw, bw, r1, r2)
+        loss["seg"].backward()
+        torch.cuda.synchronize()
+        out[nprod] = (float(loss["seg"]), m.grad.clone(), r1.grad.clone(), {n: p_.grad.clone() for n, p_ in head.named_parameters()})
+    ref, tst = out[3], out[2]
+    assert abs(tst[0] - ref[0]) <= 1e-4 * abs(ref[0])
+    assert rel_l2(tst[1].cpu().numpy(), ref[1].cpu().numpy()) < 2e-3          # dM (through the pooled-feature path)
+    assert rel_l2(tst[2].cpu().numpy(), ref[2].cpu().numpy()) < 1e-4          # dR does not see the conv branch beyond theta
+    for n in ref[3]:
+        assert torch.isfinite(tst[3][n]).all(), n
+        e = rel_l2(tst[3][n].cpu().numpy(), ref[3][n].cpu().numpy())
+        assert e < 5e-3, (n, e)
+
+
 def test_full_size_properties(rcf):
     """Size-independent properties at C2-like shapes: determinism, linearity in the upstream gradient,
     batch-shard consistency and direction symmetry."""
