@@ -642,7 +642,7 @@ def module_throughput(pkg, dev):
             out[f"{name}_nprod{nprod}"] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3}
     out["note"] = ("nprod = conv precision of the head: 3 fp32-grade (three bf16 products per fp32 product; "
                    "torch.backends.cudnn.allow_tf32 = False), 2 TF32-class (ONE product of fp16 operands, the feature-map gradient "
-                   "carried as scaled fp16; torch's default), 1 plain bf16 (autocast)")
+                   "carried as scaled fp16; torch's default and inside autocast), 1 plain bf16 (conv_precision = 1 only)")
     return out
 
 
@@ -771,7 +771,7 @@ def extras(pkg, dev):
         "stv2_stage1_train_B8_48x48_affine_full_head": (8, 4, 48, 48, dict(free_residual_with_affine=True, clamp_flow_t=20.0), 50),
         # the AMP configs (configs/rcf_stv2/rcf_stage1.yaml:60, configs/rcf_fbms59/rcf_stage1.yaml:61 `precision: 16`):
         # BOTH arms inside torch.autocast(fp16) -- the port runs its convs / einsums in fp16 and the solve in fp32 like
-        # the reference (:215-217); the drop-in runs the tcgen05 convs with plain bf16 operands and the loss core in fp32
+        # the reference (:215-217); the drop-in runs the tcgen05 convs with fp16 operands (level 2) and the loss core in fp32
         "amp_stv2_stage1_train_B8_48x48_affine_full_head": (8, 4, 48, 48, dict(free_residual_with_affine=True, clamp_flow_t=20.0), 50),
         "amp_fbms_K3_B2_480x854_affine_full_head": (2, 3, 480, 854, dict(free_residual_with_affine=True, clamp_flow_t=20.0), 10),
     }

@@ -18,8 +18,12 @@ A_F16, W_F16 = 0x100, 0x200                               # RCF_CONV64_A_F16 / R
 
 
 def default_nprod(autocast: bool = False) -> int:
+    """Conv-precision level of the default head from the caller's torch settings, like the reference's own convs:
+    3 (fp32-grade) when TF32 convolutions are disallowed and no autocast is active; otherwise 2 -- one product of fp16
+    operands with a scaled fp16 gradient.  Under autocast the reference runs fp16 convs with a loss scaler; level 2 is the
+    same arithmetic with the scale chosen per call on the device, and costs what plain bf16 (level 1) costs."""
     if autocast:
-        return 1
+        return 2
     return 2 if torch.backends.cudnn.allow_tf32 else 3
 
 

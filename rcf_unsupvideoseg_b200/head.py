@@ -148,9 +148,10 @@ class FlowAggregationHeadWithResidual(nn.Module):
         #   handwritten_stem=False sends the first conv + LeakyReLU through cuDNN/ATen instead of csrc/rcf_stem.cu.
         self.handwritten_stem = True
         #   tensor_core_conv=False sends the second conv through cuDNN/ATen instead of csrc/rcf_conv64*.cu (tcgen05).
-        #   conv_precision: bf16 products per fp32 product of the tcgen05 convs; None = what the reference's own convs would
-        #   do under the caller's torch settings: 3 (fp32-grade) when torch.backends.cudnn.allow_tf32 is False, 2 (weights
-        #   hi+lo, activations bf16: TF32 class) at torch's default, 1 (plain bf16) inside torch.autocast.
+        #   conv_precision: precision level of the tcgen05 convs; None = what the reference's own convs would do under the
+        #   caller's torch settings: 3 (fp32-grade: three bf16 products per fp32 product) when
+        #   torch.backends.cudnn.allow_tf32 is False and no autocast is active, otherwise 2 (TF32-class: one product of fp16
+        #   operands, scaled fp16 gradient).  1 = plain bf16 operands (same cost as 2, 8-bit significands).
         self.tensor_core_conv = True
         self.conv_precision = None
 
