@@ -216,8 +216,9 @@ RCF_API int rcf_stem_backward(const float* const* flow, const int64_t* flow_bstr
  * transpose_flip = 1 packs the operator of the DATA GRADIENT (din = conv(dout, W^T flipped)), so rcf_conv64_forward
  * computes it with the same kernel; transpose_flip = 2 packs BOTH in one launch (wpack then holds 2 x
  * RCF_CONV64_WPACK_BYTES: the forward image followed by the data-gradient image).
- * nprod: bf16 products per fp32 product: 3 = fp32-grade (hi + lo of both operands, ~1e-5), 2 = weights hi + lo,
- * activations in_hi only (TF32 class), 1 = in_hi x w_hi (autocast class).  in_lo may be NULL unless nprod == 3. */
+ * nprod (kernel mode): 3 = three bf16 products per fp32 product (hi + lo of both operands, fp32-grade ~1e-5), 2 = in_hi x
+ * [w_hi | w_lo] stacked in the MMA's N (two products), 1 = in_hi x w_hi (one product; bf16 operands, or IEEE fp16 with the
+ * format flags below = TF32-class, what rcf_head_* use at torch's default precision).  in_lo may be NULL unless nprod == 3. */
 #define RCF_CONV64_WPACK_BYTES (9 * 16384 + 2 * (9 * 8192 + 9 * 4096))   /* one-CTA image + the two CTA-pair images */
 /* Operand-format flags, OR-ed into `nprod` of rcf_conv64_forward / rcf_conv64_wgrad (nprod must then be 1) and into
  * `transpose_flip` of rcf_conv64_pack_weights: the 16-bit words are IEEE fp16 (11-bit significand) instead of bf16.

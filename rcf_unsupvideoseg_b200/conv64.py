@@ -2,10 +2,12 @@
 models/flow_aggregation_head_with_residual.py:89-91) -- on the 5th-generation tensor cores (csrc/rcf_conv64.cu,
 tcgen05.mma with bf16 operand splits, fp32 accumulation in tensor memory).  Channels-last fp32 in and out.  CUDA only.
 
-Precision follows what the reference's own convs do under the caller's torch settings:
-  * ``torch.backends.cudnn.allow_tf32 = False``  -> 3 bf16 products per fp32 product (fp32-grade, ~1e-5)
-  * torch's default (TF32 convolutions allowed)  -> 2 products: weights split hi+lo, activations rounded to bf16
-  * inside ``torch.autocast``                    -> 1 product (plain bf16 operands, fp32 accumulation)
+Kernel-level modes of these entry points (``nprod``): 3 = three bf16 products per fp32 product (fp32-grade, ~1e-5), 2 =
+activations x [W_hi | W_lo] stacked in N = 128 (two products, bf16 activations), 1 = one product; with the fp16 operand
+flags (``a_f16`` / ``w_f16`` / ``f16``, nprod = 1) the 16-bit words are IEEE fp16: one product at TF32-class accuracy.
+The drop-in head picks a precision LEVEL from the caller's torch settings (``default_nprod``) and maps it onto these modes
+inside ``rcf_head_forward`` / ``rcf_head_backward``: level 3 -> mode 3, level 2 (torch's default, autocast) -> mode 1 with
+fp16 operands and a scaled fp16 gradient, level 1 -> mode 1 with bf16 operands.
 """
 from __future__ import annotations
 
